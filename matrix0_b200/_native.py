@@ -1,0 +1,79 @@
+"""ctypes binding of the C-ABI shared library ``matrix0_b200/_lib/libmatrix0_b200.so``.
+
+The library is the product: there is no CPU or PyTorch fallback behind these entry points.  If
+the library is missing, was not built for sm_100a, or no CUDA device is visible, every compute
+call raises ``NativeLibraryError`` loudly instead of degrading to another implementation.
+Symbols are declared in ``include/matrix0_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libmatrix0_b200.so")
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
+SIGNATURES = {
+    "m0_last_error": (c_char_p, []),
+    "m0_version": (c_int, []),
+    "m0_device_count": (c_int, []),
+    "m0_device_sm_count": (c_int, [c_int]),
+    "m0_positions_pack": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "m0_random_playouts": (c_int, [c_void_p, c_int, c_uint64, c_int, c_void_p]),
+    "m0_encode_positions": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_encode_planes": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "m0_legal_mask": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "m0_legal_moves": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the shared library (no GPU needed for loading) and bind the declared signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). matrix0_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def lib() -> ctypes.CDLL:
+    """Library handle for compute calls: additionally requires a visible CUDA device."""
+    l = load_library()
+    if l.m0_device_count() <= 0:
+        raise NativeLibraryError("no CUDA device visible: matrix0_b200 runs only on a GPU (sm_100a), no CPU path exists")
+    return l
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load_library().m0_last_error()
+        raise NativeLibraryError(f"{what or 'native call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (or 0 for None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

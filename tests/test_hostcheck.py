@@ -1,0 +1,76 @@
+"""CPU pre-flight of the PRODUCT's chess core: matrix0_b200/csrc/chess_core.cuh compiled with g++
+(tests/hostcheck/hostcheck.cpp, a test harness, not a product path) against the oracle.  Lets the
+GPU-less build container catch logic errors before GPU time is spent; the real parity tests are
+the `-m gpu` ones that call the CUDA kernels through the C ABI."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import chess
+from conftest import ROOT, random_playout_boards
+from matrix0_b200.boards import board_to_raw, move_to_code
+from oracle import encoding_ref as E
+
+HC_DIR = os.path.join(ROOT, "tests", "hostcheck")
+U64P = ctypes.POINTER(ctypes.c_uint64)
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC_DIR, "_hostcheck.so")
+    src = os.path.join(HC_DIR, "hostcheck.cpp")
+    core = os.path.join(ROOT, "matrix0_b200", "csrc", "chess_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def pack(hc, b):
+    raw = board_to_raw(b)
+    out = np.zeros(9, dtype=np.uint64)
+    misc = int(raw[9])
+    ep = (misc >> 8) & 255
+    hc.hc_pack(raw.ctypes.data_as(U64P), ctypes.c_uint64(int(raw[8])), misc & 1, -1 if ep > 63 else ep,
+               (misc >> 16) & 0xFFFF, (misc >> 32) & 0xFFFF, out.ctypes.data_as(U64P))
+    return out
+
+
+def test_core_matches_oracle(hc):
+    boards = random_playout_boards(40, 160, seed=5)
+    boards += [chess.Board(f) for f in ["8/8/8/3pP3/8/8/8/8 w - d6 0 2", "8/8/8/8/k2Pp2Q/8/8/3K4 b - d3 0 1",
+                                        "4k3/8/8/8/8/8/8/R3K2R w KQkq - 0 1",
+                                        "R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - - 0 1"]]
+    keys = {}
+    for b in boards:
+        pos = pack(hc, b)
+        mv = np.zeros(256, dtype=np.uint16)
+        idx = np.zeros(256, dtype=np.int16)
+        n = hc.hc_legal_moves(pos.ctypes.data_as(U64P), mv.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)),
+                              idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+        exp = E.legal_moves_and_indices(b)
+        assert n == len(exp), b.fen()
+        assert mv[:n].tolist() == [c for c, _ in exp], b.fen()
+        assert idx[:n].tolist() == [i for _, i in exp], b.fen()
+        pl = np.zeros((19, 8, 8), dtype=np.float32)
+        hc.hc_planes(pos.ctypes.data_as(U64P), pl.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        assert pl.tobytes() == E.encode_board(b).tobytes(), b.fen()
+        assert bool(hc.hc_has_legal_ep(pos.ctypes.data_as(U64P))) == b.has_legal_en_passant()
+        assert bool(hc.hc_insufficient(pos.ctypes.data_as(U64P))) == b.is_insufficient_material()
+        legal = list(b.legal_moves)
+        for m in legal[:: max(1, len(legal) // 4)]:
+            out = np.zeros(9, dtype=np.uint64)
+            fl = (ctypes.c_int * 2)()
+            z, r = b.is_zeroing(m), b._reduces_castling_rights(m)
+            hc.hc_push(pos.ctypes.data_as(U64P), ctypes.c_uint16(move_to_code(m)), out.ctypes.data_as(U64P), fl)
+            b2 = b.copy()
+            b2.push(m)
+            assert (out == pack(hc, b2)).all(), (b.fen(), m.uci())
+            assert (bool(fl[0]), bool(fl[1])) == (z, r)
+            k = np.zeros(2, dtype=np.uint64)
+            hc.hc_key(out.ctypes.data_as(U64P), k.ctypes.data_as(U64P))
+            tk, kk = b2._transposition_key(), (int(k[0]), int(k[1]))
+            assert keys.setdefault(tk, kk) == kk
+    assert len(set(keys.values())) == len(keys)  # distinct transposition keys -> distinct hashes
