@@ -64,6 +64,52 @@ int m0_encode_planes(const uint64_t* d_pos, int n, float* d_planes, void* stream
 int m0_legal_mask(const uint64_t* d_pos, int n, uint8_t* d_mask, void* stream);
 int m0_legal_moves(const uint64_t* d_pos, int n, uint16_t* d_moves, uint16_t* d_idx, int32_t* d_counts, void* stream);
 
+/* ---- search engine: azchess/mcts.py ------------------------------------------------------------
+ * One engine per GPU holds up to max_games concurrent games as GPU-resident structure-of-arrays
+ * trees (Node, mcts.py:120-133), a per-game transposition table (MCTS.tt, :302) and the move-stack
+ * key history used for repetition detection.  One host thread drives an engine. */
+typedef struct m0_engine m0_engine;
+
+/* Device-relevant subset of MCTSConfig (mcts.py:61-117).  cpuct_by_depth[d] = MCTS._cpuct_at(d)
+ * (:927-944) evaluated by the caller for d = 0..cpuct_len-1 (deeper plies reuse the last entry).
+ * deterministic = 1 reproduces the reference with random.random() == 0.5 and noise off. */
+typedef struct m0_search_config {
+  double fpu_reduction, draw_penalty, selection_jitter, dirichlet_alpha, dirichlet_frac;
+  int deterministic;
+  int no_instant_backtrack, legal_softmax, enable_entropy_noise, value_from_white;
+  int cpuct_len;
+  unsigned long long seed;
+  const double* cpuct_by_depth; /* HOST pointer */
+} m0_search_config;
+
+int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, int max_depth, int hist_cap, m0_engine** out);
+int m0_engine_destroy(m0_engine* e);
+long long m0_engine_bytes(const m0_engine* e);
+int m0_engine_configure(m0_engine* e, const m0_search_config* cfg, void* stream); /* MCTS.__init__ (mcts.py:270-315) */
+int m0_games_reset(m0_engine* e, const int* d_games, int n, void* stream);         /* MCTS.reset (mcts.py:1477-1488) */
+/* `board` argument of MCTS.run (mcts.py:318): root positions uint64[n][9] plus, optionally, the move-stack
+ * history before each root: positions uint64[n][hist_stride][9], moves uint16[n][hist_stride], lengths int32[n]. */
+int m0_games_set_positions(m0_engine* e, const int* d_games, int n, const uint64_t* d_root_pos, const uint64_t* d_hist_pos,
+                           const uint16_t* d_hist_moves, const int32_t* d_hist_lens, int hist_stride, void* stream);
+/* MCTS.run prologue (mcts.py:336-371): d_info int32[G] bit0 = terminal root (d_value float64[G] = _terminal_value),
+ * bit1 = root needs an evaluation (its planes are written to d_planes float32[G][19][8][8]). */
+int m0_search_begin(m0_engine* e, float* d_planes, int32_t* d_info, double* d_value, void* stream);
+/* one mini-batch of batch_n simulations per game: _collect_leaf_position / _select (mcts.py:742-769, :851-925) */
+int m0_search_select(m0_engine* e, int batch_n, float* d_planes, void* stream);
+/* Node._expand + _register_children_in_tt + _backpropagate for the pending leaves (mcts.py:135-225, :1330-1346, :946-953);
+ * d_logits float32[G][logits_stride >= 4672], d_values float32[G] are the evaluator outputs (infer_np, inference.py:585). */
+int m0_search_expand_backup(m0_engine* e, const float* d_logits, int logits_stride, const float* d_values, void* stream);
+/* MCTS._add_dirichlet (mcts.py:955-992): d_noise float64[G][256] supplied by the caller, or NULL to draw
+ * Dirichlet(alpha) on the device; d_apply int32[G] gates games (NULL = all). */
+int m0_search_add_dirichlet(m0_engine* e, const double* d_noise, const int32_t* d_apply, void* stream);
+int m0_search_pending(m0_engine* e, int32_t* d_flags_out, void* stream);         /* int32[G], 0 = nothing pending */
+int m0_search_pending_counts(m0_engine* e, int32_t* d_counts_out, void* stream); /* int32[G] backups owed per pending leaf */
+/* MCTS.run results (mcts.py:431, :465, :504-507) in child (= legal move) order; d_child_q/d_prior/d_pi may be NULL */
+int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double* d_child_q, double* d_prior, int32_t* d_count,
+                     float* d_pi, double* d_root_q, int32_t* d_root_n, void* stream);
+int m0_engine_counters(m0_engine* e, unsigned long long* h_out16); /* host buffer; synchronises */
+int m0_engine_status(m0_engine* e, int32_t* d_status_out, int32_t* d_node_count_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

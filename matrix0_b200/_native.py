@@ -34,7 +34,33 @@ SIGNATURES = {
     "m0_encode_planes": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "m0_legal_mask": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "m0_legal_moves": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_engine_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "m0_engine_destroy": (c_int, [c_void_p]),
+    "m0_engine_bytes": (c_int64, [c_void_p]),
+    "m0_engine_configure": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_games_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "m0_games_set_positions": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "m0_search_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_search_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "m0_search_expand_backup": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "m0_search_add_dirichlet": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_search_pending": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_search_pending_counts": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_search_result": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_engine_counters": (c_int, [c_void_p, c_void_p]),
+    "m0_engine_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
 }
+
+
+class SearchConfigStruct(ctypes.Structure):
+    """struct m0_search_config (include/matrix0_b200.h)."""
+    _fields_ = [
+        ("fpu_reduction", c_double), ("draw_penalty", c_double), ("selection_jitter", c_double),
+        ("dirichlet_alpha", c_double), ("dirichlet_frac", c_double),
+        ("deterministic", c_int), ("no_instant_backtrack", c_int), ("legal_softmax", c_int),
+        ("enable_entropy_noise", c_int), ("value_from_white", c_int), ("cpuct_len", c_int),
+        ("seed", c_uint64), ("cpuct_by_depth", ctypes.POINTER(c_double)),
+    ]
 
 
 def load_library() -> ctypes.CDLL:

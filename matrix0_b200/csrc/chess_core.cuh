@@ -666,8 +666,10 @@ M0_HD u64 mix64(u64 x) {  // splitmix64 finaliser
 }
 // 128-bit hash of (8 bitboards, turn, clean castling rights, ep square iff a legal ep capture exists).
 // Clocks are NOT part of the key (python-chess), so positions that differ only in clocks merge.
-M0_HD Key128 position_key(const Position& p) {
-  int ep = has_legal_ep(p) ? pos_ep(p) : EP_NONE;
+M0_HD Key128 position_key(const Position& p, bool* ep_legal_out = nullptr) {
+  bool epl = has_legal_ep(p);
+  if (ep_legal_out) *ep_legal_out = epl;
+  int ep = epl ? pos_ep(p) : EP_NONE;
   u64 w[9] = {p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings, p.occ_w, p.occ_b,
               (u64)pos_turn(p) | ((u64)pos_castling(p) << 1) | ((u64)ep << 5)};
   u64 a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full;

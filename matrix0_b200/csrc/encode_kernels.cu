@@ -63,29 +63,6 @@ __global__ void random_playouts_kernel(u64* __restrict__ pos, int n, u64 seed, i
   store_position(pos + (size_t)i * POSITION_WORDS, p);
 }
 
-// ---- cooperative writers --------------------------------------------------------------------------
-// One warp writes the 19x8x8 float32 planes of one position: 304 float4 chunks, 16 per plane.
-__device__ __forceinline__ void warp_write_planes(const Position& p, float* __restrict__ out, int lane) {
-  float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll 2
-  for (int c = lane; c < 19 * 16; c += 32) {
-    int plane = c >> 4;
-    float4 v;
-    if (plane < 12) {
-      int row = (c & 15) >> 1, col0 = (c & 1) * 4;
-      u32 bits = (u32)(piece_plane_bb(p, plane) >> ((7 - row) * 8 + col0)) & 15u;
-      v.x = (bits & 1) ? 1.0f : 0.0f;
-      v.y = (bits & 2) ? 1.0f : 0.0f;
-      v.z = (bits & 4) ? 1.0f : 0.0f;
-      v.w = (bits & 8) ? 1.0f : 0.0f;
-    } else {
-      float f = const_plane_value(p, plane);
-      v = make_float4(f, f, f, f);
-    }
-    st_global_cs_f4(o4 + c, v);
-  }
-}
-
 // Fused kernel of the encode + legal-mask microbenchmark.  Any of planes / mask / moves may be null.
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_positions_kernel(const u64* __restrict__ pos, int n, float* __restrict__ planes, u8* __restrict__ mask,

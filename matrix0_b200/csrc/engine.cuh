@@ -1,0 +1,119 @@
+// Device-resident search engine state: thousands of concurrent games, each a structure-of-arrays
+// MCTS tree (one node per slot), a per-game transposition table and the position-key history
+// needed for repetition detection.  One warp owns one game in every tree kernel.
+//
+// Reference objects mirrored (azchess/mcts.py): Node (:120-133) -> the node_* arrays,
+// MCTS.tt (:302, OrderedDict key -> Node, last writer wins :1255) -> the tt_* arrays,
+// MCTSConfig (:61-117) -> SearchParams, board.move_stack/_stack -> hist_* (+ path_* while searching).
+#pragma once
+#include "m0_common.cuh"
+#include "search_math.cuh"
+
+namespace m0 {
+
+// pend_flags bits
+enum { PEND_ACTIVE = 1, PEND_EXPAND = 2, PEND_REGISTER = 4, PEND_SET_Q = 8, PEND_ROOT = 16 };
+// status bits (sticky, per game)
+enum { ST_NODE_OVERFLOW = 1, ST_TT_OVERFLOW = 2, ST_DEPTH_CAP = 4, ST_HIST_OVERFLOW = 8 };
+// counters
+enum { CTR_SIMS = 0, CTR_TERMINAL_SIMS, CTR_NN_EVALS, CTR_EXPANSIONS, CTR_TT_HOPS, CTR_CHILDREN_SCANNED,
+       CTR_PATH_NODES, CTR_CHILDREN_CREATED, CTR_GAMES_FINISHED, CTR_POSITIONS_PLAYED, CTR_COUNT = 16 };
+
+struct SearchParams {
+  double fpu_reduction;     // mcts.py:868-869
+  double draw_penalty;      // mcts.py:1227-1228
+  double jitter;            // selection_jitter, or 0.001 when configured 0 (mcts.py:893-897)
+  double dirichlet_alpha;   // mcts.py:960
+  double dirichlet_frac;    // mcts.py:961
+  int jitter_on;            // 0 = deterministic parity mode (equivalent to random.random() == 0.5)
+  int no_instant_backtrack; // mcts.py:883
+  int legal_softmax;        // mcts.py:158
+  int entropy_noise;        // mcts.py:179
+  int value_from_white;     // mcts.py:1184 (root evaluation only)
+  int cpuct_len;            // entries of the per-depth cpuct table (mcts.py:927-944)
+  unsigned long long seed;
+};
+
+struct EngineView {
+  int G, max_nodes, tt_cap, max_depth, hist_cap;
+  // game state
+  u64* root_pos;          // [G][9]
+  Key128* root_key;       // [G]
+  u8* root_ep_legal;      // [G]
+  int* root_node;         // [G]
+  u8* active;             // [G]
+  Key128* hist_key;       // [G][hist_cap]  key of the position BEFORE game ply i
+  u8* hist_irrev;         // [G][hist_cap]  Board.is_irreversible(move i) evaluated on that position
+  int* hist_len;          // [G]
+  // nodes [G][max_nodes]
+  double* node_prior;
+  double* node_w;
+  double* node_q;
+  int* node_n;
+  int* node_first;        // first child index, -1 = not expanded
+  int* node_creator;      // Node.parent (the node that created it), -1 = None
+  u32* node_mv;           // move | policy_idx << 16 ; move 0xFFFF = None
+  u16* node_nchild;
+  int* node_count;        // [G]
+  // transposition table [G][tt_cap], open addressing, (0,0) = empty
+  u64* tt_lo;
+  u64* tt_hi;
+  int* tt_val;
+  int* tt_count;          // [G]
+  // per-step scratch
+  int* path_node;         // [G][max_depth]
+  Key128* path_key;       // [G][max_depth]
+  u8* path_irrev;         // [G][max_depth]  irreversibility of the move path[d] -> path[d+1]
+  int* path_len;          // [G]
+  u64* leaf_pos;          // [G][9]
+  u16* leaf_moves;        // [G][256]
+  u16* leaf_idx;          // [G][256]
+  int* leaf_n;            // [G]
+  int* pend_node;         // [G]
+  int* pend_count;        // [G] number of backups owed to the pending leaf
+  int* pend_flags;        // [G]
+  int* status;            // [G]
+  unsigned long long* counters;  // [CTR_COUNT]
+  const SearchParams* params;
+  const double* cpuct;    // [cpuct_len]
+};
+
+static constexpr u32 MOVE_NONE = 0xFFFFu;
+
+// ---- transposition table -----------------------------------------------------------------------
+__device__ __forceinline__ int tt_get(const EngineView& E, int g, const Key128& k) {
+  const size_t base = (size_t)g * E.tt_cap;
+  u32 mask = (u32)E.tt_cap - 1;
+  u32 h = (u32)k.lo & mask;
+  for (int probe = 0; probe < E.tt_cap; ++probe) {
+    u64 lo = E.tt_lo[base + h];
+    u64 hi = E.tt_hi[base + h];
+    if (lo == 0 && hi == 0) return -1;
+    if (lo == k.lo && hi == k.hi) return E.tt_val[base + h];
+    h = (h + 1) & mask;
+  }
+  return -1;
+}
+// self.tt[key] = node : overwrite when present (last writer wins), insert otherwise
+__device__ __forceinline__ void tt_put(const EngineView& E, int g, const Key128& k, int node) {
+  const size_t base = (size_t)g * E.tt_cap;
+  u32 mask = (u32)E.tt_cap - 1;
+  u32 h = (u32)k.lo & mask;
+  for (int probe = 0; probe < E.tt_cap; ++probe) {
+    u64 lo = E.tt_lo[base + h];
+    u64 hi = E.tt_hi[base + h];
+    if (lo == k.lo && hi == k.hi) { E.tt_val[base + h] = node; return; }
+    if (lo == 0 && hi == 0) {
+      if (E.tt_count[g] >= E.tt_cap - E.tt_cap / 8) { E.status[g] |= ST_TT_OVERFLOW; return; }
+      E.tt_lo[base + h] = k.lo;
+      E.tt_hi[base + h] = k.hi;
+      E.tt_val[base + h] = node;
+      E.tt_count[g] += 1;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+  E.status[g] |= ST_TT_OVERFLOW;
+}
+
+}  // namespace m0

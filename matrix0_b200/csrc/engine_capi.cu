@@ -1,0 +1,272 @@
+// C-ABI of the search engine: creation / destruction of the device-resident game trees and the
+// launch wrappers around the warp-per-game tree kernels (tree_kernels.cu).
+#include "engine.cuh"
+#include <new>
+#include <string.h>
+#include <vector>
+
+namespace m0 {
+// kernels (tree_kernels.cu)
+__global__ void reset_games_kernel(EngineView E, const int* games, int n_games);
+__global__ void set_positions_kernel(EngineView E, const int* games, int n_games, const u64* root_pos, const u64* hist_pos,
+                                     const u16* hist_moves, const int* hist_lens, int hist_stride);
+__global__ void search_begin_kernel(EngineView E, float* planes, int* out_info, double* out_value);
+__global__ void search_select_kernel(EngineView E, int batch_n, float* planes, unsigned long long rng_step);
+__global__ void search_expand_backup_kernel(EngineView E, const float* logits, int logits_stride, const float* values);
+__global__ void search_result_kernel(EngineView E, u16* out_moves, int* out_visits, double* out_child_q, double* out_prior,
+                                     int* out_count, float* out_pi, double* out_root_q, int* out_root_n);
+__global__ void search_add_dirichlet_kernel(EngineView E, const double* noise, const int* apply, unsigned long long rng_step);
+}  // namespace m0
+
+using namespace m0;
+
+// Host-side mirror of MCTSConfig fields the device needs (include/matrix0_b200.h: m0_search_config)
+struct m0_search_config {
+  double fpu_reduction, draw_penalty, selection_jitter, dirichlet_alpha, dirichlet_frac;
+  int deterministic;  // 1 = parity mode: jitter term is exactly zero, no noise
+  int no_instant_backtrack, legal_softmax, enable_entropy_noise, value_from_white;
+  int cpuct_len;
+  unsigned long long seed;
+  const double* cpuct_by_depth;  // host pointer, cpuct_len entries (mcts.py:927-944 evaluated per depth)
+};
+
+struct m0_engine {
+  int device;
+  EngineView v;
+  std::vector<void*> allocs;
+  SearchParams* d_params;
+  double* d_cpuct;
+  int cpuct_cap;
+  unsigned long long rng_step;
+  size_t bytes;
+};
+
+static constexpr int TREE_WARPS = 4;
+
+template <typename T>
+static int dev_alloc(m0_engine* e, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  M0_CUDA_TRY(cudaMalloc(&q, bytes));
+  if (zero) M0_CUDA_TRY(cudaMemset(q, 0, bytes));
+  e->allocs.push_back(q);
+  e->bytes += bytes;
+  *p = (T*)q;
+  return M0_OK;
+}
+
+static int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+#define TRY(x)            \
+  do {                    \
+    int _r = (x);         \
+    if (_r != M0_OK) return _r; \
+  } while (0)
+
+static int engine_alloc(m0_engine* e) {
+  EngineView& v = e->v;
+  const size_t G = v.G, N = (size_t)v.G * v.max_nodes, T = (size_t)v.G * v.tt_cap, D = (size_t)v.G * v.max_depth,
+               H = (size_t)v.G * v.hist_cap;
+  TRY(dev_alloc(e, &v.root_pos, G * POSITION_WORDS));
+  TRY(dev_alloc(e, &v.root_key, G));
+  TRY(dev_alloc(e, &v.root_ep_legal, G));
+  TRY(dev_alloc(e, &v.root_node, G));
+  TRY(dev_alloc(e, &v.active, G));
+  TRY(dev_alloc(e, &v.hist_key, H));
+  TRY(dev_alloc(e, &v.hist_irrev, H));
+  TRY(dev_alloc(e, &v.hist_len, G));
+  TRY(dev_alloc(e, &v.node_prior, N, false));
+  TRY(dev_alloc(e, &v.node_w, N, false));
+  TRY(dev_alloc(e, &v.node_q, N, false));
+  TRY(dev_alloc(e, &v.node_n, N, false));
+  TRY(dev_alloc(e, &v.node_first, N, false));
+  TRY(dev_alloc(e, &v.node_creator, N, false));
+  TRY(dev_alloc(e, &v.node_mv, N, false));
+  TRY(dev_alloc(e, &v.node_nchild, N, false));
+  TRY(dev_alloc(e, &v.node_count, G));
+  TRY(dev_alloc(e, &v.tt_lo, T));
+  TRY(dev_alloc(e, &v.tt_hi, T));
+  TRY(dev_alloc(e, &v.tt_val, T, false));
+  TRY(dev_alloc(e, &v.tt_count, G));
+  TRY(dev_alloc(e, &v.path_node, D));
+  TRY(dev_alloc(e, &v.path_key, D));
+  TRY(dev_alloc(e, &v.path_irrev, D));
+  TRY(dev_alloc(e, &v.path_len, G));
+  TRY(dev_alloc(e, &v.leaf_pos, G * POSITION_WORDS));
+  TRY(dev_alloc(e, &v.leaf_moves, G * MAX_MOVES));
+  TRY(dev_alloc(e, &v.leaf_idx, G * MAX_MOVES));
+  TRY(dev_alloc(e, &v.leaf_n, G));
+  TRY(dev_alloc(e, &v.pend_node, G));
+  TRY(dev_alloc(e, &v.pend_count, G));
+  TRY(dev_alloc(e, &v.pend_flags, G));
+  TRY(dev_alloc(e, &v.status, G));
+  TRY(dev_alloc(e, &v.counters, (size_t)CTR_COUNT));
+  TRY(dev_alloc(e, &e->d_params, 1));
+  e->cpuct_cap = v.max_depth + 1;
+  TRY(dev_alloc(e, &e->d_cpuct, (size_t)e->cpuct_cap));
+  v.params = e->d_params;
+  v.cpuct = e->d_cpuct;
+  return M0_OK;
+}
+
+extern "C" {
+
+int m0_engine_destroy(m0_engine* e);
+
+// One engine per GPU (not thread-safe; one host thread drives it).
+// max_nodes: node slots per game; tt_capacity: transposition slots per game (rounded up to 2^k,
+// 0 = 2 * max_nodes); max_depth: selection path cap; hist_cap: game-history entries kept per game.
+int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, int max_depth, int hist_cap, m0_engine** out) {
+  if (!out || max_games <= 0 || max_nodes < 64 || max_depth < 8 || hist_cap < 0) {
+    m0_set_error("m0_engine_create: invalid argument");
+    return M0_ERR_ARG;
+  }
+  M0_CUDA_TRY(cudaSetDevice(device));
+  m0_engine* e = new (std::nothrow) m0_engine();
+  if (!e) { m0_set_error("m0_engine_create: out of host memory"); return M0_ERR_ARG; }
+  e->device = device;
+  e->bytes = 0;
+  e->rng_step = 0;
+  memset(&e->v, 0, sizeof(e->v));
+  e->v.G = max_games;
+  e->v.max_nodes = max_nodes;
+  e->v.tt_cap = next_pow2(tt_capacity > 0 ? tt_capacity : 2 * max_nodes);
+  e->v.max_depth = max_depth;
+  e->v.hist_cap = hist_cap > 0 ? hist_cap : 1;
+  int rc = engine_alloc(e);
+  if (rc != M0_OK) { m0_engine_destroy(e); return rc; }
+  *out = e;
+  return M0_OK;
+}
+
+int m0_engine_destroy(m0_engine* e) {
+  if (!e) return M0_OK;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+  return M0_OK;
+}
+
+long long m0_engine_bytes(const m0_engine* e) { return e ? (long long)e->bytes : 0; }
+
+int m0_engine_configure(m0_engine* e, const m0_search_config* c, void* stream) {
+  if (!e || !c || c->cpuct_len <= 0 || !c->cpuct_by_depth) { m0_set_error("m0_engine_configure: invalid argument"); return M0_ERR_ARG; }
+  M0_CUDA_TRY(cudaSetDevice(e->device));
+  SearchParams p;
+  memset(&p, 0, sizeof(p));
+  p.fpu_reduction = c->fpu_reduction;
+  p.draw_penalty = c->draw_penalty;
+  p.jitter = c->selection_jitter > 0 ? c->selection_jitter : 0.001;  // mcts.py:893-897
+  p.dirichlet_alpha = c->dirichlet_alpha;
+  p.dirichlet_frac = c->dirichlet_frac;
+  p.jitter_on = c->deterministic ? 0 : 1;
+  p.no_instant_backtrack = c->no_instant_backtrack;
+  p.legal_softmax = c->legal_softmax;
+  p.entropy_noise = c->deterministic ? 0 : c->enable_entropy_noise;
+  p.value_from_white = c->value_from_white;
+  int len = c->cpuct_len < e->cpuct_cap ? c->cpuct_len : e->cpuct_cap;
+  p.cpuct_len = len;
+  p.seed = c->seed;
+  cudaStream_t s = (cudaStream_t)stream;
+  M0_CUDA_TRY(cudaMemcpyAsync(e->d_params, &p, sizeof(p), cudaMemcpyHostToDevice, s));
+  M0_CUDA_TRY(cudaMemcpyAsync(e->d_cpuct, c->cpuct_by_depth, sizeof(double) * len, cudaMemcpyHostToDevice, s));
+  M0_CUDA_TRY(cudaStreamSynchronize(s));  // the host struct may go away after return
+  return M0_OK;
+}
+
+// MCTS.reset() (mcts.py:1477-1488) for a list of game slots (d_games == NULL: the first n slots)
+int m0_games_reset(m0_engine* e, const int* d_games, int n, void* stream) {
+  if (!e || n < 0 || n > e->v.G) { m0_set_error("m0_games_reset: invalid argument"); return M0_ERR_ARG; }
+  if (n == 0) return M0_OK;
+  int bx = (e->v.tt_cap + 1023) / 1024;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, n);
+  reset_games_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(e->v, d_games, n);
+  return m0_check_launch("m0_games_reset");
+}
+
+// Set root positions (packed uint64[n][9]) and optionally the move-stack history that precedes each
+// root (positions uint64[n][hist_stride][9], moves uint16[n][hist_stride], lengths int32[n]); replaces the
+// `board` argument of MCTS.run (mcts.py:318): board.copy() carries the move stack into the search (:558).
+int m0_games_set_positions(m0_engine* e, const int* d_games, int n, const uint64_t* d_root_pos, const uint64_t* d_hist_pos,
+                           const uint16_t* d_hist_moves, const int32_t* d_hist_lens, int hist_stride, void* stream) {
+  if (!e || n < 0 || n > e->v.G || !d_root_pos) { m0_set_error("m0_games_set_positions: invalid argument"); return M0_ERR_ARG; }
+  if (n == 0) return M0_OK;
+  set_positions_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(e->v, d_games, n, d_root_pos, d_hist_pos, d_hist_moves, d_hist_lens, hist_stride);
+  return m0_check_launch("m0_games_set_positions");
+}
+
+static inline int tree_blocks(const m0_engine* e) { return (e->v.G + TREE_WARPS - 1) / TREE_WARPS; }
+
+// MCTS.run prologue (mcts.py:336-371): d_info int32[G] (bit0 terminal root, bit1 needs evaluation),
+// d_value float64[G] terminal value; d_planes float32[G][19][8][8] receives the roots to evaluate.
+int m0_search_begin(m0_engine* e, float* d_planes, int32_t* d_info, double* d_value, void* stream) {
+  if (!e || !d_info || !d_value) { m0_set_error("m0_search_begin: invalid argument"); return M0_ERR_ARG; }
+  search_begin_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, d_planes, d_info, d_value);
+  return m0_check_launch("m0_search_begin");
+}
+
+// One mini-batch of `batch_n` simulations per game (mcts.py:535-558): selection + immediate terminal backups;
+// leaves needing the network are left pending and their planes written to d_planes[g].
+int m0_search_select(m0_engine* e, int batch_n, float* d_planes, void* stream) {
+  if (!e || batch_n <= 0) { m0_set_error("m0_search_select: invalid argument"); return M0_ERR_ARG; }
+  e->rng_step += 1;
+  search_select_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, batch_n, d_planes, e->rng_step);
+  return m0_check_launch("m0_search_select");
+}
+
+// Expansion (Node._expand, mcts.py:135-225), child registration (:1330-1346) and the owed backups
+// (:946-953) for every pending leaf; d_logits float32[G][stride], d_values float32[G].
+int m0_search_expand_backup(m0_engine* e, const float* d_logits, int logits_stride, const float* d_values, void* stream) {
+  if (!e || !d_logits || !d_values || logits_stride < POLICY_SIZE) { m0_set_error("m0_search_expand_backup: invalid argument"); return M0_ERR_ARG; }
+  search_expand_backup_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, d_logits, logits_stride, d_values);
+  return m0_check_launch("m0_search_expand_backup");
+}
+
+// Root Dirichlet noise (mcts.py:955-992).  d_noise float64[G][256] or NULL (device RNG); d_apply int32[G] or NULL (all).
+int m0_search_add_dirichlet(m0_engine* e, const double* d_noise, const int32_t* d_apply, void* stream) {
+  if (!e) { m0_set_error("m0_search_add_dirichlet: invalid argument"); return M0_ERR_ARG; }
+  e->rng_step += 1;
+  search_add_dirichlet_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, d_noise, d_apply, e->rng_step);
+  return m0_check_launch("m0_search_add_dirichlet");
+}
+
+// Pending-evaluation table of the current step: int32[G] multiplicities (0 = nothing pending)
+int m0_search_pending(m0_engine* e, int32_t* d_counts_out, void* stream) {
+  if (!e || !d_counts_out) { m0_set_error("m0_search_pending: invalid argument"); return M0_ERR_ARG; }
+  M0_CUDA_TRY(cudaMemcpyAsync(d_counts_out, e->v.pend_flags, sizeof(int) * e->v.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return M0_OK;
+}
+int m0_search_pending_counts(m0_engine* e, int32_t* d_counts_out, void* stream) {
+  if (!e || !d_counts_out) { m0_set_error("m0_search_pending_counts: invalid argument"); return M0_ERR_ARG; }
+  M0_CUDA_TRY(cudaMemcpyAsync(d_counts_out, e->v.pend_count, sizeof(int) * e->v.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return M0_OK;
+}
+
+// visit_counts / policy / root value of MCTS.run (mcts.py:431, :465, :504-507)
+int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double* d_child_q, double* d_prior, int32_t* d_count,
+                     float* d_pi, double* d_root_q, int32_t* d_root_n, void* stream) {
+  if (!e || !d_moves || !d_visits || !d_count || !d_root_q || !d_root_n) { m0_set_error("m0_search_result: invalid argument"); return M0_ERR_ARG; }
+  search_result_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, d_moves, d_visits, d_child_q, d_prior, d_count, d_pi, d_root_q, d_root_n);
+  return m0_check_launch("m0_search_result");
+}
+
+// Engine counters (uint64[16], see engine.cuh CTR_*) and sticky per-game status bits (int32[G])
+int m0_engine_counters(m0_engine* e, unsigned long long* h_out16) {
+  if (!e || !h_out16) { m0_set_error("m0_engine_counters: invalid argument"); return M0_ERR_ARG; }
+  M0_CUDA_TRY(cudaMemcpy(h_out16, e->v.counters, sizeof(unsigned long long) * CTR_COUNT, cudaMemcpyDeviceToHost));
+  return M0_OK;
+}
+int m0_engine_status(m0_engine* e, int32_t* d_status_out, int32_t* d_node_count_out, void* stream) {
+  if (!e) { m0_set_error("m0_engine_status: invalid argument"); return M0_ERR_ARG; }
+  if (d_status_out) M0_CUDA_TRY(cudaMemcpyAsync(d_status_out, e->v.status, sizeof(int) * e->v.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (d_node_count_out) M0_CUDA_TRY(cudaMemcpyAsync(d_node_count_out, e->v.node_count, sizeof(int) * e->v.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return M0_OK;
+}
+
+}  // extern "C"

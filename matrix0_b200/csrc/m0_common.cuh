@@ -48,6 +48,27 @@ __device__ __forceinline__ u64 ld_global_nc_u64(const u64* ptr) {
   asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(ptr));
   return v;
 }
+// One warp writes the 19x8x8 float32 planes of one position: 304 float4 chunks, 16 per plane.
+__device__ __forceinline__ void warp_write_planes(const Position& p, float* __restrict__ out, int lane) {
+  float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll 2
+  for (int c = lane; c < 19 * 16; c += 32) {
+    int plane = c >> 4;
+    float4 v;
+    if (plane < 12) {
+      int row = (c & 15) >> 1, col0 = (c & 1) * 4;
+      u32 bits = (u32)(piece_plane_bb(p, plane) >> ((7 - row) * 8 + col0)) & 15u;
+      v.x = (bits & 1) ? 1.0f : 0.0f;
+      v.y = (bits & 2) ? 1.0f : 0.0f;
+      v.z = (bits & 4) ? 1.0f : 0.0f;
+      v.w = (bits & 8) ? 1.0f : 0.0f;
+    } else {
+      float f = const_plane_value(p, plane);
+      v = make_float4(f, f, f, f);
+    }
+    st_global_cs_f4(o4 + c, v);
+  }
+}
 #endif
 
 }  // namespace m0

@@ -94,6 +94,124 @@ def main():
     kat = [{"fen": e["fen"], "legal_moves": e["legal_moves"], "move": e["move"]} for e in tact[112:1112]]
     json.dump(kat, open(os.path.join(HERE, "tactical_kat.json"), "w"))
     print("tactical KAT:", len(kat))
+    make_mcts_golden(mcts_mod, chess)
+
+
+MCTS_CFGS = {
+    # config.yaml mcts: section as self-play resolves it (SURVEY 8 "effective configuration"), noise off
+    "selfplay": dict(cpuct=2.5, cpuct_start=3.0, cpuct_end=2.0, cpuct_plies=40, fpu_reduction=0.1, draw_penalty=-0.05,
+                     legal_softmax=True, selection_jitter=0.05, inference_batch_size=96, no_instant_backtrack=True),
+    # MCTSConfig defaults with a small batch and full-policy softmax
+    "defaults_b8": dict(cpuct=1.7, fpu_reduction=0.15, legal_softmax=False, selection_jitter=0.0, inference_batch_size=8),
+    "cbase": dict(cpuct_c_base=19652.0, cpuct_c_init=1.25, fpu_reduction=0.2, legal_softmax=True, inference_batch_size=32,
+                  no_instant_backtrack=False, draw_penalty=-0.3),
+}
+MCTS_FENS = [
+    "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1",
+    "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1",
+    "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1",
+    "6k1/5ppp/8/8/8/8/5PPP/3R2K1 w - - 0 1",          # mate in one available: terminal leaves inside a batch
+    "7k/5Q2/6K1/8/8/8/8/8 b - - 0 1",                 # stalemate root -> terminal return
+    "8/8/8/8/8/5k2/6q1/7K w - - 0 1",                 # checkmated root
+    "4k3/8/8/8/8/8/8/4K2R w K - 148 90",              # 75-move rule two plies away
+    "8/5k2/8/8/8/8/2K5/6B1 w - - 0 1",                # insufficient material root
+]
+
+
+def make_mcts_golden(ref, chess):
+    """Visit counts of the UNMODIFIED reference MCTS.run with random.random() == 0.5, noise off."""
+    import logging
+    logging.disable(logging.CRITICAL)
+    from oracle.backends import ConstantBackend, HashBackend
+    ref.random.random = lambda: 0.5
+    ref.psutil_available = False
+
+    class _Model:
+        class cfg:
+            policy_size = 4672
+
+    def new(cfg_name, backend, sims):
+        kw = dict(MCTS_CFGS[cfg_name])
+        cfg = ref.MCTSConfig(num_threads=1, enable_memory_cleanup=False, dirichlet_frac=0.0, enable_entropy_noise=False,
+                             playout_random_frac=0.0, num_simulations=sims, **kw)
+        be = ConstantBackend(backend[1]) if backend[0] == "const" else HashBackend(scale=backend[1], seed=backend[2])
+        return ref.MCTS(cfg, _Model(), device="cpu", inference_backend=be)
+
+    def record(m, board, ply):
+        try:
+            vc, pi, v = m.run(board, ply=ply)
+        except RuntimeError as e:
+            return {"error": "zero visits" if "zero visits" in str(e) else str(e)[:80]}
+        root = m._last_root
+        out = {"visits": [[mv.uci(), n] for mv, n in vc.items()], "value": v, "pi_nonzero": [[int(i), float(pi[i])] for i in np.nonzero(pi)[0]]}
+        if root is not None:
+            out["root_n"] = root.n
+            out["child_q"] = [c.q for c in root.children.values()]
+            out["child_prior"] = [c.prior for c in root.children.values()]
+        return out
+
+    cases = []
+    rng = random.Random(7)
+    # (1) fresh MCTS per call on fixed positions
+    for cfg_name, backend, sims in [("selfplay", ("hash", 1.0, 0), 800), ("selfplay", ("hash", 0.02, 1), 800),
+                                    ("defaults_b8", ("hash", 2.0, 2), 200), ("cbase", ("hash", 1.0, 3), 300),
+                                    ("selfplay", ("const", 0.1), 800)]:
+        for fen in MCTS_FENS:
+            m = new(cfg_name, backend, sims)
+            b = chess.Board(fen)
+            cases.append({"kind": "fresh", "cfg": cfg_name, "backend": backend, "sims": sims, "fen": fen, "moves": [], "ply": 0,
+                          "expect": record(m, b, 0)})
+    # (2) fresh MCTS per move along a game (board carries its move stack -> repetition history)
+    for cfg_name, backend, sims, fen, plies in [("selfplay", ("hash", 1.0, 4), 300, MCTS_FENS[0], 10),
+                                                ("defaults_b8", ("hash", 1.5, 5), 120, MCTS_FENS[2], 12)]:
+        b = chess.Board(fen)
+        for ply in range(plies):
+            if b.is_game_over():
+                break
+            m = new(cfg_name, backend, sims)
+            exp = record(m, b, ply)
+            cases.append({"kind": "game_fresh", "cfg": cfg_name, "backend": backend, "sims": sims, "fen": fen,
+                          "moves": [mv.uci() for mv in b.move_stack], "ply": ply, "expect": exp})
+            if "visits" not in exp:
+                break
+            best = max(exp["visits"], key=lambda kv: kv[1])[0]
+            b.push(chess.Move.from_uci(best))
+    # (3) shuffling history: the root has occurred before, so repetition draws appear inside the tree
+    b = chess.Board()
+    for uci in ["g1f3", "g8f6", "f3g1", "f6g8", "g1f3", "g8f6", "f3g1", "f6g8", "g1f3", "g8f6", "f3g1"]:
+        b.push(chess.Move.from_uci(uci))
+    m = new("selfplay", ("hash", 0.5, 6), 400)
+    cases.append({"kind": "fresh", "cfg": "selfplay", "backend": ("hash", 0.5, 6), "sims": 400, "fen": MCTS_FENS[0],
+                  "moves": [mv.uci() for mv in b.move_stack], "ply": 11, "expect": record(m, b, 11)})
+    # (4) ONE persistent MCTS over consecutive plies (self-play usage, internal.py:305-408): tree reuse through the
+    #     transposition table; the reference raises "zero visits" on the second move (DESIGN.md, quirk Q12)
+    for cfg_name, backend, sims, fen in [("selfplay", ("hash", 1.0, 7), 300, MCTS_FENS[0]), ("defaults_b8", ("hash", 1.0, 8), 100, MCTS_FENS[1])]:
+        m = new(cfg_name, backend, sims)
+        b = chess.Board(fen)
+        seq = []
+        for ply in range(4):
+            exp = record(m, b, ply)
+            seq.append({"moves": [mv.uci() for mv in b.move_stack], "ply": ply, "expect": exp})
+            if "visits" not in exp:
+                break
+            b.push(chess.Move.from_uci(max(exp["visits"], key=lambda kv: kv[1])[0]))
+        cases.append({"kind": "persistent", "cfg": cfg_name, "backend": backend, "sims": sims, "fen": fen, "sequence": seq})
+    # (5) two persistent instances alternating (arena usage, arena.py:157-192): roots are found in the TT
+    for cfg_name, backend, sims, fen in [("selfplay", ("hash", 1.0, 9), 300, MCTS_FENS[0]), ("cbase", ("hash", 1.0, 10), 150, MCTS_FENS[1])]:
+        ms = [new(cfg_name, backend, sims), new(cfg_name, backend, sims)]
+        b = chess.Board(fen)
+        seq = []
+        for ply in range(10):
+            if b.is_game_over():
+                break
+            exp = record(ms[ply % 2], b, ply)
+            seq.append({"moves": [mv.uci() for mv in b.move_stack], "ply": ply, "expect": exp})
+            if "visits" not in exp:
+                break
+            b.push(chess.Move.from_uci(max(exp["visits"], key=lambda kv: kv[1])[0]))
+        cases.append({"kind": "alternating", "cfg": cfg_name, "backend": backend, "sims": sims, "fen": fen, "sequence": seq})
+    json.dump({"configs": MCTS_CFGS, "cases": cases}, open(os.path.join(HERE, "mcts_golden.json"), "w"))
+    print("mcts goldens:", len(cases), "cases")
 
 
 if __name__ == "__main__":
