@@ -110,6 +110,55 @@ int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double*
 int m0_engine_counters(m0_engine* e, unsigned long long* h_out16); /* host buffer; synchronises */
 int m0_engine_status(m0_engine* e, int32_t* d_status_out, int32_t* d_node_count_out, void* stream);
 
+/* ---- evaluator: azchess/model/resnet.py PolicyValueNet (inference forward) ------------------------------
+ * Activations are NHWC ([board][square = row*8+col][channel]) inside the library; the API keeps the
+ * reference's NCHW planes in and (B,4672)/(B,) out. */
+#define M0_MAX_BLOCKS 64
+#define M0_MAX_SSL_HEADS 8
+enum { M0_ACT_NONE = 0, M0_ACT_RELU = 1, M0_ACT_SILU = 2, M0_ACT_LEAKY = 3 };
+
+typedef struct m0_net_config { /* NetConfig, resnet.py:247-282 */
+  int planes, channels, blocks, policy_size;
+  int se, se_hidden;
+  int attention, attention_heads, attention_every_k, attention_relbias, infer_attention_stride;
+  float attention_unmasked_mix;
+  int policy_factor_rank;
+  int activation, value_activation; /* M0_ACT_* */
+  int chess_features, piece_square_tables;
+  int n_ssl_heads;
+  int ssl_out_channels[M0_MAX_SSL_HEADS];
+} m0_net_config;
+
+/* Device pointers to contiguous float32 parameters owned by the caller (state_dict tensors re-laid-out):
+ * convolution / linear weights as W[n][k], k = (ky*3+kx)*Cin + ci for 3x3 kernels; fc weights that consume a
+ * flattened NCHW feature map have their columns permuted to NHWC order (sq*channels + c). */
+typedef struct m0_block_weights {
+  const float *gn1_w, *gn1_b, *conv1_w, *gn2_w, *gn2_b, *conv2_w; /* ResidualBlock, resnet.py:27-84 */
+  const float *se_w1, *se_b1, *se_w2, *se_b2;
+  int has_attention;                                                  /* ChessAttention follows, resnet.py:87-190 */
+  const float *att_qkv_w, *att_proj_w, *att_ln_w, *att_ln_b, *att_rel_bias;
+} m0_block_weights;
+
+typedef struct m0_net_weights {
+  const float *stem_w, *stem_gn_w, *stem_gn_b;                        /* resnet.py:314-318 */
+  const float *pos_enc, *pst_w, *pst_gn_w, *pst_gn_b, *inter_w, *inter_gn_w, *inter_gn_b; /* ChessSpecificFeatures :197-244 */
+  m0_block_weights blocks[M0_MAX_BLOCKS];
+  const float *pol_conv_w, *pol_gn_w, *pol_gn_b, *pol_fc1_w, *pol_fc1_b, *pol_fc2_w, *pol_fc2_b; /* :447-452, :483-491 */
+  float policy_logit_scale;                                           /* clamp(softplus(raw)+1e-3, max 5), :709-710 */
+  const float *val_conv1_w, *val_gn1_w, *val_gn1_b, *val_conv2_w, *val_gn2_w, *val_gn2_b;         /* :494-502 */
+  const float *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b, *val_gate_w, *val_gate_b, *val_fc3_w, *val_fc3_b; /* :503-509 */
+  const float *ssl_conv1_w[M0_MAX_SSL_HEADS], *ssl_gn_w[M0_MAX_SSL_HEADS], *ssl_gn_b[M0_MAX_SSL_HEADS], *ssl_conv2_w[M0_MAX_SSL_HEADS];
+} m0_net_weights;
+
+typedef struct m0_net m0_net;
+int m0_net_create(int device, const m0_net_config* cfg, const m0_net_weights* weights, m0_net** out);
+int m0_net_destroy(m0_net* net);
+/* PolicyValueNet.forward (resnet.py:755-760): d_planes float32[B][planes][8][8] -> d_logits float32[B][4672], d_values
+ * float32[B].  precision 0 = fp32 SIMT kernels, 1 = bf16 tcgen05 tensor-core pipeline. */
+int m0_net_forward(m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, int precision, void* stream);
+/* forward(x, return_ssl=True) (resnet.py:736-745): d_ssl_out[h] float32[B][k_h][8][8] for each SSL head (fp32 path) */
+int m0_net_forward_ssl(m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, float* const* d_ssl_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ SIGNATURES = {
     "m0_search_result": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_engine_counters": (c_int, [c_void_p, c_void_p]),
     "m0_engine_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_net_create": (c_int, [c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
+    "m0_net_destroy": (c_int, [c_void_p]),
+    "m0_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "m0_net_forward_ssl": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

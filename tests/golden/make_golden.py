@@ -95,6 +95,61 @@ def main():
     json.dump(kat, open(os.path.join(HERE, "tactical_kat.json"), "w"))
     print("tactical KAT:", len(kat))
     make_mcts_golden(mcts_mod, chess)
+    make_nn_golden()
+
+
+NN_CASES = {
+    # name -> overrides of config.yaml's model: section (SURVEY headline fact 3: R24 = 320 / 24 / 20)
+    "small": dict(channels=64, blocks=6, attention_heads=4, policy_factor_rank=32),
+    "r24": dict(channels=320, blocks=24, attention_heads=20),
+}
+
+
+def nn_inputs(n, seed):
+    """Real encoded positions (binary planes) from seeded random playouts."""
+    import chess
+    from oracle.encoding_ref import encode_board
+    rng = random.Random(seed)
+    out = []
+    while len(out) < n:
+        b = chess.Board()
+        for _ in range(rng.randint(0, 100)):
+            if b.is_game_over():
+                break
+            b.push(rng.choice(list(b.legal_moves)))
+        out.append(encode_board(b))
+    return np.stack(out)
+
+
+def make_nn_golden():
+    """Outputs of the UNMODIFIED reference PolicyValueNet (fp32: infer_amp_tower off) on deterministic weights."""
+    import torch
+    import yaml
+    from oracle import nn_ref
+    from matrix0_b200.model import NetConfig, parameter_shapes
+    resnet = refload.load_reference("model.resnet")
+    base = yaml.safe_load(open(os.path.join(refload.REFERENCE_ROOT, "config.yaml")))["model"]
+    out = {}
+    for name, over in NN_CASES.items():
+        d = dict(base)
+        d.update(over)
+        d["infer_amp_tower"] = False
+        ref = resnet.PolicyValueNet.from_config(d).eval()
+        known = set(NetConfig.__dataclass_fields__)
+        cfg = NetConfig(**{k: v for k, v in d.items() if k in known})
+        sd = nn_ref.make_state_dict(parameter_shapes(cfg), seed=1)
+        ref.load_state_dict(sd, strict=False)
+        x = torch.from_numpy(nn_inputs(6, seed=5))
+        with torch.no_grad():
+            p, v, ssl = ref(x, return_ssl=True)
+        out[f"{name}_x"] = x.numpy()
+        out[f"{name}_logits"] = p.numpy()
+        out[f"{name}_values"] = v.numpy()
+        for t, s in ssl.items():
+            out[f"{name}_ssl_{t}"] = s.numpy()
+        out[f"{name}_cfg"] = np.array(json.dumps(d))
+    np.savez_compressed(os.path.join(HERE, "nn_golden.npz"), **out)
+    print("nn goldens:", list(NN_CASES))
 
 
 MCTS_CFGS = {

@@ -1,0 +1,73 @@
+"""GPU parity of the evaluator (CUDA kernels through m0_net_forward) against the fp32 oracle and the
+committed reference outputs.  Bars from BASELINE north_star: fp32 path within 1e-4 relative; bf16 path
+>= 99 % top-1 policy agreement and |delta value| <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_ref
+from test_oracle_nn import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def make_net(cfg, sd, precision):
+    from matrix0_b200.model import PolicyValueNet
+    net = PolicyValueNet(cfg, device="cuda", precision=precision)
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return net
+
+
+def rel_close(got, ref, tol):
+    scale = float(np.abs(ref).max())
+    return float(np.abs(got - ref).max()) <= tol * max(scale, 1e-6), float(np.abs(got - ref).max()), scale
+
+
+@pytest.mark.parametrize("name", ["small", "r24"])
+def test_fp32_path_vs_reference_golden(golden_dir, name):
+    g, cfg, sd = load_case(golden_dir, name)
+    net = make_net(cfg, sd, "fp32")
+    x = torch.from_numpy(g[f"{name}_x"]).cuda()
+    p, v, ssl = net.forward(x, return_ssl=True)
+    ok, err, scale = rel_close(p.cpu().numpy(), g[f"{name}_logits"], 1e-4)
+    assert ok, (err, scale)
+    ok, err, scale = rel_close(v.cpu().numpy(), g[f"{name}_values"], 1e-4)
+    assert ok, (err, scale)
+    for t, s in ssl.items():
+        ok, err, scale = rel_close(s.cpu().numpy(), g[f"{name}_ssl_{t}"], 1e-4)
+        assert ok, (t, err, scale)
+
+
+def test_fp32_batch_invariance_and_api(golden_dir):
+    g, cfg, sd = load_case(golden_dir, "small")
+    net = make_net(cfg, sd, "fp32")
+    x = torch.rand(37, 19, 8, 8, generator=torch.Generator().manual_seed(1))
+    p, v = net.forward(x)
+    assert p.shape == (37, 4672) and v.shape == (37,) and p.dtype == torch.float32
+    with torch.no_grad():
+        pr, vr = nn_ref.forward(sd, cfg, x)
+    assert rel_close(p.cpu().numpy(), pr.numpy(), 1e-4)[0] and rel_close(v.cpu().numpy(), vr.numpy(), 1e-4)[0]
+    p1, v1 = net.forward(x[5:6])
+    assert torch.equal(p1[0], p[5]) and torch.equal(v1[0], v[5])      # rows are evaluated independently
+    pn, vn = net.infer_np(x[:3].numpy())                               # inference-backend seam
+    assert pn.shape == (3, 4672) and vn.shape == (3,)
+    assert net.count_parameters() == sum(t.numel() for t in sd.values())
+    assert net.forward(x[:0])[0].shape == (0, 4672)                    # empty batch
+
+
+@pytest.mark.parametrize("name", ["small", "r24"])
+def test_bf16_path_agreement(golden_dir, name):
+    g, cfg, sd = load_case(golden_dir, name)
+    net = make_net(cfg, sd, "bf16")
+    from conftest import random_playout_boards
+    from oracle.encoding_ref import encode_board
+    boards = random_playout_boards(8, 120, seed=31)[:: 3][:192]
+    x = torch.from_numpy(np.stack([encode_board(b) for b in boards]))
+    p, v = net.forward(x)
+    f32 = make_net(cfg, sd, "fp32")
+    pr, vr = f32.forward(x)                                            # fp32 CUDA path == reference within 1e-4 (test above)
+    top1 = (p.argmax(1) == pr.argmax(1)).float().mean().item()
+    dv = (v - vr).abs().max().item()
+    assert top1 >= 0.99, top1
+    assert dv <= 2e-2, dv
