@@ -38,6 +38,7 @@ const char* m0_last_error(void);
 int m0_version(void);
 int m0_device_count(void);            /* <= 0: the product cannot run (no CPU path) */
 int m0_device_sm_count(int device);
+unsigned long long m0_launch_count(void); /* kernel launches issued by the library so far */
 
 /* ---- positions ------------------------------------------------------------------------------
  * Raw record per position (uint64[10]), the public fields of python-chess's chess.Board that the
@@ -98,6 +99,8 @@ int m0_search_begin(m0_engine* e, float* d_planes, int32_t* d_info, double* d_va
 int m0_search_select(m0_engine* e, int batch_n, float* d_planes, void* stream);
 /* Node._expand + _register_children_in_tt + _backpropagate for the pending leaves (mcts.py:135-225, :1330-1346, :946-953);
  * d_logits float32[G][logits_stride >= 4672], d_values float32[G] are the evaluator outputs (infer_np, inference.py:585). */
+/* the same with per-game simulation budgets d_sims_left int32[G] (playout-cap randomisation, mcts.py:380-385) */
+int m0_search_select_var(m0_engine* e, int batch_cap, int32_t* d_sims_left, float* d_planes, void* stream);
 int m0_search_expand_backup(m0_engine* e, const float* d_logits, int logits_stride, const float* d_values, void* stream);
 /* MCTS._add_dirichlet (mcts.py:955-992): d_noise float64[G][256] supplied by the caller, or NULL to draw
  * Dirichlet(alpha) on the device; d_apply int32[G] gates games (NULL = all). */
@@ -109,6 +112,25 @@ int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double*
                      float* d_pi, double* d_root_q, int32_t* d_root_n, void* stream);
 int m0_engine_counters(m0_engine* e, unsigned long long* h_out16); /* host buffer; synchronises */
 int m0_engine_status(m0_engine* e, int32_t* d_status_out, int32_t* d_node_count_out, void* stream);
+
+/* ---- self-play game loop: azchess/selfplay/internal.py:326-600 for all game slots of an engine -------------- */
+typedef struct m0_selfplay_config { /* selfplay: section of the reference config, internal.py:347-381 */
+  double temperature_start, temperature_end, resign_threshold, resign_min_entropy, resign_value_margin;
+  int temperature_moves, max_game_len, min_resign_plies, resign_window, resign_consecutive_bad, opening_random_plies;
+  unsigned long long seed;
+} m0_selfplay_config;
+typedef struct m0_finished_game {
+  int game, plies; /* slot, len(states) */
+  float z;         /* result from White's point of view (internal.py:587-599) */
+  int reason;      /* 1 checkmate 2 stalemate 3 insufficient material 4 fifty-move claim 5 repetition claim 6 max_game_len 7 resignation */
+  float avg_entropy;
+} m0_finished_game;
+int m0_selfplay_configure(m0_engine* e, const m0_selfplay_config* cfg, void* stream);
+int m0_selfplay_start(m0_engine* e, void* stream);                      /* new game in every slot, internal.py:326-379 */
+int m0_selfplay_advance(m0_engine* e, uint16_t* d_out_move, void* stream); /* one ply: sample, resign, push, finish/restart */
+int m0_selfplay_plies(m0_engine* e, int32_t* d_out, void* stream);        /* len(states) per slot, int32[G] */
+int m0_trees_clear(m0_engine* e, void* stream);                         /* fresh MCTS per move (keeps positions + histories) */
+int m0_selfplay_finished(m0_engine* e, m0_finished_game* h_out, int max_records, int* n_out, void* stream); /* host buffer; syncs */
 
 /* ---- evaluator: azchess/model/resnet.py PolicyValueNet (inference forward) ------------------------------
  * Activations are NHWC ([board][square = row*8+col][channel]) inside the library; the API keeps the

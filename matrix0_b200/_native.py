@@ -28,6 +28,7 @@ SIGNATURES = {
     "m0_version": (c_int, []),
     "m0_device_count": (c_int, []),
     "m0_device_sm_count": (c_int, [c_int]),
+    "m0_launch_count": (c_uint64, []),
     "m0_positions_pack": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "m0_random_playouts": (c_int, [c_void_p, c_int, c_uint64, c_int, c_void_p]),
     "m0_encode_positions": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -49,6 +50,13 @@ SIGNATURES = {
     "m0_search_result": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_engine_counters": (c_int, [c_void_p, c_void_p]),
     "m0_engine_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_search_select_var": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "m0_selfplay_plies": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_selfplay_configure": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_selfplay_start": (c_int, [c_void_p, c_void_p]),
+    "m0_selfplay_advance": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_trees_clear": (c_int, [c_void_p, c_void_p]),
+    "m0_selfplay_finished": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p]),
     "m0_net_create": (c_int, [c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     "m0_net_destroy": (c_int, [c_void_p]),
     "m0_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),

@@ -1,0 +1,229 @@
+"""bench.py workload "selfplay" (BASELINE configs[3] / [4]): batched self-play, G concurrent games x
+`sims` simulations per move, ResNet-24 (320 channels, 24 blocks, 20 heads), one process per GPU.
+
+A step = one search step over all games of the rank: select -> encode -> NN forward -> expand -> backup
+(the first step of a move is the MCTS.run prologue: root evaluation + expansion; the last one is followed by
+the move sampling / push kernel).  Reported separately, as SURVEY 8d demands: sims/s (reference accounting:
+one evaluated leaf stands for up to inference_batch_size simulations), unique NN evaluations/s and
+self-play positions/s.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+FLOP_PER_POSITION = 6.068e9  # SURVEY 6 [measured with FlopCounterMode]: conv 6020 + addmm 16 + bmm 31 MFLOP
+
+
+def reference_cfg(sims: int):
+    """config.yaml of the reference (mcts: / selfplay: / model: sections) with the BASELINE overrides:
+    ResNet-24 = 320 channels / 24 blocks / 20 heads, num_simulations = sims."""
+    model = dict(planes=19, channels=320, blocks=24, attention=True, attention_heads=20, policy_size=4672, norm="group", activation="silu",
+                 value_activation="leaky_relu", preact=True, droppath=0.0, policy_factor_rank=160, infer_attention_stride=2,
+                 infer_amp_tower=True, aux_policy_from_square=True, aux_policy_move_type=True, ssl_curriculum=True, self_supervised=True,
+                 ssl_tasks=["piece", "threat", "pin", "fork", "control"])
+    selfplay = dict(max_game_len=200, min_resign_plies=50, resign_threshold=-0.85, opening_random_plies=12, num_simulations=sims,
+                    temperature_start=1.2, temperature_end=0.3, temperature_moves=40)
+    mcts = dict(num_threads=4, num_simulations=sims, cpuct=2.5, cpuct_start=3.0, cpuct_end=2.0, cpuct_plies=40, dirichlet_alpha=0.3,
+                dirichlet_frac=0.25, dirichlet_plies=30, selection_jitter=0.05, fpu=0.6, fpu_reduction=0.1, draw_penalty=-0.05,
+                tt_capacity=1500000, tt_cleanup_frequency=5000, encoder_cache=True, legal_softmax=True, max_children=0, min_child_prior=0.0,
+                no_instant_backtrack=True, parent_q_init=True, tt_cleanup_interval_s=5, value_from_white=False, virtual_loss=1.0,
+                enable_memory_cleanup=True, inference_batch_size=96, parallel_simulations=True, tree_parallelism=True,
+                memory_cleanup_threshold_mb=512, max_tree_nodes=100000, playout_random_frac=0.05, enable_entropy_noise=True)
+    return {"model": model, "selfplay": selfplay, "mcts": mcts}
+
+
+def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ranks):
+    import numpy as np
+    import torch
+    from matrix0_b200 import _native
+    from matrix0_b200.model import PolicyValueNet
+    from matrix0_b200.selfplay import SelfPlayEngine
+    lib = _native.lib()
+    precision = os.environ.get("M0_BENCH_PRECISION", args.precision if hasattr(args, "precision") else "bf16")
+    G = args.games
+    cfg = reference_cfg(args.sims)
+    net = PolicyValueNet.from_config(cfg["model"], device=f"cuda:{local}", precision=precision, seed=0)
+    if world > 1:  # identical weights everywhere: one NCCL broadcast of every parameter from rank 0
+        import torch.distributed as dist
+        for t in net._params.values():
+            dist.broadcast(t, src=0)
+    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=1234 + 7919 * rank, precision=precision, max_nodes=4096)
+    stream = torch.cuda.current_stream()
+    sp.start()
+    per_move = 1 + sp.batches_per_move()
+
+    class Cycle:
+        i = 0
+
+    def step():
+        k = Cycle.i % per_move
+        if k == 0:
+            sp.begin_move()
+        else:
+            sp.search_step()
+        if k == per_move - 1:
+            sp.end_move()
+        Cycle.i += 1
+
+    # warm-up: one full move (buffers, workspaces) + the requested number of steps
+    for _ in range(per_move + args.warmup):
+        step()
+    while Cycle.i % per_move:
+        step()
+    torch.cuda.synchronize()
+    c0 = sp.counters()
+    l0 = int(lib.m0_launch_count())
+    sampler = ClockSampler(local)
+    barrier(world)
+    sampler.start()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        step()
+    t1.record(stream)
+    barrier(world)
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(t0.elapsed_time(t1), world)
+    c1 = sp.counters()
+    launches = int(lib.m0_launch_count()) - l0
+    d = {k: c1[k] - c0[k] for k in c1}
+    nn_rows = args.steps * G
+
+    def allsum(x):
+        if world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+    sims_all = allsum(d["sims"])
+    pos_all = allsum(d["positions_played"])
+    evals_all = allsum(d["nn_evals"] + G * (args.steps // per_move + (1 if args.steps % per_move else 0)))
+    secs = total_ms * 1e-3
+
+    # dominant kernels in isolation: the NN forward over one step's batch, CUDA events on the launching stream
+    planes = sp.engine.planes
+    for _ in range(2):
+        net.forward_planes(planes, precision)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+    for a, b in ev:
+        a.record(stream)
+        net.forward_planes(planes, precision)
+        b.record(stream)
+    torch.cuda.synchronize()
+    nn_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    peaks = load_peaks()
+    achieved = FLOP_PER_POSITION * G / (nn_ms * 1e-3) / 1e12
+
+    # end to end with HOST buffers: root positions come from pinned host memory every move and the search
+    # results (moves, visit counts, pi, root value) go back to pinned host memory
+    eng = sp.engine
+    root_host = torch.empty((G, 9), dtype=torch.int64).pin_memory()
+    root_host.copy_(torch.from_numpy(np.zeros((G, 9), dtype=np.int64)))
+    pos_dev = torch.empty((G, 9), dtype=torch.int64, device="cuda")
+    _native.check(lib.m0_random_playouts(pos_dev.data_ptr(), G, 99 + rank, 60, stream.cuda_stream))
+    root_host.copy_(pos_dev)
+    h_moves = torch.empty((G, 256), dtype=torch.int16).pin_memory()
+    h_visits = torch.empty((G, 256), dtype=torch.int32).pin_memory()
+    h_pi = torch.empty((G, 4672), dtype=torch.float32).pin_memory()
+    h_q = torch.empty((G,), dtype=torch.float64).pin_memory()
+
+    def e2e_move():
+        pos_dev.copy_(root_host, non_blocking=True)
+        eng.set_positions_packed(pos_dev)
+        sp.begin_move()
+        for _ in range(per_move - 1):
+            sp.search_step()
+        eng.result(with_pi=True)
+        h_moves.copy_(eng.res_moves, non_blocking=True)
+        h_visits.copy_(eng.res_visits, non_blocking=True)
+        h_pi.copy_(eng.res_pi, non_blocking=True)
+        h_q.copy_(eng.res_root_q, non_blocking=True)
+        stream.synchronize()
+
+    e2e_move()
+    ce0 = sp.counters()
+    barrier(world)
+    te = time.perf_counter()
+    n_e2e = max(1, min(2, args.steps // per_move))
+    for _ in range(n_e2e):
+        e2e_move()
+    barrier(world)
+    e2e_s = max_over_ranks((time.perf_counter() - te) * 1e3, world) * 1e-3
+    ce1 = sp.counters()
+    e2e_sims = allsum(ce1["sims"] - ce0["sims"])
+
+    out = {
+        "metric": "MCTS sims/sec, batched self-play, ResNet-24 (BASELINE configs[3])", "value": sims_all / secs, "unit": "sims/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+        "config": {"workload": f"batched self-play: {G} concurrent games/GPU x {args.sims} sims/move, ResNet-24 320ch/24 blocks/20 heads {precision}, random init",
+                   "games_per_gpu": G, "sims_per_move": args.sims, "inference_batch_size": 96, "steps_per_move": per_move,
+                   "mode": "reference-exact accounting (one evaluated leaf per game and mini-batch, SURVEY Q1), fresh tree per move",
+                   "openings": "start position + 12 random plies (device RNG)", "l2": "per-step activations (>1 GB) exceed the 126 MB L2"},
+        "positions_per_s": pos_all / secs, "unique_nn_evals_per_s": allsum(nn_rows) / secs, "pending_leaf_evals_per_s": evals_all / secs,
+        "clocks": clocks,
+        "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": int(G * 72 / per_move),
+                "d2h_bytes_per_step": int(G * (4672 * 4 + 256 * 6 + 8) / per_move), "moves_timed": n_e2e},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                     "kernel": "m0_net_forward (3x3 implicit-GEMM convolutions = 93% of the FLOPs)", "algorithmic_flops_per_launch": FLOP_PER_POSITION * G,
+                     "kernel_ms": nn_ms, "share_of_step": nn_ms / (total_ms / args.steps)},
+        "tree": {"children_scanned": d["children_scanned"], "path_nodes": d["path_nodes"], "children_created": d["children_created"],
+                 "terminal_sims": d["terminal_sims"], "tt_hops": d["tt_hops"],
+                 "algorithmic_bytes": 24 * d["children_scanned"] + 24 * d["path_nodes"] + 44 * d["children_created"]},
+    }
+    if rank == 0:
+        out["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
+    return out
+
+
+def cpu_baseline(sims: int, budget_s: float, moves_cap: int = 1):
+    """The reference's CPU self-play path restated (oracle port): RefMCTS on the oracle chess shim + the fp32 torch
+    restatement of ResNet-24 on all host cores, one game from the start position, fresh MCTS per move."""
+    import torch
+    from oracle import chess_shim  # noqa: F401
+    import chess
+    from oracle import nn_ref
+    from oracle.mcts_ref import RefConfig, RefMCTS
+    from matrix0_b200.model import NetConfig, parameter_shapes
+    cfg = reference_cfg(sims)
+    known = set(NetConfig.__dataclass_fields__)
+    ncfg = NetConfig(**{k: v for k, v in cfg["model"].items() if k in known})
+    sd = nn_ref.make_state_dict(parameter_shapes(ncfg), seed=1)
+    net = nn_ref.OracleNet(ncfg, sd)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = {k: v for k, v in cfg["mcts"].items()}
+    b = chess.Board()
+    t0 = time.perf_counter()
+    done_sims = moves = 0
+    evals = 0
+    while moves < moves_cap or time.perf_counter() - t0 < budget_s * 0.5:
+        mc = RefMCTS(RefConfig(**{**m, "dirichlet_frac": 0.0, "enable_entropy_noise": False, "playout_random_frac": 0.0}), net, jitter_value=None)
+        vc, pi, v = mc.run(b, ply=moves)
+        done_sims += sims
+        evals += mc.unique_evals
+        moves += 1
+        b.push(max(vc.items(), key=lambda kv: kv[1])[0])
+        if b.is_game_over() or time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done_sims / dt, "unit": "sims/s", "cores": cores, "kind": "port",
+            "sample": f"{moves} move(s) x {sims} sims of one game from the start position in {dt:.1f}s ({evals} NN calls of <=96 rows, fp32 torch CPU); "
+                      f"positions/s = {moves / dt:.4f}",
+            "positions_per_s": moves / dt}
+
+
+def reference_arm(args):
+    base = cpu_baseline(args.sims, max(20.0, args.cpu_seconds * 2), moves_cap=2)
+    return {"impl": "reference", "metric": "MCTS sims/sec, batched self-play, ResNet-24 (BASELINE configs[3])", "value": base["value"],
+            "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"self-play, ResNet-24 fp32 on host cores, {args.sims} sims/move, single game (the reference's CPU path)"},
+            "positions_per_s": base["positions_per_s"], "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -17,13 +17,21 @@ int m0_check_cuda(cudaError_t e, const char* what) {
   return M0_ERR_CUDA;
 }
 
-int m0_check_launch(const char* what) { return m0_check_cuda(cudaGetLastError(), what); }
+static unsigned long long g_launches = 0;
+
+int m0_check_launch(const char* what) {
+  g_launches++;
+  return m0_check_cuda(cudaGetLastError(), what);
+}
 
 extern "C" {
 
 const char* m0_last_error(void) { return g_err; }
 
 int m0_version(void) { return 100; }
+
+// Number of kernel launches issued by this library so far (bench.py reports the per-step count).
+unsigned long long m0_launch_count(void) { return g_launches; }
 
 // Number of CUDA devices visible to the library (<= 0 means the product cannot run: there is no
 // CPU path behind this ABI).

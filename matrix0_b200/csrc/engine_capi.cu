@@ -3,7 +3,6 @@
 #include "engine.cuh"
 #include <new>
 #include <string.h>
-#include <vector>
 
 namespace m0 {
 // kernels (tree_kernels.cu)
@@ -11,7 +10,7 @@ __global__ void reset_games_kernel(EngineView E, const int* games, int n_games);
 __global__ void set_positions_kernel(EngineView E, const int* games, int n_games, const u64* root_pos, const u64* hist_pos,
                                      const u16* hist_moves, const int* hist_lens, int hist_stride);
 __global__ void search_begin_kernel(EngineView E, float* planes, int* out_info, double* out_value);
-__global__ void search_select_kernel(EngineView E, int batch_n, float* planes, unsigned long long rng_step);
+__global__ void search_select_kernel(EngineView E, int batch_cap, int* sims_left, float* planes, unsigned long long rng_step);
 __global__ void search_expand_backup_kernel(EngineView E, const float* logits, int logits_stride, const float* values);
 __global__ void search_result_kernel(EngineView E, u16* out_moves, int* out_visits, double* out_child_q, double* out_prior,
                                      int* out_count, float* out_pi, double* out_root_q, int* out_root_n);
@@ -20,47 +19,7 @@ __global__ void search_add_dirichlet_kernel(EngineView E, const double* noise, c
 
 using namespace m0;
 
-// Host-side mirror of MCTSConfig fields the device needs (include/matrix0_b200.h: m0_search_config)
-struct m0_search_config {
-  double fpu_reduction, draw_penalty, selection_jitter, dirichlet_alpha, dirichlet_frac;
-  int deterministic;  // 1 = parity mode: jitter term is exactly zero, no noise
-  int no_instant_backtrack, legal_softmax, enable_entropy_noise, value_from_white;
-  int cpuct_len;
-  unsigned long long seed;
-  const double* cpuct_by_depth;  // host pointer, cpuct_len entries (mcts.py:927-944 evaluated per depth)
-};
-
-struct m0_engine {
-  int device;
-  EngineView v;
-  std::vector<void*> allocs;
-  SearchParams* d_params;
-  double* d_cpuct;
-  int cpuct_cap;
-  unsigned long long rng_step;
-  size_t bytes;
-};
-
-static constexpr int TREE_WARPS = 4;
-
-template <typename T>
-static int dev_alloc(m0_engine* e, T** p, size_t count, bool zero = true) {
-  void* q = nullptr;
-  size_t bytes = count * sizeof(T);
-  if (bytes == 0) bytes = sizeof(T);
-  M0_CUDA_TRY(cudaMalloc(&q, bytes));
-  if (zero) M0_CUDA_TRY(cudaMemset(q, 0, bytes));
-  e->allocs.push_back(q);
-  e->bytes += bytes;
-  *p = (T*)q;
-  return M0_OK;
-}
-
-static int next_pow2(int x) {
-  int p = 1;
-  while (p < x) p <<= 1;
-  return p;
-}
+#include "engine_host.cuh"
 
 #define TRY(x)            \
   do {                    \
@@ -133,6 +92,10 @@ int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, 
   e->bytes = 0;
   e->rng_step = 0;
   memset(&e->v, 0, sizeof(e->v));
+  memset(&e->sp, 0, sizeof(e->sp));
+  e->d_sp_params = nullptr;
+  e->sp_step = 0;
+  e->finished_read = 0;
   e->v.G = max_games;
   e->v.max_nodes = max_nodes;
   e->v.tt_cap = next_pow2(tt_capacity > 0 ? tt_capacity : 2 * max_nodes);
@@ -216,8 +179,17 @@ int m0_search_begin(m0_engine* e, float* d_planes, int32_t* d_info, double* d_va
 int m0_search_select(m0_engine* e, int batch_n, float* d_planes, void* stream) {
   if (!e || batch_n <= 0) { m0_set_error("m0_search_select: invalid argument"); return M0_ERR_ARG; }
   e->rng_step += 1;
-  search_select_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, batch_n, d_planes, e->rng_step);
+  search_select_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, batch_n, nullptr, d_planes, e->rng_step);
   return m0_check_launch("m0_search_select");
+}
+
+// Same with a per-game simulation budget: game g runs min(batch_cap, d_sims_left[g]) simulations and its budget is
+// decremented (playout-cap randomisation gives every MCTS.run its own count, mcts.py:380-385).
+int m0_search_select_var(m0_engine* e, int batch_cap, int32_t* d_sims_left, float* d_planes, void* stream) {
+  if (!e || batch_cap <= 0 || !d_sims_left) { m0_set_error("m0_search_select_var: invalid argument"); return M0_ERR_ARG; }
+  e->rng_step += 1;
+  search_select_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, batch_cap, d_sims_left, d_planes, e->rng_step);
+  return m0_check_launch("m0_search_select_var");
 }
 
 // Expansion (Node._expand, mcts.py:135-225), child registration (:1330-1346) and the owed backups

@@ -235,7 +235,7 @@ search_begin_kernel(EngineView E, float* __restrict__ planes, int* __restrict__ 
 // (remaining simulations of the batch), which is exactly what the reference's collected batch
 // contains when nothing can change between its selections.
 __global__ void __launch_bounds__(TREE_THREADS)
-search_select_kernel(EngineView E, int batch_n, float* __restrict__ planes, unsigned long long rng_step) {
+search_select_kernel(EngineView E, int batch_cap, int* __restrict__ sims_left, float* __restrict__ planes, unsigned long long rng_step) {
   __shared__ u16 s_moves[TREE_WARPS][MAX_MOVES];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * TREE_WARPS + wib;
@@ -254,6 +254,13 @@ search_select_kernel(EngineView E, int batch_n, float* __restrict__ planes, unsi
   const bool root_epl = E.root_ep_legal[g] != 0;
   unsigned long long c_scanned = 0, c_path = 0, c_term = 0, c_hops = 0;
 
+  int batch_n = batch_cap;
+  if (sims_left) {  // per-game simulation budgets (playout cap randomisation, mcts.py:380-385)
+    int left = sims_left[g];
+    batch_n = left < batch_cap ? left : batch_cap;
+    __syncwarp();
+    if (lane == 0) sims_left[g] = left - batch_n;
+  }
   int remaining = batch_n;
   int pend_m = 0;
   while (remaining > 0) {

@@ -211,6 +211,8 @@ class PolicyValueNet:
                 unexpected.append(k)
                 continue
             t = torch.as_tensor(v).detach().to(device=self.device, dtype=torch.float32)
+            if t.numel() == 1 and len(self._shapes[k]) == 0:
+                t = t.reshape(())  # torch accepts a (1,) tensor for a 0-dim parameter
             if tuple(t.shape) != tuple(self._shapes[k]):
                 raise RuntimeError(f"size mismatch for {k}: checkpoint {tuple(t.shape)} vs model {tuple(self._shapes[k])}")
             self._params[k] = t.contiguous().clone()
@@ -351,6 +353,8 @@ class PolicyValueNet:
         logits = torch.empty((B, self.cfg.policy_size), dtype=torch.float32, device=planes.device)
         values = torch.empty((B,), dtype=torch.float32, device=planes.device)
         prec = 1 if (precision or self.precision) == "bf16" else 0
+        if B == 0:
+            return logits, values
         with torch.cuda.device(planes.device):
             _native.check(_native.lib().m0_net_forward(self._handle, planes.data_ptr(), B, logits.data_ptr(), values.data_ptr(), prec,
                                                        _native.current_stream()), "m0_net_forward")

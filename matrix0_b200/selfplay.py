@@ -1,0 +1,186 @@
+"""Batched, device-resident self-play: the B200 replacement of ``azchess/selfplay/internal.py``.
+
+``SelfPlayEngine`` keeps G games on one GPU and advances all of them in lock step:
+
+    per move :  trees_clear -> search_begin -> NN(root) -> expand           (MCTS.run prologue)
+                [select -> NN(leaves) -> expand+backup]  x ceil(sims / inference_batch_size)
+                selfplay_advance (sample move, resign, push, finish / restart games)
+
+Every step is a CUDA kernel launched through the C ABI; planes and logits never leave the GPU.
+Search semantics per move are those of the reference's ``MCTS.run`` on a fresh ``MCTS`` object
+("reference-exact" accounting: one pending leaf per game and mini-batch).  The reference
+itself reuses one MCTS object across moves, which makes its self-play fail with "zero visits" on
+the second move, so per-move fresh trees are the only working reading.
+
+The configuration is the reference's YAML dictionary (``mcts:`` / ``selfplay:`` sections), merged
+exactly as ``selfplay_worker`` does (internal.py:269-304).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import time
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+from . import _native
+from .engine import SearchEngine
+from .mcts import MCTSConfig
+
+END_REASONS = {1: "checkmate", 2: "stalemate", 3: "insufficient_material", 4: "fifty_moves", 5: "repetition", 6: "max_game_len", 7: "resign"}
+
+
+class SelfPlayConfigStruct(ctypes.Structure):
+    """struct m0_selfplay_config (include/matrix0_b200.h)."""
+    _fields_ = [(n, ctypes.c_double) for n in ("temperature_start", "temperature_end", "resign_threshold", "resign_min_entropy",
+                                               "resign_value_margin")] \
+        + [(n, ctypes.c_int) for n in ("temperature_moves", "max_game_len", "min_resign_plies", "resign_window",
+                                       "resign_consecutive_bad", "opening_random_plies")] \
+        + [("seed", ctypes.c_uint64)]
+
+
+class FinishedGameStruct(ctypes.Structure):
+    _fields_ = [("game", ctypes.c_int), ("plies", ctypes.c_int), ("z", ctypes.c_float), ("reason", ctypes.c_int), ("avg_entropy", ctypes.c_float)]
+
+
+def resolve_mcts_config(cfg_dict: Dict[str, Any]) -> MCTSConfig:
+    """The MCTSConfig ``selfplay_worker`` builds (internal.py:269-304): selfplay keys override mcts keys."""
+    sp = dict(cfg_dict.get("selfplay", {}) or {})
+    base = dict(cfg_dict.get("mcts", {}) or {}) or dict(cfg_dict.get("mcts_defaults", {}) or {})
+    base.setdefault("num_simulations", int(sp.get("num_simulations", 800)))
+    base.setdefault("cpuct", float(sp.get("cpuct", 2.5)))
+    base.setdefault("dirichlet_alpha", float(sp.get("dirichlet_alpha", 0.3)))
+    base.setdefault("dirichlet_frac", float(sp.get("dirichlet_frac", 0.25)))
+    base.setdefault("inference_batch_size", 96)
+    base.setdefault("selection_jitter", float(sp.get("selection_jitter", 0.01)))
+    m = dict(base)
+    m.update({
+        "num_simulations": int(sp.get("num_simulations", m.get("num_simulations", 800))),
+        "cpuct": float(sp.get("cpuct", m.get("cpuct", 2.5))),
+        "dirichlet_alpha": float(sp.get("dirichlet_alpha", m.get("dirichlet_alpha", 0.3))),
+        "dirichlet_frac": float(sp.get("dirichlet_frac", m.get("dirichlet_frac", 0.25))),
+        "tt_capacity": int(m.get("tt_capacity", 2000000)),
+        "selection_jitter": float(sp.get("selection_jitter", m.get("selection_jitter", 0.01))),
+        "inference_batch_size": int(m.get("inference_batch_size", 96)),
+        "fpu": float(sp.get("fpu", m.get("fpu", 0.5))),
+        "parent_q_init": bool(sp.get("parent_q_init", m.get("parent_q_init", True))),
+        "tt_cleanup_frequency": int(m.get("tt_cleanup_frequency", 500)),
+        "draw_penalty": float(m.get("draw_penalty", -0.1)),
+        "value_from_white": bool(m.get("value_from_white", False)),
+    })
+    return MCTSConfig.from_dict(m)
+
+
+class SelfPlayEngine:
+    def __init__(self, model, cfg_dict: Dict[str, Any], games: int = 4096, device: Optional[int] = None, deterministic: bool = False,
+                 seed: int = 1234, precision: Optional[str] = None, max_nodes: int = 4096):
+        import torch
+        self.model = model
+        self.cfg_dict = cfg_dict
+        self.mcfg = resolve_mcts_config(cfg_dict)
+        self.sp = dict(cfg_dict.get("selfplay", {}) or {})
+        self.G = int(games)
+        self.deterministic = bool(deterministic)
+        self.precision = precision
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        with torch.cuda.device(self.device):
+            self.engine = SearchEngine(self.G, max_nodes=max_nodes, max_depth=128, hist_cap=int(self.sp.get("max_game_len", 200)) + 64,
+                                       device=self.device_index)
+            self.engine.configure(self.mcfg, deterministic, seed)
+            s = SelfPlayConfigStruct()
+            s.temperature_start = float(self.sp.get("temperature_start", 1.0))
+            s.temperature_end = float(self.sp.get("temperature_end", 0.1))
+            s.temperature_moves = int(self.sp.get("temperature_moves", 20))
+            s.resign_threshold = float(self.sp.get("resign_threshold", -0.98))
+            s.resign_min_entropy = float(self.sp.get("resign_min_entropy", 0.3))
+            s.resign_value_margin = float(self.sp.get("resign_value_margin", 0.05))
+            s.max_game_len = int(self.sp.get("max_game_len", 200))
+            s.min_resign_plies = int(self.sp.get("min_resign_plies", 24))
+            s.resign_window = int(self.sp.get("resign_window", 4))
+            s.resign_consecutive_bad = int(self.sp.get("resign_consecutive_bad", 5))
+            s.opening_random_plies = int(self.sp.get("opening_random_plies", cfg_dict.get("openings", {}).get("random_plies", 0)))
+            s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            lib = _native.lib()
+            _native.check(lib.m0_selfplay_configure(self.engine._h, ctypes.byref(s), _native.current_stream()), "m0_selfplay_configure")
+        self._lib = lib
+        self.sims_left = torch.zeros((self.G,), dtype=torch.int32, device=self.device)
+        self.plies = torch.zeros((self.G,), dtype=torch.int32, device=self.device)
+        self.moves_played = torch.zeros((self.G,), dtype=torch.int16, device=self.device)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed))
+        self.nn_evals = 0
+        self.nn_rows = 0
+        self.moves = 0
+        self.steps = 0
+
+    # ---- step plan --------------------------------------------------------------------------------
+    def batches_per_move(self) -> int:
+        sims = int(self.mcfg.num_simulations)
+        frac = 0.0 if self.deterministic else float(self.mcfg.playout_random_frac)
+        hi = int(max(max(1, sims * (1.0 - frac)), sims * (1.0 + frac))) if frac > 0 else sims
+        bs = max(1, int(self.mcfg.inference_batch_size))
+        return (hi + bs - 1) // bs
+
+    def start(self) -> None:
+        _native.check(self._lib.m0_selfplay_start(self.engine._h, _native.current_stream()), "m0_selfplay_start")
+
+    def _forward(self, planes):
+        self.nn_evals += 1
+        self.nn_rows += planes.shape[0]
+        return self.model.forward_planes(planes, self.precision) if self.precision else self.model.forward_planes(planes)
+
+    def begin_move(self) -> None:
+        """MCTS.run prologue for every game: fresh tree, root evaluation + expansion, Dirichlet noise, budgets."""
+        import torch
+        eng = self.engine
+        _native.check(self._lib.m0_trees_clear(eng._h, _native.current_stream()), "m0_trees_clear")
+        eng.begin()
+        logits, values = self._forward(eng.planes)
+        eng.expand_backup(logits, values)
+        if not self.deterministic and float(self.mcfg.dirichlet_frac) > 0:
+            _native.check(self._lib.m0_selfplay_plies(eng._h, self.plies.data_ptr(), _native.current_stream()), "m0_selfplay_plies")
+            dp = getattr(self.mcfg, "dirichlet_plies", None)
+            apply = None if dp is None else (self.plies < int(dp)).to(torch.int32)
+            eng.add_dirichlet(None, apply)
+        sims = int(self.mcfg.num_simulations)
+        frac = 0.0 if self.deterministic else float(self.mcfg.playout_random_frac)
+        if frac > 0.0 and sims > 0:  # per-game budgets, mcts.py:380-385
+            low = int(max(1, sims * (1.0 - frac)))
+            high = int(max(low, sims * (1.0 + frac)))
+            self.sims_left.copy_(torch.randint(low, high + 1, (self.G,), device=self.device, generator=self._gen, dtype=torch.int32))
+        else:
+            self.sims_left.fill_(sims)
+        self.steps += 1
+
+    def search_step(self) -> None:
+        """One mini-batch: select -> evaluate the pending leaves of all games -> expand + backup."""
+        eng = self.engine
+        _native.check(self._lib.m0_search_select_var(eng._h, int(self.mcfg.inference_batch_size), self.sims_left.data_ptr(),
+                                                     eng.planes.data_ptr(), _native.current_stream()), "m0_search_select_var")
+        logits, values = self._forward(eng.planes)
+        eng.expand_backup(logits, values)
+        self.steps += 1
+
+    def end_move(self) -> None:
+        _native.check(self._lib.m0_selfplay_advance(self.engine._h, self.moves_played.data_ptr(), _native.current_stream()), "m0_selfplay_advance")
+        self.moves += 1
+
+    def play_move(self) -> None:
+        self.begin_move()
+        for _ in range(self.batches_per_move()):
+            self.search_step()
+        self.end_move()
+
+    # ---- results ----------------------------------------------------------------------------------
+    def finished_games(self, max_records: int = 65536) -> List[Dict[str, Any]]:
+        buf = (FinishedGameStruct * max_records)()
+        n = ctypes.c_int(0)
+        _native.check(self._lib.m0_selfplay_finished(self.engine._h, buf, max_records, ctypes.byref(n), _native.current_stream()), "m0_selfplay_finished")
+        return [{"slot": buf[i].game, "moves": buf[i].plies, "result": float(buf[i].z), "reason": END_REASONS.get(buf[i].reason, "?"),
+                 "resigned": buf[i].reason == 7, "draw": float(buf[i].z) == 0.0, "avg_policy_entropy": float(buf[i].avg_entropy)}
+                for i in range(n.value)]
+
+    def counters(self) -> Dict[str, int]:
+        return self.engine.counters()

@@ -37,7 +37,7 @@ def make_state_dict(shapes: Dict[str, tuple], seed: int = 0) -> Dict[str, torch.
         else:
             fan_in = int(np.prod(shape[1:]))
             v = (rs.standard_normal(shape) * math.sqrt(2.0 / fan_in)).astype(np.float32)
-        sd[name] = torch.from_numpy(np.ascontiguousarray(v))
+        sd[name] = torch.from_numpy(np.ascontiguousarray(v)).reshape(tuple(shape))
     return sd
 
 
