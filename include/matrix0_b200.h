@@ -178,6 +178,11 @@ int m0_net_destroy(m0_net* net);
 /* PolicyValueNet.forward (resnet.py:755-760): d_planes float32[B][planes][8][8] -> d_logits float32[B][4672], d_values
  * float32[B].  precision 0 = fp32 SIMT kernels, 1 = bf16 tcgen05 tensor-core pipeline. */
 int m0_net_forward(m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, int precision, void* stream);
+/* The dominant kernel on its own (tests, roofline micro-benchmark): tcgen05/TMA implicit GEMM over bf16 operands.
+ * taps = 9: 3x3 "same" convolution of NHWC activations d_act_bf16[boards][8][8][cin] with d_w_bf16[n][9*cin]
+ * (k = (ky*3+kx)*cin + ci, nn.Conv2d of resnet.py:32-34); taps = 1: d_act_bf16[boards*64][cin] x d_w_bf16[n][cin]^T.
+ * d_out_f32[boards*64][n].  boards even, cin % 64 == 0, n % 16 == 0, n <= 320. */
+int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, int boards, int cin, int n, int taps, float* d_out_f32, void* stream);
 /* forward(x, return_ssl=True) (resnet.py:736-745): d_ssl_out[h] float32[B][k_h][8][8] for each SSL head (fp32 path) */
 int m0_net_forward_ssl(m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, float* const* d_ssl_out, void* stream);
 

@@ -1,30 +1,11 @@
 // C-ABI of the evaluator: PolicyValueNet.forward (azchess/model/resnet.py:755-760) as a sequence of
 // CUDA kernel launches on the caller's stream.  precision 0 = fp32 SIMT path (parity within 1e-4),
 // precision 1 = bf16 tensor-core path (nn_tc_kernels.cu).
-#include "nn.cuh"
+#include "net_host.cuh"
 #include <new>
 #include <string.h>
 
 using namespace m0;
-
-struct m0_net;
-namespace m0 {
-int tc_net_prepare(::m0_net* net, cudaStream_t s);
-int tc_net_forward(::m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, cudaStream_t s);
-void tc_net_release(::m0_net* net);
-}  // namespace m0
-
-struct m0_net {
-  int device;
-  m0_net_config cfg;
-  m0_net_weights w;
-  // workspace (fp32 path), grown on demand
-  int ws_batch;
-  float *x, *t1, *t2, *qkv;          // [B][64][C], [B][64][C], [B][64][C], [B][64][3C]
-  float *ph, *pf, *vh1, *vh2, *vf1, *vf2, *vg;  // head temporaries
-  float *ssl_a, *ssl_b, *ssl_c;
-  void* tc;                          // bf16 path state (opaque, nn_tc_kernels.cu)
-};
 
 #define TRY(x)            \
   do {                    \
@@ -204,10 +185,8 @@ int m0_net_forward_ssl(m0_net* n, const float* d_planes, int B, float* d_logits,
 
 }  // extern "C"
 
-// accessors for the tensor-core path
+// shared with the tensor-core path (nn_tc_kernels.cu)
 namespace m0 {
-const m0_net_config& net_cfg(const ::m0_net* n) { return n->cfg; }
-const m0_net_weights& net_weights(const ::m0_net* n) { return n->w; }
-void*& net_tc_state(::m0_net* n) { return n->tc; }
-int net_device(const ::m0_net* n) { return n->device; }
+int net_ws_reserve(::m0_net* n, int B) { return ws_reserve(n, B); }
+int net_forward_heads_f32(::m0_net* n, int B, float* logits, float* values, cudaStream_t s) { return forward_heads_f32(n, B, logits, values, s); }
 }  // namespace m0

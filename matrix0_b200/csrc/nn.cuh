@@ -1,8 +1,12 @@
 // PolicyValueNet inference (azchess/model/resnet.py) -- shared declarations of the CUDA evaluator.
 #pragma once
+#include <cuda_bf16.h>
 #include "m0_common.cuh"
 
 namespace m0 {
+int nn_groupnorm_mixed(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride,
+                       float* out, __nv_bfloat16* out_bf16, int B, int C, int act, cudaStream_t s);
+int nn_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_LEAKY = 3, ACT_TANH = 4, ACT_SIGMOID = 5 };
 enum { A_DIRECT = 0, A_IM2COL_NHWC = 1, A_IM2COL_NCHW = 2 };

@@ -102,7 +102,7 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const 
 // half-warps.  out = act(GN(x)) + residual  (residual optional, batch stride may be 0 = broadcast)
 __global__ void groupnorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ residual, long long residual_bstride, float* __restrict__ out,
-                                     int C, int act) {
+                                     __nv_bfloat16* __restrict__ out_bf16, int C, int act) {
   const int b = blockIdx.x, c = threadIdx.x;
   const float* xb = x + (size_t)b * 64 * C;
   float s = 0.0f;
@@ -119,12 +119,29 @@ __global__ void groupnorm_f32_kernel(const float* __restrict__ x, const float* _
   for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
   const float rstd = rsqrtf(v * (1.0f / 1024.0f) + 1e-5f);
   const float g = gamma[c] * rstd, bb = beta[c] - mean * g;
-  float* ob = out + (size_t)b * 64 * C;
+  float* ob = out ? out + (size_t)b * 64 * C : nullptr;
+  __nv_bfloat16* hb = out_bf16 ? out_bf16 + (size_t)b * 64 * C : nullptr;
   const float* rb = residual ? residual + (size_t)b * residual_bstride : nullptr;
   for (int sq = 0; sq < 64; ++sq) {
     float y = act_apply(fmaf(xb[sq * C + c], g, bb), act);
     if (rb) y += rb[sq * C + c];
-    ob[sq * C + c] = y;
+    if (ob) ob[sq * C + c] = y;
+    if (hb) hb[sq * C + c] = __float2bfloat16(y);
+  }
+}
+
+// fp32 -> bf16 copy (weights at prepare time; activations that feed a tensor-core GEMM)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + i) = pk;
+  } else {
+    for (; i < n; ++i) out[i] = __float2bfloat16(in[i]);
   }
 }
 
@@ -278,8 +295,19 @@ int nn_gemm_f32(int mode, const float* A, const float* W, const float* bias, con
 }
 int nn_groupnorm_f32(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride,
                      float* out, int B, int C, int act, cudaStream_t s) {
-  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, C, act);
+  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, nullptr, C, act);
   return m0_check_launch("groupnorm_f32");
+}
+int nn_groupnorm_mixed(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride,
+                       float* out, __nv_bfloat16* out_bf16, int B, int C, int act, cudaStream_t s) {
+  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, out_bf16, C, act);
+  return m0_check_launch("groupnorm_mixed");
+}
+int nn_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+  if (n == 0) return M0_OK;
+  size_t threads = (n + 3) / 4;
+  f32_to_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(in, out, n);
+  return m0_check_launch("f32_to_bf16");
 }
 int nn_se_residual_f32(const float* conv_out, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                        float* x_out, int B, int C, int hidden, int act, int use_se, cudaStream_t s) {

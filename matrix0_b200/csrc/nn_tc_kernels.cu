@@ -1,17 +1,286 @@
-// BF16 tensor-core path of the PolicyValueNet forward (tcgen05 / TMEM / TMA implicit GEMM).
-// Placeholder translation unit: the entry points exist so that the library links; the kernels land
-// in the next commit.  Calling the bf16 precision before that fails loudly.
-#include "nn.cuh"
+// BF16 tensor-core path of PolicyValueNet.forward: every 3x3 / 1x1 convolution of the trunk runs as the
+// tcgen05 + TMEM + TMA implicit GEMM of tc_gemm.cuh (bf16 operands, fp32 accumulation in tensor memory);
+// normalisation statistics, SE, softmax and the heads stay in fp32.
+#include "net_host.cuh"
+#include "tc_gemm.cuh"
+#include <new>
+#include <string.h>
+#include <vector>
 
-struct m0_net;
+using namespace m0;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows][cols], box {64 cols, box_rows}, 128-byte swizzle, zero fill outside
+int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { m0_set_error("cuTensorMapEncodeTiled is not available from the driver"); return M0_ERR_CUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { m0_set_error("cuTensorMapEncodeTiled(2d %llu x %llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (int)r); return M0_ERR_CUDA; }
+  return M0_OK;
+}
+
+// 4-D view of NHWC activations [boards][8][8][C] bf16: dims {C, 8, 8, boards}, box {64, 8, 8, 2}
+int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { m0_set_error("cuTensorMapEncodeTiled is not available from the driver"); return M0_ERR_CUDA; }
+  cuuint64_t dims[4] = {C, 8, 8, boards};
+  cuuint64_t strides[3] = {C * 2, C * 2 * 8, C * 2 * 64};
+  cuuint32_t box[4] = {64, 8, 8, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { m0_set_error("cuTensorMapEncodeTiled(nhwc boards=%llu C=%llu) failed: %d", (unsigned long long)boards, (unsigned long long)C, (int)r); return M0_ERR_CUDA; }
+  return M0_OK;
+}
+
+struct TcWeight {
+  __nv_bfloat16* w = nullptr;  // [n][k] bf16
+  CUtensorMap map;             // box {64, n_part}
+  int n = 0, k = 0, n_part = 0;
+};
+
+struct TcBlock {
+  TcWeight conv1, conv2, qkv, proj;
+};
+
+struct TcState {
+  int sm_count = 148;
+  int max_smem = 0;
+  TcWeight pst, inter;
+  std::vector<TcBlock> blocks;
+  // bf16 activation buffers [cap][64][C] and their maps
+  int cap = 0;
+  __nv_bfloat16 *a1 = nullptr, *a2 = nullptr;
+  CUtensorMap a1_conv, a2_conv, a1_mat, a2_mat;
+  std::vector<void*> allocs;
+};
+
+#define TRY(x)            \
+  do {                    \
+    int _r = (x);         \
+    if (_r != M0_OK) return _r; \
+  } while (0)
+
+int n_part_for(int n) { return n <= 256 ? n : n / 2; }
+
+int make_weight(TcState* st, TcWeight* out, const float* w_f32, int n, int k, cudaStream_t s) {
+  // launches cover at most 320 output channels each (N <= 320 -> <= 512 TMEM columns); wider layers are split by rows
+  int n_launch = n <= 320 ? n : 320;
+  out->n = n;
+  out->k = k;
+  out->n_part = n_part_for(n_launch);
+  void* p = nullptr;
+  M0_CUDA_TRY(cudaMalloc(&p, (size_t)n * k * 2));
+  st->allocs.push_back(p);
+  out->w = (__nv_bfloat16*)p;
+  TRY(nn_f32_to_bf16(w_f32, out->w, (size_t)n * k, s));
+  return make_map_2d(&out->map, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)out->n_part);
+}
+
+int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// one launch of the tensor-core GEMM: rows [0, M), output columns [w_row0, w_row0 + N) of the layer
+int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M, int conv, int taps, int cin, int w_row0, int N, float* out_f32,
+                __nv_bfloat16* out_bf16, int ldc, int col0, const float* bias, int act, float scale, cudaStream_t s) {
+  tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M;
+  p.N = N;
+  p.n_part = w.n_part < N ? w.n_part : N;
+  p.taps = taps;
+  p.kb_per_tap = cin / 64;
+  p.conv = conv;
+  p.w_row0 = w_row0;
+  p.tmem_cols = pow2_cols(N);
+  p.out_f32 = out_f32;
+  p.out_bf16 = out_bf16;
+  p.ldc = ldc;
+  p.col0 = col0;
+  p.bias = bias;
+  p.act = act;
+  p.scale = scale;
+  const int stage_bytes = tc::A_TILE_BYTES + N * tc::BK * 2;
+  int stages = (st->max_smem - 2048) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) { m0_set_error("tensor-core GEMM: tile does not fit in shared memory (N=%d)", N); return M0_ERR_ARG; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static size_t configured = 0;
+  if (smem > configured) {
+    M0_CUDA_TRY(cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tiles = (M + tc::BM - 1) / tc::BM;
+  const int grid = tiles < st->sm_count ? tiles : st->sm_count;
+  tc::gemm_tc_kernel<<<grid, tc::NUM_THREADS, smem, s>>>(a_map, w.map, p);
+  return m0_check_launch("gemm_tc_kernel");
+}
+
+int tc_reserve(m0_net* n, TcState* st, int B) {
+  const int need = (B + 1) & ~1;  // tiles hold two boards
+  if (need <= st->cap) return M0_OK;
+  const size_t C = n->cfg.channels;
+  if (st->a1) cudaFree(st->a1);
+  if (st->a2) cudaFree(st->a2);
+  st->a1 = st->a2 = nullptr;
+  st->cap = 0;
+  M0_CUDA_TRY(cudaMalloc((void**)&st->a1, (size_t)need * 64 * C * 2));
+  M0_CUDA_TRY(cudaMalloc((void**)&st->a2, (size_t)need * 64 * C * 2));
+  M0_CUDA_TRY(cudaMemset(st->a1, 0, (size_t)need * 64 * C * 2));
+  M0_CUDA_TRY(cudaMemset(st->a2, 0, (size_t)need * 64 * C * 2));
+  TRY(make_map_nhwc(&st->a1_conv, st->a1, need, C));
+  TRY(make_map_nhwc(&st->a2_conv, st->a2, need, C));
+  TRY(make_map_2d(&st->a1_mat, st->a1, (uint64_t)need * 64, C, 128));
+  TRY(make_map_2d(&st->a2_mat, st->a2, (uint64_t)need * 64, C, 128));
+  st->cap = need;
+  return M0_OK;
+}
+
+}  // namespace
+
 namespace m0 {
-int tc_net_prepare(::m0_net*, cudaStream_t) {
-  m0_set_error("bf16 tensor-core path not available in this build");
-  return M0_ERR_STATE;
+
+int tc_net_prepare(::m0_net* n, cudaStream_t s) {
+  if (n->tc) return M0_OK;
+  const m0_net_config& c = n->cfg;
+  if (c.channels % 64 != 0) { m0_set_error("bf16 tensor-core path needs channels %% 64 == 0 (got %d)", c.channels); return M0_ERR_ARG; }
+  if (c.channels > 320) { m0_set_error("bf16 tensor-core path supports up to 320 channels (got %d)", c.channels); return M0_ERR_ARG; }
+  TcState* st = new (std::nothrow) TcState();
+  if (!st) { m0_set_error("out of host memory"); return M0_ERR_ARG; }
+  cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, n->device);
+  cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, n->device);
+  const int C = c.channels;
+  int rc = M0_OK;
+  do {
+    if (c.chess_features) {
+      if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, s)) != M0_OK) break;
+    }
+    st->blocks.resize(c.blocks);
+    for (int i = 0; i < c.blocks && rc == M0_OK; ++i) {
+      const m0_block_weights& b = n->w.blocks[i];
+      if ((rc = make_weight(st, &st->blocks[i].conv1, b.conv1_w, C, 9 * C, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->blocks[i].conv2, b.conv2_w, C, 9 * C, s)) != M0_OK) break;
+      if (b.has_attention) {
+        if ((rc = make_weight(st, &st->blocks[i].qkv, b.att_qkv_w, 3 * C, C, s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].proj, b.att_proj_w, C, C, s)) != M0_OK) break;
+      }
+    }
+  } while (0);
+  if (rc != M0_OK) {
+    for (void* p : st->allocs) cudaFree(p);
+    delete st;
+    return rc;
+  }
+  n->tc = st;
+  return M0_OK;
 }
-int tc_net_forward(::m0_net*, const float*, int, float*, float*, cudaStream_t) {
-  m0_set_error("bf16 tensor-core path not available in this build");
-  return M0_ERR_STATE;
+
+void tc_net_release(::m0_net* n) {
+  TcState* st = (TcState*)n->tc;
+  if (!st) return;
+  for (void* p : st->allocs) cudaFree(p);
+  if (st->a1) cudaFree(st->a1);
+  if (st->a2) cudaFree(st->a2);
+  delete st;
+  n->tc = nullptr;
 }
-void tc_net_release(::m0_net*) {}
+
+int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float* values, cudaStream_t s) {
+  TcState* st = (TcState*)n->tc;
+  TRY(net_ws_reserve(n, B));
+  TRY(tc_reserve(n, st, B));
+  const m0_net_config& c = n->cfg;
+  const m0_net_weights& w = n->w;
+  const int C = c.channels, M = B * 64, act = c.activation;
+  // stem (K = 9 * 19 = 171 is not a multiple of 64: fp32 SIMT, 0.1 % of the FLOPs) + position encoding
+  TRY(nn_gemm_f32(A_IM2COL_NCHW, planes, w.stem_w, nullptr, nullptr, n->t1, M, C, 9 * c.planes, 0, C, c.planes, ACT_NONE, 1.0f, s));
+  if (c.chess_features) {
+    TRY(nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
+    float* cur = n->x;
+    if (c.piece_square_tables) {
+      TRY(launch_gemm(st, st->a1_mat, st->pst, M, 0, 1, C, 0, C, n->t1, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+      TRY(nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
+      cur = n->t2;
+    }
+    TRY(launch_gemm(st, st->a1_conv, st->inter, M, 1, 9, C, 0, C, n->t1, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+    TRY(nn_groupnorm_mixed(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
+  } else {
+    TRY(nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
+  }
+  int att_seen = 0;
+  const int stride = c.infer_attention_stride > 1 ? c.infer_attention_stride : 1;
+  for (int i = 0; i < c.blocks; ++i) {
+    const m0_block_weights& b = w.blocks[i];
+    const TcBlock& tb = st->blocks[i];
+    TRY(nn_groupnorm_mixed(n->x, b.gn1_w, b.gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));
+    TRY(launch_gemm(st, st->a1_conv, tb.conv1, M, 1, 9, C, 0, C, n->t1, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+    TRY(nn_groupnorm_mixed(n->t1, b.gn2_w, b.gn2_b, nullptr, 0, nullptr, st->a2, B, C, act, s));
+    TRY(launch_gemm(st, st->a2_conv, tb.conv2, M, 1, 9, C, 0, C, n->t2, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+    TRY(nn_se_residual_f32(n->t2, n->x, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n->x, B, C, c.se_hidden, act, c.se, s));
+    if (b.has_attention) {
+      att_seen++;
+      if (att_seen % stride == 0) {
+        TRY(nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
+        for (int r0 = 0; r0 < 3 * C; r0 += C)
+          TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, nullptr, ACT_NONE, 1.0f, s));
+        TRY(nn_attention_f32(n->qkv, c.attention_relbias ? b.att_rel_bias : nullptr, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
+        TRY(nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
+        TRY(launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+        TRY(nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
+      }
+    }
+  }
+  return net_forward_heads_f32(n, B, logits, values, s);
+}
+
 }  // namespace m0
+
+// Stand-alone entry point of the tensor-core convolution / GEMM (tests and the roofline micro-benchmark):
+//   taps = 9: out[b*64+sq][n] = conv3x3(act NHWC bf16 [boards][8][8][cin], w [n][9*cin]) ; taps = 1: plain GEMM act[boards*64][cin] x w[n][cin]^T
+extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, int boards, int cin, int n, int taps, float* d_out_f32,
+                          void* stream) {
+  if (!d_act_bf16 || !d_w_bf16 || !d_out_f32 || boards <= 0 || (boards & 1) || cin % 64 != 0 || n % 16 != 0 || n > 320 || (taps != 1 && taps != 9)) {
+    m0_set_error("m0_tc_conv: invalid argument (boards even, cin %% 64 == 0, n %% 16 == 0, n <= 320, taps in {1, 9})");
+    return M0_ERR_ARG;
+  }
+  static TcState st;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&st.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  TcWeight w;
+  w.w = (__nv_bfloat16*)d_w_bf16;
+  w.n = n;
+  w.k = taps * cin;
+  w.n_part = n_part_for(n);
+  TRY(make_map_2d(&w.map, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)w.n_part));
+  CUtensorMap a;
+  if (taps == 9) TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin));
+  else TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));
+  return launch_gemm(&st, a, w, boards * 64, taps == 9 ? 1 : 0, taps, cin, 0, n, d_out_f32, nullptr, n, 0, nullptr, ACT_NONE, 1.0f, (cudaStream_t)stream);
+}

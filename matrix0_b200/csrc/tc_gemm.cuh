@@ -1,0 +1,309 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernel for sm_100a (hand-written PTX wrappers + kernel).
+//
+//   D[m][n] = sum_k A(m, k) * W[n][k]          A, W bf16 (K-major), D fp32 accumulated in tensor memory
+//
+// A is either a plain row-major matrix [M][K] (2-D TMA map) or the 3x3 "same" convolution view of an
+// NHWC activation tensor [B][8][8][C]: M = B*64 rows, K = 9*C, one (ky,kx) tap per group of C/64
+// k-blocks.  For the convolution the A tile of a k-block is ONE 4-D TMA box {64 ch, 8, 8, 2 boards}
+// whose (x, y) start coordinates are shifted by the tap offset: the TMA unit zero-fills the
+// out-of-board elements, which is exactly the zero padding of the convolution, and writes the
+// 128 rows x 128 B in the 128-byte-swizzled K-major layout tcgen05.mma consumes (no im2col buffer).
+//
+// CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane,
+// owns the TMEM allocation), warps 2..5 = epilogue (one thread per accumulator row / TMEM lane).
+// Persistent over M tiles of 128 rows; smem ring of STAGES x {A 16 KB, W N*128 B}; accumulator
+// 128 lanes x N fp32 columns of tensor memory (N <= 320 -> 512-column allocation).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "nn.cuh"
+
+namespace m0 {
+namespace tc {
+
+static constexpr int BM = 128;          // rows per tile (2 boards)
+static constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+static constexpr int A_TILE_BYTES = BM * BK * 2;
+static constexpr int NUM_THREADS = 192;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (bf16 inputs, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// make the mbarrier track completion of all tcgen05 operations issued so far by this thread
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64)   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
+// n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- kernel ----------------------------------------------------------------------------------------------------------
+struct GemmParams {
+  int M;            // valid rows of D (rows >= M are computed on zero / stale A rows and not stored)
+  int N;            // output columns handled by this launch (<= 320, multiple of 16)
+  int n_part;       // columns per tcgen05.mma (N if N <= 256, else N / 2); multiple of 16
+  int taps;         // 9 (3x3 convolution) or 1 (plain GEMM / 1x1 convolution)
+  int kb_per_tap;   // k-blocks per tap = Cin / 64 (plain GEMM: K / 64)
+  int conv;         // 1: A is the 4-D NHWC map, 0: A is the 2-D [M][K] map
+  int w_row0;       // first row of W (output-channel offset of this launch)
+  int stages;
+  int tmem_cols;    // power of two >= N, >= 32
+  // epilogue: out[m][col0 + n] = act(acc + bias[n]) * scale (* mul[m][n]); either output may be null
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ldc, col0;
+  const float* bias;   // indexed by w_row0 + n when non-null
+  int act;
+  float scale;
+};
+
+__device__ __forceinline__ float tc_act(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return x > 0.0f ? x : 0.0f;
+    case ACT_SILU: return x / (1.0f + __expf(-x));
+    case ACT_LEAKY: return x > 0.0f ? x : 0.05f * x;
+    case ACT_TANH: return tanhf(x);
+    case ACT_SIGMOID: return 1.0f / (1.0f + __expf(-x));
+    default: return x;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle; the dynamic smem base is aligned by the attribute,
+  // but align defensively
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int w_tile_bytes = p.N * BK * 2;
+  const int stage_bytes = A_TILE_BYTES + w_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (p.M + BM - 1) / BM;
+  const int kblocks = p.taps * p.kb_per_tap;
+  const int n_parts = p.N / p.n_part;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+          uint8_t* w_dst = a_dst + A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
+          if (p.conv) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(a_dst, &tma_a, &full_bar[stage], kc * BK, dx, dy, m0 >> 6);
+          } else {
+            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m0);
+          }
+          for (int part = 0; part < n_parts; ++part)
+            tma_load_2d(w_dst + (size_t)part * p.n_part * BK * 2, &tma_w, &full_bar[stage], kb * BK, p.w_row0 + part * p.n_part);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, p.n_part);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t w_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(a_addr + k * 32);
+            for (int part = 0; part < n_parts; ++part) {
+              const uint64_t bdesc = make_smem_desc(w_addr + part * p.n_part * BK * 2 + k * 32);
+              umma_bf16(tmem_base + (uint32_t)(part * p.n_part), adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full_bar);        // accumulator complete
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quarter = warp & 3;            // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    const int row = quarter * 32 + lane;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_full_bar, acc_phase);
+      tc_fence_after();
+      const int m = tile * BM + row;
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (m < p.M) {
+          const int ncols = (p.N - c0) < 32 ? (p.N - c0) : 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias && j < ncols) x += p.bias[p.w_row0 + c0 + j];
+            v[j] = tc_act(x, p.act) * p.scale;
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + (size_t)m * p.ldc + p.col0 + c0;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < ncols; ++j) o[j] = v[j];
+            }
+          }
+          if (p.out_bf16) {
+            __nv_bfloat16* o = p.out_bf16 + (size_t)m * p.ldc + p.col0 + c0;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar);
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace tc
+}  // namespace m0
