@@ -4,6 +4,7 @@
 #include "net_host.cuh"
 #include "tc_gemm.cuh"
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -55,9 +56,21 @@ int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C) 
 
 struct TcWeight {
   __nv_bfloat16* w = nullptr;  // [n][k] bf16
-  CUtensorMap map;             // box {64, n_part}
-  int n = 0, k = 0, n_part = 0;
+  CUtensorMap map;             // box {64, n_part / cluster}
+  int n = 0, k = 0, n_part = 0, cluster = 1;
 };
+
+// CTAs per cluster for a launch: the W tile is multicast within the cluster (M0_TC_CLUSTER overrides)
+int pick_cluster(int n_part) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("M0_TC_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  int cs = forced > 0 ? forced : 2;
+  while (cs > 1 && ((n_part / cs) % 8 != 0 || n_part % cs != 0)) cs >>= 1;  // slices are whole 8-row swizzle atoms
+  return cs;
+}
 
 struct TcBlock {
   TcWeight conv1, conv2, qkv, proj;
@@ -83,18 +96,18 @@ struct TcState {
 
 int n_part_for(int n) { return n <= 256 ? n : n / 2; }
 
-int make_weight(TcState* st, TcWeight* out, const float* w_f32, int n, int k, cudaStream_t s) {
-  // launches cover at most 320 output channels each (N <= 320 -> <= 512 TMEM columns); wider layers are split by rows
-  int n_launch = n <= 320 ? n : 320;
+// n_launch: output channels per kernel launch (N <= 320 -> <= 512 TMEM columns); wider layers are split by rows
+int make_weight(TcState* st, TcWeight* out, const float* w_f32, int n, int k, int n_launch, cudaStream_t s) {
   out->n = n;
   out->k = k;
   out->n_part = n_part_for(n_launch);
+  out->cluster = pick_cluster(out->n_part);
   void* p = nullptr;
   M0_CUDA_TRY(cudaMalloc(&p, (size_t)n * k * 2));
   st->allocs.push_back(p);
   out->w = (__nv_bfloat16*)p;
   TRY(nn_f32_to_bf16(w_f32, out->w, (size_t)n * k, s));
-  return make_map_2d(&out->map, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)out->n_part);
+  return make_map_2d(&out->map, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)(out->n_part / out->cluster));
 }
 
 int pow2_cols(int n) {
@@ -110,7 +123,8 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   memset(&p, 0, sizeof(p));
   p.M = M;
   p.N = N;
-  p.n_part = w.n_part < N ? w.n_part : N;
+  if (w.n_part > N || N % w.n_part != 0) { m0_set_error("tensor-core GEMM: launch width %d does not match the weight map box %d", N, w.n_part); return M0_ERR_ARG; }
+  p.n_part = w.n_part;
   p.taps = taps;
   p.kb_per_tap = cin / 64;
   p.conv = conv;
@@ -123,20 +137,37 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   p.bias = bias;
   p.act = act;
   p.scale = scale;
+  p.cluster = w.cluster;
   const int stage_bytes = tc::A_TILE_BYTES + N * tc::BK * 2;
-  int stages = (st->max_smem - 2048) / stage_bytes;
+  int stages = (st->max_smem - 2048 - tc::EPI_STAGE_BYTES) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) { m0_set_error("tensor-core GEMM: tile does not fit in shared memory (N=%d)", N); return M0_ERR_ARG; }
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + tc::EPI_STAGE_BYTES + 1024 + 256;
   static size_t configured = 0;
   if (smem > configured) {
     M0_CUDA_TRY(cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int tiles = (M + tc::BM - 1) / tc::BM;
-  const int grid = tiles < st->sm_count ? tiles : st->sm_count;
-  tc::gemm_tc_kernel<<<grid, tc::NUM_THREADS, smem, s>>>(a_map, w.map, p);
+  const int cs = w.cluster;
+  const int groups = (tiles + cs - 1) / cs;
+  int clusters = st->sm_count / cs;
+  if (clusters > groups) clusters = groups;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * cs));
+  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::gemm_tc_kernel, a_map, w.map, p));
   return m0_check_launch("gemm_tc_kernel");
 }
 
@@ -177,17 +208,17 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
   int rc = M0_OK;
   do {
     if (c.chess_features) {
-      if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, s)) != M0_OK) break;
-      if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, s)) != M0_OK) break;
+      if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, C, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, C, s)) != M0_OK) break;
     }
     st->blocks.resize(c.blocks);
     for (int i = 0; i < c.blocks && rc == M0_OK; ++i) {
       const m0_block_weights& b = n->w.blocks[i];
-      if ((rc = make_weight(st, &st->blocks[i].conv1, b.conv1_w, C, 9 * C, s)) != M0_OK) break;
-      if ((rc = make_weight(st, &st->blocks[i].conv2, b.conv2_w, C, 9 * C, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->blocks[i].conv1, b.conv1_w, C, 9 * C, C, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->blocks[i].conv2, b.conv2_w, C, 9 * C, C, s)) != M0_OK) break;
       if (b.has_attention) {
-        if ((rc = make_weight(st, &st->blocks[i].qkv, b.att_qkv_w, 3 * C, C, s)) != M0_OK) break;
-        if ((rc = make_weight(st, &st->blocks[i].proj, b.att_proj_w, C, C, s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].qkv, b.att_qkv_w, 3 * C, C, C, s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].proj, b.att_proj_w, C, C, C, s)) != M0_OK) break;
       }
     }
   } while (0);
@@ -278,7 +309,8 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
   w.n = n;
   w.k = taps * cin;
   w.n_part = n_part_for(n);
-  TRY(make_map_2d(&w.map, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)w.n_part));
+  w.cluster = pick_cluster(w.n_part);
+  TRY(make_map_2d(&w.map, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)(w.n_part / w.cluster)));
   CUtensorMap a;
   if (taps == 9) TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin));
   else TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));

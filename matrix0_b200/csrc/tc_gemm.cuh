@@ -68,6 +68,36 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
                : "memory");
 }
 
+// the same box delivered to the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier
+// (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
 }
@@ -92,6 +122,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // make the mbarrier track completion of all tcgen05 operations issued so far by this thread
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same, arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t), columns c..c+31
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -130,7 +166,8 @@ struct GemmParams {
   int w_row0;       // first row of W (output-channel offset of this launch)
   int stages;
   int tmem_cols;    // power of two >= N, >= 32
-  // epilogue: out[m][col0 + n] = act(acc + bias[n]) * scale (* mul[m][n]); either output may be null
+  int cluster;      // CTAs per cluster (1, 2 or 4): the W tile of a stage is loaded once per cluster and multicast
+  // epilogue: out[m][col0 + n] = act(acc + bias[n]) * scale; either output may be null
   float* out_f32;
   __nv_bfloat16* out_bf16;
   int ldc, col0;
@@ -150,31 +187,40 @@ __device__ __forceinline__ float tc_act(float x, int act) {
   }
 }
 
+static constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // one 32x32 fp32 transpose buffer per epilogue warp
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128-byte swizzle; the dynamic smem base is aligned by the attribute,
-  // but align defensively
+  // the 128-byte swizzle needs 1024-byte aligned tiles; the offset is identical in every CTA of a cluster
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int w_tile_bytes = p.N * BK * 2;
   const int stage_bytes = A_TILE_BYTES + w_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cs = p.cluster;
+  const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
   const int num_tiles = (p.M + BM - 1) / BM;
+  const int num_groups = (num_tiles + cs - 1) / cs;          // a cluster processes cs consecutive M tiles together
+  const int num_clusters = gridDim.x / cs;
+  const int cluster_id = blockIdx.x / cs;
   const int kblocks = p.taps * p.kb_per_tap;
   const int n_parts = p.N / p.n_part;
+  const int slice_rows = p.n_part / cs;                       // W rows of each part fetched by this CTA for the whole cluster
+  const uint16_t mask = (uint16_t)((1u << cs) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)cs);   // every CTA of the cluster must have consumed the stage
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(tmem_empty_bar, 128);
@@ -186,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -194,8 +241,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = tile * BM;
+      for (int g = cluster_id; g < num_groups; g += num_clusters) {
+        const int m0 = (g * cs + rank) * BM;   // may lie past M for the padding tiles of the last group: TMA zero-fills
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
@@ -208,89 +255,122 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else {
             tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m0);
           }
-          for (int part = 0; part < n_parts; ++part)
-            tma_load_2d(w_dst + (size_t)part * p.n_part * BK * 2, &tma_w, &full_bar[stage], kb * BK, p.w_row0 + part * p.n_part);
+          for (int part = 0; part < n_parts; ++part) {
+            uint8_t* dst = w_dst + ((size_t)part * p.n_part + (size_t)rank * slice_rows) * BK * 2;
+            const int row = p.w_row0 + part * p.n_part + rank * slice_rows;
+            if (cs > 1) tma_load_2d_mcast(dst, &tma_w, &full_bar[stage], kb * BK, row, mask);
+            else tma_load_2d(dst, &tma_w, &full_bar[stage], kb * BK, row);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, p.n_part);
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the accumulator
+    // The whole warp walks the pipeline (all values stay warp-uniform, so descriptors live in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = make_idesc_bf16(BM, p.n_part);
+    const uint32_t part_bytes = (uint32_t)(p.n_part * BK * 2);
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    for (int g = cluster_id; g < num_groups; g += num_clusters) {
+      mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t w_addr = a_addr + A_TILE_BYTES;
+        const uint32_t a_addr = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
+        const uint64_t adesc0 = make_smem_desc(a_addr);
+        const uint64_t bdesc0 = make_smem_desc(a_addr + A_TILE_BYTES);
+        const uint64_t bdesc1 = make_smem_desc(a_addr + A_TILE_BYTES + part_bytes);
+        if (elect_one()) {
+          if (n_parts == 2) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * 32);
-            for (int part = 0; part < n_parts; ++part) {
-              const uint64_t bdesc = make_smem_desc(w_addr + part * p.n_part * BK * 2 + k * 32);
-              umma_bf16(tmem_base + (uint32_t)(part * p.n_part), adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+              umma_bf16(tmem_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, accum);
+              umma_bf16(tmem_base + (uint32_t)p.n_part, adesc0 + 2 * k, bdesc1 + 2 * k, idesc, accum);
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          // frees the smem stage (in every CTA of the cluster) once these MMAs have read it
+          if (cs > 1) umma_commit_mcast(&empty_bar[stage], mask);
+          else umma_commit(&empty_bar[stage]);
         }
-        umma_commit(tmem_full_bar);        // accumulator complete
-        acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+      __syncwarp();
+      acc_phase ^= 1;
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (bias / activation) -> smem transpose -> coalesced global stores =====
     const int quarter = warp & 3;            // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
-    const int row = quarter * 32 + lane;
+    float* stg = epi_stage + quarter * (32 * 32);
+    const bool plain = (p.bias == nullptr) && (p.act == ACT_NONE) && (p.scale == 1.0f);
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int g = cluster_id; g < num_groups; g += num_clusters) {
       mbar_wait(tmem_full_bar, acc_phase);
       tc_fence_after();
-      const int m = tile * BM + row;
+      const int tile_row0 = (g * cs + rank) * BM + quarter * 32;
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (m < p.M) {
-          const int ncols = (p.N - c0) < 32 ? (p.N - c0) : 32;
-          float v[32];
+        if (!plain) {
+          const float* bias = p.bias ? p.bias + p.w_row0 + c0 : nullptr;
+          const int act = p.act;
+          const float scale = p.scale;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]);
-            if (p.bias && j < ncols) x += p.bias[p.w_row0 + c0 + j];
-            v[j] = tc_act(x, p.act) * p.scale;
+            if (bias && c0 + j < p.N) x += bias[j];
+            r[j] = __float_as_uint(tc_act(x, act) * scale);
           }
-          if (p.out_f32) {
-            float* o = p.out_f32 + (size_t)m * p.ldc + p.col0 + c0;
-            if (ncols == 32) {
+        }
+        // lane = row of the 32x32 block; 16-byte chunk q of row i is stored at chunk position q ^ (i & 7)
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < ncols; ++j) o[j] = v[j];
-            }
-          }
-          if (p.out_bf16) {
-            __nv_bfloat16* o = p.out_bf16 + (size_t)m * p.ldc + p.col0 + c0;
-            if (ncols == 32) {
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        const int ncols = (p.N - c0) < 32 ? (p.N - c0) : 32;
+        if (p.out_f32) {
+          // 8 lanes cover the 128 contiguous bytes of one row: each store instruction writes 4 full lines
+          const int q = lane & 7;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
-            } else {
-              for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16(v[j]);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;
+            const int m = tile_row0 + rr;
+            if (m < p.M && 4 * q < ncols) {
+              uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((q ^ (rr & 7)) << 2));
+              *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + p.col0 + c0 + 4 * q) = v;
             }
           }
         }
+        if (p.out_bf16) {
+          // 4 lanes cover the 64 contiguous bytes of one row (8 bf16 per lane)
+          const int q2 = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i;
+            const int m = tile_row0 + rr;
+            if (m < p.M && 8 * q2 < ncols) {
+              float4 lo = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * q2) ^ (rr & 7)) << 2));
+              float4 hi = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * q2 + 1) ^ (rr & 7)) << 2));
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(lo.x, lo.y), t1 = __floats2bfloat162_rn(lo.z, lo.w);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(hi.x, hi.y), t3 = __floats2bfloat162_rn(hi.z, hi.w);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldc + p.col0 + c0 + 8 * q2) = pk;
+            }
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(tmem_empty_bar);
@@ -299,6 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA leaves while peers may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
