@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=800)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--precision", default=os.environ.get("M0_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("M0_BENCH_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     args = ap.parse_args()
     if args.workload == "auto":
         try:

@@ -41,7 +41,7 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     from matrix0_b200.model import PolicyValueNet
     from matrix0_b200.selfplay import SelfPlayEngine
     lib = _native.lib()
-    precision = os.environ.get("M0_BENCH_PRECISION", args.precision if hasattr(args, "precision") else "bf16")
+    precision = os.environ.get("M0_BENCH_PRECISION", args.precision if hasattr(args, "precision") else "fp16")
     G = args.games
     cfg = reference_cfg(args.sims)
     net = PolicyValueNet.from_config(cfg["model"], device=f"cuda:{local}", precision=precision, seed=0)

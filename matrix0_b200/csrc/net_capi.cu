@@ -152,7 +152,8 @@ int m0_net_forward(m0_net* n, const float* d_planes, int B, float* d_logits, flo
   if (!n || !d_planes || !d_logits || !d_values || B < 0) { m0_set_error("m0_net_forward: invalid argument"); return M0_ERR_ARG; }
   if (B == 0) return M0_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (precision == 1) {
+  if (precision == 1 || precision == 2) {  // 1 = bf16, 2 = fp16 operands (fp32 accumulate)
+    nn_set_half_format(precision == 2);
     TRY(tc_net_prepare(n, s));
     return tc_net_forward(n, d_planes, B, d_logits, d_values, s);
   }

@@ -7,6 +7,8 @@ namespace m0 {
 int nn_groupnorm_mixed(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride,
                        float* out, __nv_bfloat16* out_bf16, int B, int C, int act, cudaStream_t s);
 int nn_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
+void nn_set_half_format(int fp16);  // 0 = bf16, 1 = fp16 storage for the 16-bit tensor-core operands
+int nn_half_format();
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_LEAKY = 3, ACT_TANH = 4, ACT_SIGMOID = 5 };
 enum { A_DIRECT = 0, A_IM2COL_NHWC = 1, A_IM2COL_NCHW = 2 };

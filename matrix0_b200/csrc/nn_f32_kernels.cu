@@ -6,8 +6,22 @@
 // (NHWC: [board][square = row*8 + col][channel]) and the weight layout (GEMM "B" operand
 // W[n][k], k = (ky*3 + kx)*Cin + ci for 3x3 convolutions).
 #include "nn.cuh"
+#include <cuda_fp16.h>
 
 namespace m0 {
+
+// 16-bit operand format of the tensor-core path: bf16 (default) or IEEE fp16, selected per forward call
+static int g_half_fp16 = 0;
+void nn_set_half_format(int fp16) { g_half_fp16 = fp16 ? 1 : 0; }
+int nn_half_format() { return g_half_fp16; }
+
+__device__ __forceinline__ __nv_bfloat16 to_half16(float x, int fp16) {
+  if (fp16) {
+    __half h = __float2half_rn(x);
+    return *reinterpret_cast<__nv_bfloat16*>(&h);  // storage is an opaque 16-bit word
+  }
+  return __float2bfloat16(x);
+}
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
@@ -102,7 +116,7 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const 
 // half-warps.  out = act(GN(x)) + residual  (residual optional, batch stride may be 0 = broadcast)
 __global__ void groupnorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ residual, long long residual_bstride, float* __restrict__ out,
-                                     __nv_bfloat16* __restrict__ out_bf16, int C, int act) {
+                                     __nv_bfloat16* __restrict__ out_bf16, int C, int act, int fp16) {
   const int b = blockIdx.x, c = threadIdx.x;
   const float* xb = x + (size_t)b * 64 * C;
   float s = 0.0f;
@@ -126,22 +140,21 @@ __global__ void groupnorm_f32_kernel(const float* __restrict__ x, const float* _
     float y = act_apply(fmaf(xb[sq * C + c], g, bb), act);
     if (rb) y += rb[sq * C + c];
     if (ob) ob[sq * C + c] = y;
-    if (hb) hb[sq * C + c] = __float2bfloat16(y);
+    if (hb) hb[sq * C + c] = to_half16(y, fp16);
   }
 }
 
 // fp32 -> bf16 copy (weights at prepare time; activations that feed a tensor-core GEMM)
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n, int fp16) {
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(in + i);
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&a);
-    pk.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(out + i) = pk;
+    out[i] = to_half16(v.x, fp16);
+    out[i + 1] = to_half16(v.y, fp16);
+    out[i + 2] = to_half16(v.z, fp16);
+    out[i + 3] = to_half16(v.w, fp16);
   } else {
-    for (; i < n; ++i) out[i] = __float2bfloat16(in[i]);
+    for (; i < n; ++i) out[i] = to_half16(in[i], fp16);
   }
 }
 
@@ -295,18 +308,18 @@ int nn_gemm_f32(int mode, const float* A, const float* W, const float* bias, con
 }
 int nn_groupnorm_f32(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride,
                      float* out, int B, int C, int act, cudaStream_t s) {
-  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, nullptr, C, act);
+  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, nullptr, C, act, 0);
   return m0_check_launch("groupnorm_f32");
 }
 int nn_groupnorm_mixed(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride,
                        float* out, __nv_bfloat16* out_bf16, int B, int C, int act, cudaStream_t s) {
-  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, out_bf16, C, act);
+  groupnorm_f32_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, out_bf16, C, act, g_half_fp16);
   return m0_check_launch("groupnorm_mixed");
 }
 int nn_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   if (n == 0) return M0_OK;
   size_t threads = (n + 3) / 4;
-  f32_to_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(in, out, n);
+  f32_to_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(in, out, n, g_half_fp16);
   return m0_check_launch("f32_to_bf16");
 }
 int nn_se_residual_f32(const float* conv_out, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

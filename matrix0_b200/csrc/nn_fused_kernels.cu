@@ -1,0 +1,83 @@
+// Memory-bound glue kernels of the tensor-core forward, fused so that the residual stream is read and
+// written once per residual block.
+#include "nn.cuh"
+#include <cuda_fp16.h>
+
+namespace m0 {
+
+__device__ __forceinline__ float fk_act(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return x > 0.0f ? x : 0.0f;
+    case ACT_SILU: return x / (1.0f + __expf(-x));
+    default: return x;
+  }
+}
+__device__ __forceinline__ __nv_bfloat16 fk_half(float x, int fp16) {
+  if (fp16) {
+    __half h = __float2half_rn(x);
+    return *reinterpret_cast<__nv_bfloat16*>(&h);
+  }
+  return __float2bfloat16(x);
+}
+
+// x_new = x + conv_out * gate   (SE excitation + residual add, resnet.py:68-80)
+// a_out = half(act(GroupNorm(x_new)))   (bn1 + activation of the NEXT pre-activation block, resnet.py:46-47), optional
+// One block per board, one thread per channel; the thread keeps its 64 values in registers, so x and conv_out are
+// read once and x_new / a_out written once.
+template <int C_MAX_UNUSED>
+__global__ void __launch_bounds__(320)
+se_apply_gn_kernel(const float* __restrict__ conv_out, const float* __restrict__ gate, float* __restrict__ x,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ a_out, int C, int act, int fp16) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const size_t base = (size_t)b * 64 * C + c;
+  const float e = gate ? gate[(size_t)b * C + c] : 1.0f;
+  float v[64];
+  float s = 0.0f;
+#pragma unroll
+  for (int sq = 0; sq < 64; ++sq) {
+    float y = fmaf(conv_out[base + (size_t)sq * C], e, x[base + (size_t)sq * C]);
+    v[sq] = y;
+    s += y;
+    x[base + (size_t)sq * C] = y;
+  }
+  if (!a_out) return;
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+  const float mean = s * (1.0f / 1024.0f);
+  float q = 0.0f;
+#pragma unroll
+  for (int sq = 0; sq < 64; ++sq) {
+    float d = v[sq] - mean;
+    q = fmaf(d, d, q);
+  }
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, off);
+  const float rstd = rsqrtf(q * (1.0f / 1024.0f) + 1e-5f);
+  const float g = gamma[c] * rstd, bb = beta[c] - mean * g;
+#pragma unroll
+  for (int sq = 0; sq < 64; ++sq) a_out[base + (size_t)sq * C] = fk_half(fk_act(fmaf(v[sq], g, bb), act), fp16);
+}
+
+// NCHW float32 planes [B][P][8][8] -> NHWC half [B][64][64] with channels P..63 zero (stem input of the tensor-core path)
+__global__ void planes_to_nhwc_half_kernel(const float* __restrict__ planes, __nv_bfloat16* __restrict__ out, int B, int P, int fp16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*64*64
+  if (i >= (size_t)B * 64 * 64) return;
+  const int c = (int)(i & 63);
+  const int sq = (int)((i >> 6) & 63);
+  const size_t b = i >> 12;
+  out[i] = c < P ? fk_half(planes[(b * P + c) * 64 + sq], fp16) : fk_half(0.0f, fp16);
+}
+
+int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
+                   int C, int act, cudaStream_t s) {
+  if (C > 320 || C % 32 != 0) { m0_set_error("se_apply_gn: unsupported channel count %d", C); return M0_ERR_ARG; }
+  se_apply_gn_kernel<0><<<B, C, 0, s>>>(conv_out, gate, x, gamma, beta, a_out, C, act, nn_half_format());
+  return m0_check_launch("se_apply_gn");
+}
+int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s) {
+  const size_t total = (size_t)B * 64 * 64;
+  planes_to_nhwc_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, out, B, P, nn_half_format());
+  return m0_check_launch("planes_to_nhwc_half");
+}
+
+}  // namespace m0

@@ -10,6 +10,29 @@
 
 using namespace m0;
 
+namespace m0 {
+int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
+                   int C, int act, cudaStream_t s);
+int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s);
+}  // namespace m0
+
+namespace m0 {
+// W1x[h][half*C + c] = W1[h][c] / 64 for both halves: the SE squeeze then reads the half-board sums directly
+__global__ void build_se_w1x_kernel(const float* __restrict__ w1, float* __restrict__ out, int hid, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hid * 2 * C) return;
+  int h = i / (2 * C), c = i % C;
+  out[i] = w1[h * C + c] * (1.0f / 64.0f);
+}
+// stem weights [C][9][P] -> [C][9][64] (zero padded input channels)
+__global__ void pad_stem_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int P) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 9 * 64) return;
+  int ci = i & 63, tap = (i >> 6) % 9, co = i / (9 * 64);
+  out[i] = ci < P ? w[(co * 9 + tap) * P + ci] : 0.0f;
+}
+}  // namespace m0
+
 namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -81,6 +104,13 @@ struct TcState {
   int max_smem = 0;
   TcWeight pst, inter;
   std::vector<TcBlock> blocks;
+  // SE: pooled half-board sums [cap][2][C], hidden [cap][hid], gate [cap][C]; W1 duplicated over the two halves and scaled by 1/64
+  float *pool = nullptr, *se_hid = nullptr, *se_gate = nullptr;
+  std::vector<float*> se_w1x;   // per block [hid][2C]
+  // stem on tensor cores: planes as NHWC half with 64 channels, weights [C][9*64]
+  __nv_bfloat16* planes_h = nullptr;
+  CUtensorMap planes_conv;
+  TcWeight stem;
   // bf16 activation buffers [cap][64][C] and their maps
   int cap = 0;
   __nv_bfloat16 *a1 = nullptr, *a2 = nullptr;
@@ -118,7 +148,8 @@ int pow2_cols(int n) {
 
 // one launch of the tensor-core GEMM: rows [0, M), output columns [w_row0, w_row0 + N) of the layer
 int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M, int conv, int taps, int cin, int w_row0, int N, float* out_f32,
-                __nv_bfloat16* out_bf16, int ldc, int col0, const float* bias, int act, float scale, cudaStream_t s) {
+                __nv_bfloat16* out_bf16, int ldc, int col0, const float* bias, int act, float scale, cudaStream_t s,
+                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr) {
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M;
@@ -137,7 +168,12 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   p.bias = bias;
   p.act = act;
   p.scale = scale;
+  p.gn_gamma = gn_gamma;
+  p.gn_beta = gn_beta;
+  p.pool_part = pool_part;
+  if ((gn_gamma || pool_part) && (w_row0 != 0 || N % 32 != 0)) { m0_set_error("fused epilogue needs the full channel range"); return M0_ERR_ARG; }
   p.cluster = w.cluster;
+  p.fp16 = nn_half_format();
   const int stage_bytes = tc::A_TILE_BYTES + N * tc::BK * 2;
   int stages = (st->max_smem - 2048 - tc::EPI_STAGE_BYTES) / stage_bytes;
   if (stages > 6) stages = 6;
@@ -177,8 +213,20 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   const size_t C = n->cfg.channels;
   if (st->a1) cudaFree(st->a1);
   if (st->a2) cudaFree(st->a2);
+  if (st->pool) cudaFree(st->pool);
+  if (st->se_hid) cudaFree(st->se_hid);
+  if (st->se_gate) cudaFree(st->se_gate);
+  if (st->planes_h) cudaFree(st->planes_h);
   st->a1 = st->a2 = nullptr;
+  st->pool = st->se_hid = st->se_gate = nullptr;
+  st->planes_h = nullptr;
   st->cap = 0;
+  M0_CUDA_TRY(cudaMalloc((void**)&st->pool, (size_t)need * 2 * C * 4));
+  M0_CUDA_TRY(cudaMalloc((void**)&st->se_hid, (size_t)need * (n->cfg.se_hidden > 0 ? n->cfg.se_hidden : 1) * 4));
+  M0_CUDA_TRY(cudaMalloc((void**)&st->se_gate, (size_t)need * C * 4));
+  M0_CUDA_TRY(cudaMalloc((void**)&st->planes_h, (size_t)need * 64 * 64 * 2));
+  M0_CUDA_TRY(cudaMemset(st->planes_h, 0, (size_t)need * 64 * 64 * 2));
+  TRY(make_map_nhwc(&st->planes_conv, st->planes_h, need, 64));
   M0_CUDA_TRY(cudaMalloc((void**)&st->a1, (size_t)need * 64 * C * 2));
   M0_CUDA_TRY(cudaMalloc((void**)&st->a2, (size_t)need * 64 * C * 2));
   M0_CUDA_TRY(cudaMemset(st->a1, 0, (size_t)need * 64 * C * 2));
@@ -195,8 +243,16 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
 
 namespace m0 {
 
+struct TcStates {
+  TcState* st[2] = {nullptr, nullptr};
+};
+
 int tc_net_prepare(::m0_net* n, cudaStream_t s) {
-  if (n->tc) return M0_OK;
+  if (!n->tc) n->tc = new (std::nothrow) TcStates();
+  TcStates* all = (TcStates*)n->tc;
+  if (!all) { m0_set_error("out of host memory"); return M0_ERR_ARG; }
+  const int fmt = nn_half_format();
+  if (all->st[fmt]) return M0_OK;
   const m0_net_config& c = n->cfg;
   if (c.channels % 64 != 0) { m0_set_error("bf16 tensor-core path needs channels %% 64 == 0 (got %d)", c.channels); return M0_ERR_ARG; }
   if (c.channels > 320) { m0_set_error("bf16 tensor-core path supports up to 320 channels (got %d)", c.channels); return M0_ERR_ARG; }
@@ -207,6 +263,26 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
   const int C = c.channels;
   int rc = M0_OK;
   do {
+    {  // stem on tensor cores: input channels zero-padded to 64
+      float* padded = nullptr;
+      if ((rc = m0_check_cuda(cudaMalloc((void**)&padded, (size_t)C * 9 * 64 * 4), "cudaMalloc stem")) != M0_OK) break;
+      st->allocs.push_back(padded);
+      pad_stem_kernel<<<(C * 9 * 64 + 255) / 256, 256, 0, s>>>(n->w.stem_w, padded, C, c.planes);
+      if ((rc = m0_check_launch("pad_stem")) != M0_OK) break;
+      if ((rc = make_weight(st, &st->stem, padded, C, 9 * 64, C, s)) != M0_OK) break;
+    }
+    if (c.se) {
+      st->se_w1x.resize(c.blocks, nullptr);
+      for (int i = 0; i < c.blocks && rc == M0_OK; ++i) {
+        float* wx = nullptr;
+        if ((rc = m0_check_cuda(cudaMalloc((void**)&wx, (size_t)c.se_hidden * 2 * C * 4), "cudaMalloc se")) != M0_OK) break;
+        st->allocs.push_back(wx);
+        st->se_w1x[i] = wx;
+        build_se_w1x_kernel<<<(c.se_hidden * 2 * C + 255) / 256, 256, 0, s>>>(n->w.blocks[i].se_w1, wx, c.se_hidden, C);
+        rc = m0_check_launch("build_se_w1x");
+      }
+      if (rc != M0_OK) break;
+    }
     if (c.chess_features) {
       if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, C, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, C, s)) != M0_OK) break;
@@ -227,63 +303,90 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
     delete st;
     return rc;
   }
-  n->tc = st;
+  all->st[fmt] = st;
   return M0_OK;
 }
 
 void tc_net_release(::m0_net* n) {
-  TcState* st = (TcState*)n->tc;
-  if (!st) return;
-  for (void* p : st->allocs) cudaFree(p);
-  if (st->a1) cudaFree(st->a1);
-  if (st->a2) cudaFree(st->a2);
-  delete st;
+  TcStates* all = (TcStates*)n->tc;
+  if (!all) return;
+  for (int f = 0; f < 2; ++f) {
+    TcState* st = all->st[f];
+    if (!st) continue;
+    for (void* p : st->allocs) cudaFree(p);
+    if (st->a1) cudaFree(st->a1);
+    if (st->a2) cudaFree(st->a2);
+    if (st->pool) cudaFree(st->pool);
+    if (st->se_hid) cudaFree(st->se_hid);
+    if (st->se_gate) cudaFree(st->se_gate);
+    if (st->planes_h) cudaFree(st->planes_h);
+    delete st;
+  }
+  delete all;
   n->tc = nullptr;
 }
 
 int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float* values, cudaStream_t s) {
-  TcState* st = (TcState*)n->tc;
+  TcState* st = ((TcStates*)n->tc)->st[nn_half_format()];
   TRY(net_ws_reserve(n, B));
   TRY(tc_reserve(n, st, B));
   const m0_net_config& c = n->cfg;
   const m0_net_weights& w = n->w;
   const int C = c.channels, M = B * 64, act = c.activation;
-  // stem (K = 9 * 19 = 171 is not a multiple of 64: fp32 SIMT, 0.1 % of the FLOPs) + position encoding
-  TRY(nn_gemm_f32(A_IM2COL_NCHW, planes, w.stem_w, nullptr, nullptr, n->t1, M, C, 9 * c.planes, 0, C, c.planes, ACT_NONE, 1.0f, s));
+  const float* none = nullptr;
+  // stem: planes -> NHWC half (64 channels, zero padded) -> tensor-core conv3x3 -> GN + act (+ position encoding)
+  TRY(nn_planes_to_nhwc_half(planes, st->planes_h, B, c.planes, s));
+  TRY(launch_gemm(st, st->planes_conv, st->stem, M, 1, 9, 64, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
   if (c.chess_features) {
     TRY(nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
     float* cur = n->x;
     if (c.piece_square_tables) {
-      TRY(launch_gemm(st, st->a1_mat, st->pst, M, 0, 1, C, 0, C, n->t1, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+      TRY(launch_gemm(st, st->a1_mat, st->pst, M, 0, 1, C, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
       TRY(nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
       cur = n->t2;
     }
-    TRY(launch_gemm(st, st->a1_conv, st->inter, M, 1, 9, C, 0, C, n->t1, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
+    TRY(launch_gemm(st, st->a1_conv, st->inter, M, 1, 9, C, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
     TRY(nn_groupnorm_mixed(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
   } else {
     TRY(nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
   }
+  // a1 = act(GN1(x)) of the first block; later blocks get it from the fused SE / residual kernel of their predecessor
+  if (c.blocks > 0) TRY(nn_groupnorm_mixed(n->x, w.blocks[0].gn1_w, w.blocks[0].gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));
   int att_seen = 0;
   const int stride = c.infer_attention_stride > 1 ? c.infer_attention_stride : 1;
   for (int i = 0; i < c.blocks; ++i) {
     const m0_block_weights& b = w.blocks[i];
     const TcBlock& tb = st->blocks[i];
-    TRY(nn_groupnorm_mixed(n->x, b.gn1_w, b.gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));
-    TRY(launch_gemm(st, st->a1_conv, tb.conv1, M, 1, 9, C, 0, C, n->t1, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
-    TRY(nn_groupnorm_mixed(n->t1, b.gn2_w, b.gn2_b, nullptr, 0, nullptr, st->a2, B, C, act, s));
-    TRY(launch_gemm(st, st->a2_conv, tb.conv2, M, 1, 9, C, 0, C, n->t2, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
-    TRY(nn_se_residual_f32(n->t2, n->x, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n->x, B, C, c.se_hidden, act, c.se, s));
+    bool run_att = false;
     if (b.has_attention) {
       att_seen++;
-      if (att_seen % stride == 0) {
-        TRY(nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
-        for (int r0 = 0; r0 < 3 * C; r0 += C)
-          TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, nullptr, ACT_NONE, 1.0f, s));
-        TRY(nn_attention_f32(n->qkv, c.attention_relbias ? b.att_rel_bias : nullptr, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
-        TRY(nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
-        TRY(launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, nullptr, ACT_NONE, 1.0f, s));
-        TRY(nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
-      }
+      run_att = (att_seen % stride) == 0;
+    }
+    const bool last = (i + 1 == c.blocks);
+    // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
+    TRY(launch_gemm(st, st->a1_conv, tb.conv1, M, 1, 9, C, 0, C, nullptr, st->a2, C, 0, none, act, 1.0f, s, b.gn2_w, b.gn2_b, nullptr));
+    // conv2 with the SE squeeze (half-board column sums) fused into the epilogue
+    TRY(launch_gemm(st, st->a2_conv, tb.conv2, M, 1, 9, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s, nullptr, nullptr,
+                    c.se ? st->pool : nullptr));
+    const float* gate = nullptr;
+    if (c.se) {
+      TRY(nn_gemm_f32(A_DIRECT, st->pool, st->se_w1x[i], b.se_b1, nullptr, st->se_hid, B, c.se_hidden, 2 * C, 2 * C, c.se_hidden, 0, act, 1.0f, s));
+      TRY(nn_gemm_f32(A_DIRECT, st->se_hid, b.se_w2, b.se_b2, nullptr, st->se_gate, B, C, c.se_hidden, c.se_hidden, C, 0, ACT_SIGMOID, 1.0f, s));
+      gate = st->se_gate;
+    }
+    // x += conv2 * gate ; a1 = act(GN1_{i+1}(x)) unless attention or the heads consume x next
+    const bool fuse_next = !last && !run_att;
+    TRY(nn_se_apply_gn(n->t2, gate, n->x, fuse_next ? w.blocks[i + 1].gn1_w : nullptr, fuse_next ? w.blocks[i + 1].gn1_b : nullptr,
+                       fuse_next ? st->a1 : nullptr, B, C, act, s));
+    if (run_att) {
+      TRY(nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
+      for (int r0 = 0; r0 < 3 * C; r0 += C)
+        TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+      TRY(nn_attention_f32(n->qkv, c.attention_relbias ? b.att_rel_bias : nullptr, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
+      TRY(nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
+      TRY(launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+      TRY(nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
+      if (!last) TRY(nn_groupnorm_mixed(n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));
     }
   }
   return net_forward_heads_f32(n, B, logits, values, s);

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "nn.cuh"
 
 namespace m0 {
@@ -151,8 +152,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
 // n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int fp16 = 0) {
+  const uint32_t fmt = fp16 ? 0u : 1u;  // F16F32Format: 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---- kernel ----------------------------------------------------------------------------------------------------------
@@ -166,6 +168,7 @@ struct GemmParams {
   int w_row0;       // first row of W (output-channel offset of this launch)
   int stages;
   int tmem_cols;    // power of two >= N, >= 32
+  int fp16;         // operands are IEEE fp16 instead of bf16
   int cluster;      // CTAs per cluster (1, 2 or 4): the W tile of a stage is loaded once per cluster and multicast
   // epilogue: out[m][col0 + n] = act(acc + bias[n]) * scale; either output may be null
   float* out_f32;
@@ -174,7 +177,24 @@ struct GemmParams {
   const float* bias;   // indexed by w_row0 + n when non-null
   int act;
   float scale;
+  // fused epilogues (need the full channel range in the tile: w_row0 == 0, N == channels, N % 32 == 0):
+  //   gn_gamma != null : out_bf16 = half(act(GroupNorm_16ch(acc) * gamma + beta)); statistics over the 64 rows of each board
+  //                      (nn.GroupNorm(C/16, C) + activation that follow conv1 in the pre-activation block, resnet.py:49-50)
+  //   pool_part != null: pool_part[(board*2 + half)][n] = sum over the 32 rows of that half board (SE squeeze, resnet.py:61)
+  const float* gn_gamma;
+  const float* gn_beta;
+  float* pool_part;
 };
+
+// two floats -> one 32-bit word of bf16 or fp16 (low half = first value)
+__device__ __forceinline__ uint32_t pack_half2(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 
 __device__ __forceinline__ float tc_act(float x, int act) {
   switch (act) {
@@ -187,7 +207,7 @@ __device__ __forceinline__ float tc_act(float x, int act) {
   }
 }
 
-static constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // one 32x32 fp32 transpose buffer per epilogue warp
+static constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4 + 2 * 320 * 4 + 4 * 20 * 2 * 4;  // 4 transpose buffers + gamma/beta + GN partial sums
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const GemmParams p) {
@@ -197,6 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int w_tile_bytes = p.N * BK * 2;
   const int stage_bytes = A_TILE_BYTES + w_tile_bytes;
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  float* s_gamma = epi_stage + 4 * 32 * 32;   // [320]
+  float* s_beta = s_gamma + 320;              // [320]
+  float* s_stats = s_beta + 320;              // [4 quarters][20 groups][sum, sumsq]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
@@ -269,7 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===== MMA issuer =====
     // The whole warp walks the pipeline (all values stay warp-uniform, so descriptors live in uniform registers);
     // one elected lane issues the tcgen05 instructions.
-    const uint32_t idesc = make_idesc_bf16(BM, p.n_part);
+    const uint32_t idesc = make_idesc_bf16(BM, p.n_part, p.fp16);
     const uint32_t part_bytes = (uint32_t)(p.n_part * BK * 2);
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
@@ -312,16 +335,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int quarter = warp & 3;            // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
     float* stg = epi_stage + quarter * (32 * 32);
     const bool plain = (p.bias == nullptr) && (p.act == ACT_NONE) && (p.scale == 1.0f);
+    const bool fused_gn = p.gn_gamma != nullptr;
+    const int epi_tid = (quarter << 5) | lane;   // 0..127
+    if (fused_gn) {
+      for (int c = epi_tid; c < p.N; c += 128) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     uint32_t acc_phase = 0;
     for (int g = cluster_id; g < num_groups; g += num_clusters) {
       mbar_wait(tmem_full_bar, acc_phase);
       tc_fence_after();
       const int tile_row0 = (g * cs + rank) * BM + quarter * 32;
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      if (fused_gn) {
+        // pass 1: per (half board = this warp, group of 16 channels) sum and sum of squares
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
+          tmem_ld_wait();
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(r[j]), b = __uint_as_float(r[16 + j]);
+            s0 += a; q0 = fmaf(a, a, q0);
+            s1 += b; q1 = fmaf(b, b, q1);
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, off); q0 += __shfl_xor_sync(0xFFFFFFFFu, q0, off);
+            s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, off); q1 += __shfl_xor_sync(0xFFFFFFFFu, q1, off);
+          }
+          if (lane == 0) {
+            float* st = s_stats + (quarter * 20 + (c0 >> 4)) * 2;
+            st[0] = s0; st[1] = q0; st[2] = s1; st[3] = q1;
+          }
+        }
+        // the two warps that hold one board (quarters 2b, 2b+1) exchange their partial sums
+        if (quarter < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+        else asm volatile("bar.sync 3, 64;" ::: "memory");
+      }
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (!plain) {
+        if (fused_gn) {
+          const int act = p.act;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int grp = (c0 >> 4) + h;
+            const float* sa = s_stats + ((quarter & 2) * 20 + grp) * 2;
+            const float* sb = s_stats + ((quarter | 1) * 20 + grp) * 2;
+            const float mean = (sa[0] + sb[0]) * (1.0f / 1024.0f);
+            const float var = fmaxf((sa[1] + sb[1]) * (1.0f / 1024.0f) - mean * mean, 0.0f);
+            const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + h * 16 + j;
+              const float gm = s_gamma[c] * rstd;
+              const float y = fmaf(__uint_as_float(r[h * 16 + j]) - mean, gm, s_beta[c]);
+              r[h * 16 + j] = __float_as_uint(tc_act(y, act));
+            }
+          }
+        } else if (!plain) {
           const float* bias = p.bias ? p.bias + p.w_row0 + c0 : nullptr;
           const int act = p.act;
           const float scale = p.scale;
@@ -338,6 +413,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
         __syncwarp();
         const int ncols = (p.N - c0) < 32 ? (p.N - c0) : 32;
+        if (p.pool_part && tile_row0 < p.M && lane < ncols) {
+          // column sums of this half board (lane = column): conflict-free reads of the swizzled buffer
+          float cs_sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) cs_sum += stg[i * 32 + ((((lane >> 2) ^ (i & 7)) << 2) | (lane & 3))];
+          p.pool_part[(size_t)(tile_row0 >> 5) * p.N + c0 + lane] = cs_sum;
+        }
         if (p.out_f32) {
           // 8 lanes cover the 128 contiguous bytes of one row: each store instruction writes 4 full lines
           const int q = lane & 7;
@@ -352,7 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         if (p.out_bf16) {
-          // 4 lanes cover the 64 contiguous bytes of one row (8 bf16 per lane)
+          // 4 lanes cover the 64 contiguous bytes of one row (8 half-precision values per lane)
           const int q2 = lane & 3;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -361,11 +443,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (m < p.M && 8 * q2 < ncols) {
               float4 lo = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * q2) ^ (rr & 7)) << 2));
               float4 hi = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * q2 + 1) ^ (rr & 7)) << 2));
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(lo.x, lo.y), t1 = __floats2bfloat162_rn(lo.z, lo.w);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(hi.x, hi.y), t3 = __floats2bfloat162_rn(hi.z, hi.w);
               uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
+              pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
               *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldc + p.col0 + c0 + 8 * q2) = pk;
             }
           }

@@ -145,7 +145,7 @@ def parameter_shapes(cfg: NetConfig) -> Dict[str, Tuple[int, ...]]:
 
 
 class PolicyValueNet:
-    def __init__(self, cfg: NetConfig, device: Optional[str] = None, precision: str = "bf16", seed: Optional[int] = None):
+    def __init__(self, cfg: NetConfig, device: Optional[str] = None, precision: str = "fp16", seed: Optional[int] = None):
         import torch
         if cfg.policy_size != 4672:
             raise ValueError(f"Unsupported policy_size={cfg.policy_size}. Matrix0 currently supports legacy 4672 only")  # resnet.py:302-306
@@ -352,7 +352,7 @@ class PolicyValueNet:
         B = planes.shape[0]
         logits = torch.empty((B, self.cfg.policy_size), dtype=torch.float32, device=planes.device)
         values = torch.empty((B,), dtype=torch.float32, device=planes.device)
-        prec = 1 if (precision or self.precision) == "bf16" else 0
+        prec = {"fp32": 0, "bf16": 1, "fp16": 2}[precision or self.precision]
         if B == 0:
             return logits, values
         with torch.cuda.device(planes.device):

@@ -56,18 +56,36 @@ def test_fp32_batch_invariance_and_api(golden_dir):
     assert net.forward(x[:0])[0].shape == (0, 4672)                    # empty batch
 
 
-@pytest.mark.parametrize("name", ["small", "r24"])
-def test_bf16_path_agreement(golden_dir, name):
+def _agreement(golden_dir, name, precision):
     g, cfg, sd = load_case(golden_dir, name)
-    net = make_net(cfg, sd, "bf16")
+    net = make_net(cfg, sd, precision)
     from conftest import random_playout_boards
-    from oracle.encoding_ref import encode_board
-    boards = random_playout_boards(8, 120, seed=31)[:: 3][:192]
+    from oracle.encoding_ref import encode_board, get_legal_actions
+    boards = random_playout_boards(20, 120, seed=31)[:: 3][:320]
     x = torch.from_numpy(np.stack([encode_board(b) for b in boards]))
+    legal = torch.from_numpy(np.stack([get_legal_actions(b) for b in boards])).cuda()
     p, v = net.forward(x)
     f32 = make_net(cfg, sd, "fp32")
-    pr, vr = f32.forward(x)                                            # fp32 CUDA path == reference within 1e-4 (test above)
-    top1 = (p.argmax(1) == pr.argmax(1)).float().mean().item()
-    dv = (v - vr).abs().max().item()
-    assert top1 >= 0.99, top1
+    pr, vr = f32.forward(x)                                            # fp32 CUDA path == reference within 1e-4 (tests above)
+    neg = torch.full_like(pr, -1e30)
+    top1_all = (p.argmax(1) == pr.argmax(1)).float().mean().item()
+    top1_legal = (torch.where(legal, p, neg).argmax(1) == torch.where(legal, pr, neg).argmax(1)).float().mean().item()
+    return top1_all, top1_legal, (v - vr).abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["small", "r24"])
+def test_fp16_tensor_core_path_meets_the_gate(golden_dir, name):
+    """The throughput path: fp16 operands (the reference's own inference dtype: torch.autocast(float16), resnet.py:676-677 and
+    mcts.py:679-683), fp32 accumulation in tensor memory.  Gate of BASELINE north_star for the reduced-precision path:
+    >= 99 % top-1 policy agreement (over all 4672 logits and over the legal moves) and |delta value| <= 2e-2."""
+    top1_all, top1_legal, dv = _agreement(golden_dir, name, "fp16")
+    assert top1_all >= 0.99 and top1_legal >= 0.99, (top1_all, top1_legal)
     assert dv <= 2e-2, dv
+
+
+def test_bf16_operands_are_measurably_worse(golden_dir):
+    """bf16 operands (8-bit mantissa) run at the same tensor-core rate but do NOT meet the gate on this 24-block trunk with
+    the synthetic weights (measured on B200: 95 % / 97 % top-1, |dv| 0.05), which is why fp16 is the default.  The path is kept
+    selectable; this test only pins that it stays sane."""
+    top1_all, top1_legal, dv = _agreement(golden_dir, "r24", "bf16")
+    assert top1_legal >= 0.90 and dv <= 0.15, (top1_all, top1_legal, dv)
