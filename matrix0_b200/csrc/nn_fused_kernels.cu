@@ -33,14 +33,22 @@ se_apply_gn_kernel(const float* __restrict__ conv_out, const float* __restrict__
   const float e = gate ? gate[(size_t)b * C + c] : 1.0f;
   float v[64];
   float s = 0.0f;
+  // all loads first (x is read and written through the same pointer: keep the stores out of the load stream)
+#pragma unroll
+  for (int sq = 0; sq < 64; ++sq) v[sq] = __ldg(conv_out + base + (size_t)sq * C);
+#pragma unroll
+  for (int sq = 0; sq < 64; ++sq) v[sq] = fmaf(v[sq], e, x[base + (size_t)sq * C]);
 #pragma unroll
   for (int sq = 0; sq < 64; ++sq) {
-    float y = fmaf(conv_out[base + (size_t)sq * C], e, x[base + (size_t)sq * C]);
-    v[sq] = y;
-    s += y;
-    x[base + (size_t)sq * C] = y;
+    s += v[sq];
+    x[base + (size_t)sq * C] = v[sq];
   }
   if (!a_out) return;
+  if (!gamma) {  // the next consumer is the attention qkv GEMM: it takes the raw residual stream in half precision
+#pragma unroll
+    for (int sq = 0; sq < 64; ++sq) a_out[base + (size_t)sq * C] = fk_half(v[sq], fp16);
+    return;
+  }
 #pragma unroll
   for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
   const float mean = s * (1.0f / 1024.0f);
@@ -66,6 +74,51 @@ __global__ void planes_to_nhwc_half_kernel(const float* __restrict__ planes, __n
   const int sq = (int)((i >> 6) & 63);
   const size_t b = i >> 12;
   out[i] = c < P ? fk_half(planes[(b * P + c) * 64 + sq], fp16) : fk_half(0.0f, fp16);
+}
+
+// SE excitation for 16 boards per block (resnet.py:61-64): s = avgpool, h = act(W1 s + b1), gate = sigmoid(W2 h + b2).
+// pool: half-board column sums [B][2][C]; w1t [C][hid] and w2t [hid][C] are transposed so that threads read them coalesced.
+__global__ void __launch_bounds__(320)
+se_gate_kernel(const float* __restrict__ pool, const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
+               const float* __restrict__ b2, float* __restrict__ gate, int B, int C, int hid, int act) {
+  extern __shared__ float sm[];
+  float* s_pool = sm;              // [16][C]
+  float* s_hid = sm + 16 * C;      // [16][hid]
+  const int b0 = blockIdx.x * 16, t = threadIdx.x;
+  const int nb = min(16, B - b0);
+  for (int i = t; i < nb * C; i += blockDim.x) {
+    const int j = i / C, c = i - j * C;
+    const float* pp = pool + (size_t)(b0 + j) * 2 * C;
+    s_pool[j * C + c] = (pp[c] + pp[C + c]) * (1.0f / 64.0f);
+  }
+  __syncthreads();
+  for (int o = t; o < nb * hid; o += blockDim.x) {
+    const int j = o / hid, u = o - j * hid;
+    float h = b1[u];
+    const float* sp = s_pool + j * C;
+    for (int c = 0; c < C; ++c) h = fmaf(w1t[c * hid + u], sp[c], h);
+    s_hid[j * hid + u] = fk_act(h, act);
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += blockDim.x) {
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = b2[c];
+    for (int u = 0; u < hid; ++u) {
+      const float w = w2t[u * C + c];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = fmaf(w, s_hid[j * hid + u], z[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nb) gate[(size_t)(b0 + j) * C + c] = 1.0f / (1.0f + __expf(-z[j]));
+  }
+}
+
+int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float* w2t, const float* b2, float* gate, int B, int C, int hid, int act,
+               cudaStream_t s) {
+  se_gate_kernel<<<(B + 15) / 16, 320, (size_t)16 * (C + hid) * sizeof(float), s>>>(pool, w1t, b1, w2t, b2, gate, B, C, hid, act);
+  return m0_check_launch("se_gate");
 }
 
 int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,

@@ -14,15 +14,18 @@ namespace m0 {
 int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
                    int C, int act, cudaStream_t s);
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s);
+int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half, int B, int C, int heads, float mix, cudaStream_t s);
+int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float* w2t, const float* b2, float* gate, int B, int C, int hid, int act,
+               cudaStream_t s);
 }  // namespace m0
 
 namespace m0 {
-// W1x[h][half*C + c] = W1[h][c] / 64 for both halves: the SE squeeze then reads the half-board sums directly
-__global__ void build_se_w1x_kernel(const float* __restrict__ w1, float* __restrict__ out, int hid, int C) {
+// out[c][r] = in[r][c]  (SE weights are read coalesced by the gate kernel)
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hid * 2 * C) return;
-  int h = i / (2 * C), c = i % C;
-  out[i] = w1[h * C + c] * (1.0f / 64.0f);
+  if (i >= rows * cols) return;
+  int r = i / cols, c = i % cols;
+  out[c * rows + r] = in[i];
 }
 // stem weights [C][9][P] -> [C][9][64] (zero padded input channels)
 __global__ void pad_stem_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int P) {
@@ -106,9 +109,10 @@ struct TcState {
   std::vector<TcBlock> blocks;
   // SE: pooled half-board sums [cap][2][C], hidden [cap][hid], gate [cap][C]; W1 duplicated over the two halves and scaled by 1/64
   float *pool = nullptr, *se_hid = nullptr, *se_gate = nullptr;
-  std::vector<float*> se_w1x;   // per block [hid][2C]
+  std::vector<float*> se_w1t, se_w2t;   // per block [C][hid], [hid][C]
   // stem on tensor cores: planes as NHWC half with 64 channels, weights [C][9*64]
   __nv_bfloat16* planes_h = nullptr;
+  __nv_bfloat16* qkv_h = nullptr;   // [cap][64][3C] half (attention input)
   CUtensorMap planes_conv;
   TcWeight stem;
   // bf16 activation buffers [cap][64][C] and their maps
@@ -217,6 +221,8 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   if (st->se_hid) cudaFree(st->se_hid);
   if (st->se_gate) cudaFree(st->se_gate);
   if (st->planes_h) cudaFree(st->planes_h);
+  if (st->qkv_h) cudaFree(st->qkv_h);
+  st->qkv_h = nullptr;
   st->a1 = st->a2 = nullptr;
   st->pool = st->se_hid = st->se_gate = nullptr;
   st->planes_h = nullptr;
@@ -225,6 +231,7 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   M0_CUDA_TRY(cudaMalloc((void**)&st->se_hid, (size_t)need * (n->cfg.se_hidden > 0 ? n->cfg.se_hidden : 1) * 4));
   M0_CUDA_TRY(cudaMalloc((void**)&st->se_gate, (size_t)need * C * 4));
   M0_CUDA_TRY(cudaMalloc((void**)&st->planes_h, (size_t)need * 64 * 64 * 2));
+  M0_CUDA_TRY(cudaMalloc((void**)&st->qkv_h, (size_t)need * 64 * 3 * C * 2));
   M0_CUDA_TRY(cudaMemset(st->planes_h, 0, (size_t)need * 64 * 64 * 2));
   TRY(make_map_nhwc(&st->planes_conv, st->planes_h, need, 64));
   M0_CUDA_TRY(cudaMalloc((void**)&st->a1, (size_t)need * 64 * C * 2));
@@ -272,14 +279,20 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
       if ((rc = make_weight(st, &st->stem, padded, C, 9 * 64, C, s)) != M0_OK) break;
     }
     if (c.se) {
-      st->se_w1x.resize(c.blocks, nullptr);
+      st->se_w1t.resize(c.blocks, nullptr);
+      st->se_w2t.resize(c.blocks, nullptr);
+      const int hc = c.se_hidden * C;
       for (int i = 0; i < c.blocks && rc == M0_OK; ++i) {
-        float* wx = nullptr;
-        if ((rc = m0_check_cuda(cudaMalloc((void**)&wx, (size_t)c.se_hidden * 2 * C * 4), "cudaMalloc se")) != M0_OK) break;
-        st->allocs.push_back(wx);
-        st->se_w1x[i] = wx;
-        build_se_w1x_kernel<<<(c.se_hidden * 2 * C + 255) / 256, 256, 0, s>>>(n->w.blocks[i].se_w1, wx, c.se_hidden, C);
-        rc = m0_check_launch("build_se_w1x");
+        float *w1t = nullptr, *w2t = nullptr;
+        if ((rc = m0_check_cuda(cudaMalloc((void**)&w1t, (size_t)hc * 4), "cudaMalloc se")) != M0_OK) break;
+        st->allocs.push_back(w1t);
+        if ((rc = m0_check_cuda(cudaMalloc((void**)&w2t, (size_t)hc * 4), "cudaMalloc se")) != M0_OK) break;
+        st->allocs.push_back(w2t);
+        st->se_w1t[i] = w1t;
+        st->se_w2t[i] = w2t;
+        transpose_f32_kernel<<<(hc + 255) / 256, 256, 0, s>>>(n->w.blocks[i].se_w1, w1t, c.se_hidden, C);   // [hid][C] -> [C][hid]
+        transpose_f32_kernel<<<(hc + 255) / 256, 256, 0, s>>>(n->w.blocks[i].se_w2, w2t, C, c.se_hidden);   // [C][hid] -> [hid][C]
+        rc = m0_check_launch("transpose_se");
       }
       if (rc != M0_OK) break;
     }
@@ -320,6 +333,7 @@ void tc_net_release(::m0_net* n) {
     if (st->se_hid) cudaFree(st->se_hid);
     if (st->se_gate) cudaFree(st->se_gate);
     if (st->planes_h) cudaFree(st->planes_h);
+    if (st->qkv_h) cudaFree(st->qkv_h);
     delete st;
   }
   delete all;
@@ -370,20 +384,26 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
                     c.se ? st->pool : nullptr));
     const float* gate = nullptr;
     if (c.se) {
-      TRY(nn_gemm_f32(A_DIRECT, st->pool, st->se_w1x[i], b.se_b1, nullptr, st->se_hid, B, c.se_hidden, 2 * C, 2 * C, c.se_hidden, 0, act, 1.0f, s));
-      TRY(nn_gemm_f32(A_DIRECT, st->se_hid, b.se_w2, b.se_b2, nullptr, st->se_gate, B, C, c.se_hidden, c.se_hidden, C, 0, ACT_SIGMOID, 1.0f, s));
+      TRY(nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
       gate = st->se_gate;
     }
-    // x += conv2 * gate ; a1 = act(GN1_{i+1}(x)) unless attention or the heads consume x next
+    // x += conv2 * gate ; a1 = act(GN1_{i+1}(x)), or half(x) when the attention qkv GEMM consumes x next
     const bool fuse_next = !last && !run_att;
+    const bool tc_att = run_att && C == c.attention_heads * 16;
     TRY(nn_se_apply_gn(n->t2, gate, n->x, fuse_next ? w.blocks[i + 1].gn1_w : nullptr, fuse_next ? w.blocks[i + 1].gn1_b : nullptr,
-                       fuse_next ? st->a1 : nullptr, B, C, act, s));
+                       (fuse_next || run_att) ? st->a1 : nullptr, B, C, act, s));
     if (run_att) {
-      TRY(nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
-      for (int r0 = 0; r0 < 3 * C; r0 += C)
-        TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, none, ACT_NONE, 1.0f, s));
-      TRY(nn_attention_f32(n->qkv, c.attention_relbias ? b.att_rel_bias : nullptr, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
-      TRY(nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
+      const float* rb = c.attention_relbias ? b.att_rel_bias : nullptr;
+      if (tc_att) {
+        for (int r0 = 0; r0 < 3 * C; r0 += C)
+          TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, nullptr, st->qkv_h, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+        TRY(nn_attention_tc(st->qkv_h, rb, st->a2, B, C, c.attention_heads, c.attention_unmasked_mix, s));
+      } else {
+        for (int r0 = 0; r0 < 3 * C; r0 += C)
+          TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+        TRY(nn_attention_f32(n->qkv, rb, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
+        TRY(nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
+      }
       TRY(launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
       TRY(nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
       if (!last) TRY(nn_groupnorm_mixed(n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));

@@ -25,7 +25,7 @@ namespace tc {
 static constexpr int BM = 128;          // rows per tile (2 boards)
 static constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 static constexpr int A_TILE_BYTES = BM * BK * 2;
-static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -207,7 +207,7 @@ __device__ __forceinline__ float tc_act(float x, int act) {
   }
 }
 
-static constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4 + 2 * 320 * 4 + 4 * 20 * 2 * 4;  // 4 transpose buffers + gamma/beta + GN partial sums
+static constexpr int EPI_STAGE_BYTES = 8 * 32 * 32 * 4 + 2 * 320 * 4 + 4 * 20 * 2 * 4;  // 8 transpose buffers + gamma/beta + GN partial sums
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const GemmParams p) {
@@ -217,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int w_tile_bytes = p.N * BK * 2;
   const int stage_bytes = A_TILE_BYTES + w_tile_bytes;
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  float* s_gamma = epi_stage + 4 * 32 * 32;   // [320]
+  float* s_gamma = epi_stage + 8 * 32 * 32;   // [320]
   float* s_beta = s_gamma + 320;              // [320]
   float* s_stats = s_beta + 320;              // [4 quarters][20 groups][sum, sumsq]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + EPI_STAGE_BYTES);
@@ -246,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&empty_bar[s], (uint32_t)cs);   // every CTA of the cluster must have consumed the stage
     }
     mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 128);
+    mbar_init(tmem_empty_bar, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -333,13 +333,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     // ===== epilogue: TMEM -> registers -> (bias / activation) -> smem transpose -> coalesced global stores =====
     const int quarter = warp & 3;            // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
-    float* stg = epi_stage + quarter * (32 * 32);
+    const int cset = (warp - 2) >> 2;        // the two warps of a quarter take alternate 32-column chunks
+    float* stg = epi_stage + (warp - 2) * (32 * 32);
     const bool plain = (p.bias == nullptr) && (p.act == ACT_NONE) && (p.scale == 1.0f);
     const bool fused_gn = p.gn_gamma != nullptr;
-    const int epi_tid = (quarter << 5) | lane;   // 0..127
+    const int epi_tid = ((warp - 2) << 5) | lane;   // 0..255
     if (fused_gn) {
-      for (int c = epi_tid; c < p.N; c += 128) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = epi_tid; c < p.N; c += 256) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     uint32_t acc_phase = 0;
     for (int g = cluster_id; g < num_groups; g += num_clusters) {
@@ -349,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
       if (fused_gn) {
         // pass 1: per (half board = this warp, group of 16 channels) sum and sum of squares
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
+        for (int c0 = cset * 32; c0 < p.N; c0 += 64) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
           tmem_ld_wait();
@@ -371,10 +372,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         // the two warps that hold one board (quarters 2b, 2b+1) exchange their partial sums
-        if (quarter < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
-        else asm volatile("bar.sync 3, 64;" ::: "memory");
+        if (quarter < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
       }
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
+      for (int c0 = cset * 32; c0 < p.N; c0 += 64) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
         tmem_ld_wait();
