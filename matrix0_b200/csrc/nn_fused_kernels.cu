@@ -21,49 +21,75 @@ __device__ __forceinline__ __nv_bfloat16 fk_half(float x, int fp16) {
 }
 
 // x_new = x + conv_out * gate   (SE excitation + residual add, resnet.py:68-80)
-// a_out = half(act(GroupNorm(x_new)))   (bn1 + activation of the NEXT pre-activation block, resnet.py:46-47), optional
-// One block per board, one thread per channel; the thread keeps its 64 values in registers, so x and conv_out are
-// read once and x_new / a_out written once.
-template <int C_MAX_UNUSED>
-__global__ void __launch_bounds__(320)
+// a_out = half(act(GroupNorm(x_new)))   (bn1 + activation of the NEXT pre-activation block, resnet.py:46-47), or half(x_new) when
+// gamma is null, or nothing when a_out is null.
+// One block per board.  Thread (rg, q) owns 4 consecutive channels (one float4) of 16 rows: x and conv_out are read once with
+// 16-byte loads, x_new / a_out written once.  GroupNorm statistics: 4 threads (= 16 channels) x 4 row groups per group.
+__global__ void __launch_bounds__(320, 2)
 se_apply_gn_kernel(const float* __restrict__ conv_out, const float* __restrict__ gate, float* __restrict__ x,
                    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ a_out, int C, int act, int fp16) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  const size_t base = (size_t)b * 64 * C + c;
-  const float e = gate ? gate[(size_t)b * C + c] : 1.0f;
-  float v[64];
-  float s = 0.0f;
-  // all loads first (x is read and written through the same pointer: keep the stores out of the load stream)
+  __shared__ float s_part[4][80][2];
+  const int b = blockIdx.x;
+  const int nq = C >> 2;                       // float4 columns (<= 80)
+  const int q = threadIdx.x % nq, rg = threadIdx.x / nq;   // rg < 4 when blockDim == 4 * nq
+  const size_t base = (size_t)b * 64 * C + (size_t)rg * 16 * C + 4 * q;
+  float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (gate) e = *reinterpret_cast<const float4*>(gate + (size_t)b * C + 4 * q);
+  float4 v[16];
+  if (conv_out) {
 #pragma unroll
-  for (int sq = 0; sq < 64; ++sq) v[sq] = __ldg(conv_out + base + (size_t)sq * C);
+    for (int r = 0; r < 16; ++r) v[r] = __ldg(reinterpret_cast<const float4*>(conv_out + base + (size_t)r * C));
 #pragma unroll
-  for (int sq = 0; sq < 64; ++sq) v[sq] = fmaf(v[sq], e, x[base + (size_t)sq * C]);
+    for (int r = 0; r < 16; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
+      v[r].x = fmaf(v[r].x, e.x, xv.x); v[r].y = fmaf(v[r].y, e.y, xv.y);
+      v[r].z = fmaf(v[r].z, e.z, xv.z); v[r].w = fmaf(v[r].w, e.w, xv.w);
+    }
 #pragma unroll
-  for (int sq = 0; sq < 64; ++sq) {
-    s += v[sq];
-    x[base + (size_t)sq * C] = v[sq];
+    for (int r = 0; r < 16; ++r) *reinterpret_cast<float4*>(x + base + (size_t)r * C) = v[r];
+  } else {   // plain GroupNorm of x: nothing to add, nothing to write back
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
   }
   if (!a_out) return;
+  __nv_bfloat16* ao = a_out + base;
   if (!gamma) {  // the next consumer is the attention qkv GEMM: it takes the raw residual stream in half precision
 #pragma unroll
-    for (int sq = 0; sq < 64; ++sq) a_out[base + (size_t)sq * C] = fk_half(v[sq], fp16);
+    for (int r = 0; r < 16; ++r) {
+      __nv_bfloat16 h4[4] = {fk_half(v[r].x, fp16), fk_half(v[r].y, fp16), fk_half(v[r].z, fp16), fk_half(v[r].w, fp16)};
+      *reinterpret_cast<uint2*>(ao + (size_t)r * C) = *reinterpret_cast<uint2*>(h4);
+    }
     return;
   }
+  float s = 0.f;
 #pragma unroll
-  for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
-  const float mean = s * (1.0f / 1024.0f);
-  float q = 0.0f;
+  for (int r = 0; r < 16; ++r) s += (v[r].x + v[r].y) + (v[r].z + v[r].w);
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);   // 4 adjacent threads = one group of 16 channels (nq % 4 == 0, warps hold whole groups)
+  s_part[rg][q][0] = s;
+  __syncthreads();
+  const float mean = (s_part[0][q][0] + s_part[1][q][0] + s_part[2][q][0] + s_part[3][q][0]) * (1.0f / 1024.0f);
+  float d2 = 0.f;
 #pragma unroll
-  for (int sq = 0; sq < 64; ++sq) {
-    float d = v[sq] - mean;
-    q = fmaf(d, d, q);
+  for (int r = 0; r < 16; ++r) {
+    float a0 = v[r].x - mean, a1 = v[r].y - mean, a2 = v[r].z - mean, a3 = v[r].w - mean;
+    d2 = fmaf(a0, a0, d2); d2 = fmaf(a1, a1, d2); d2 = fmaf(a2, a2, d2); d2 = fmaf(a3, a3, d2);
   }
+  d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 1);
+  d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 2);
+  s_part[rg][q][1] = d2;
+  __syncthreads();
+  const float var = (s_part[0][q][1] + s_part[1][q][1] + s_part[2][q][1] + s_part[3][q][1]) * (1.0f / 1024.0f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + 4 * q), bt = *reinterpret_cast<const float4*>(beta + 4 * q);
+  const float g0 = gm.x * rstd, g1 = gm.y * rstd, g2 = gm.z * rstd, g3 = gm.w * rstd;
+  const float b0 = bt.x - mean * g0, b1 = bt.y - mean * g1, b2 = bt.z - mean * g2, b3 = bt.w - mean * g3;
 #pragma unroll
-  for (int off = 8; off > 0; off >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, off);
-  const float rstd = rsqrtf(q * (1.0f / 1024.0f) + 1e-5f);
-  const float g = gamma[c] * rstd, bb = beta[c] - mean * g;
-#pragma unroll
-  for (int sq = 0; sq < 64; ++sq) a_out[base + (size_t)sq * C] = fk_half(fk_act(fmaf(v[sq], g, bb), act), fp16);
+  for (int r = 0; r < 16; ++r) {
+    __nv_bfloat16 h4[4] = {fk_half(fk_act(fmaf(v[r].x, g0, b0), act), fp16), fk_half(fk_act(fmaf(v[r].y, g1, b1), act), fp16),
+                           fk_half(fk_act(fmaf(v[r].z, g2, b2), act), fp16), fk_half(fk_act(fmaf(v[r].w, g3, b3), act), fp16)};
+    *reinterpret_cast<uint2*>(ao + (size_t)r * C) = *reinterpret_cast<uint2*>(h4);
+  }
 }
 
 // NCHW float32 planes [B][P][8][8] -> NHWC half [B][64][64] with channels P..63 zero (stem input of the tensor-core path)
@@ -124,7 +150,8 @@ int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float
 int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
                    int C, int act, cudaStream_t s) {
   if (C > 320 || C % 32 != 0) { m0_set_error("se_apply_gn: unsupported channel count %d", C); return M0_ERR_ARG; }
-  se_apply_gn_kernel<0><<<B, C, 0, s>>>(conv_out, gate, x, gamma, beta, a_out, C, act, nn_half_format());
+  if (C % 16 != 0) { m0_set_error("se_apply_gn: channels must be a multiple of 16"); return M0_ERR_ARG; }
+  se_apply_gn_kernel<<<B, C, 0, s>>>(conv_out, gate, x, gamma, beta, a_out, C, act, nn_half_format());
   return m0_check_launch("se_apply_gn");
 }
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s) {

@@ -113,6 +113,12 @@ struct TcState {
   // stem on tensor cores: planes as NHWC half with 64 channels, weights [C][9*64]
   __nv_bfloat16* planes_h = nullptr;
   __nv_bfloat16* qkv_h = nullptr;   // [cap][64][3C] half (attention input)
+  // heads on tensor cores
+  bool heads_tc = false;
+  TcWeight pol_conv, pol_fc1, pol_fc2, val_conv1, val_conv2, val_fc1;
+  int pol_rank_pad = 0;
+  __nv_bfloat16 *ph_h = nullptr, *pf_h = nullptr, *vh_h = nullptr;   // [cap][4096], [cap][rank_pad], [cap][64][128]
+  CUtensorMap ph_mat, pf_mat, vh_conv_mat, vh_fc_mat;
   CUtensorMap planes_conv;
   TcWeight stem;
   // bf16 activation buffers [cap][64][C] and their maps
@@ -153,11 +159,12 @@ int pow2_cols(int n) {
 // one launch of the tensor-core GEMM: rows [0, M), output columns [w_row0, w_row0 + N) of the layer
 int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M, int conv, int taps, int cin, int w_row0, int N, float* out_f32,
                 __nv_bfloat16* out_bf16, int ldc, int col0, const float* bias, int act, float scale, cudaStream_t s,
-                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr) {
+                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr, int n_store = -1) {
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M;
   p.N = N;
+  p.n_store = n_store >= 0 ? n_store : N;
   if (w.n_part > N || N % w.n_part != 0) { m0_set_error("tensor-core GEMM: launch width %d does not match the weight map box %d", N, w.n_part); return M0_ERR_ARG; }
   p.n_part = w.n_part;
   p.taps = taps;
@@ -222,7 +229,10 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   if (st->se_gate) cudaFree(st->se_gate);
   if (st->planes_h) cudaFree(st->planes_h);
   if (st->qkv_h) cudaFree(st->qkv_h);
-  st->qkv_h = nullptr;
+  if (st->ph_h) cudaFree(st->ph_h);
+  if (st->pf_h) cudaFree(st->pf_h);
+  if (st->vh_h) cudaFree(st->vh_h);
+  st->qkv_h = st->ph_h = st->pf_h = st->vh_h = nullptr;
   st->a1 = st->a2 = nullptr;
   st->pool = st->se_hid = st->se_gate = nullptr;
   st->planes_h = nullptr;
@@ -232,6 +242,17 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   M0_CUDA_TRY(cudaMalloc((void**)&st->se_gate, (size_t)need * C * 4));
   M0_CUDA_TRY(cudaMalloc((void**)&st->planes_h, (size_t)need * 64 * 64 * 2));
   M0_CUDA_TRY(cudaMalloc((void**)&st->qkv_h, (size_t)need * 64 * 3 * C * 2));
+  if (st->heads_tc) {
+    const size_t rp = (size_t)st->pol_rank_pad;
+    M0_CUDA_TRY(cudaMalloc((void**)&st->ph_h, (size_t)need * 4096 * 2));
+    M0_CUDA_TRY(cudaMalloc((void**)&st->pf_h, (size_t)need * rp * 2));
+    M0_CUDA_TRY(cudaMalloc((void**)&st->vh_h, (size_t)need * 8192 * 2));
+    M0_CUDA_TRY(cudaMemset(st->pf_h, 0, (size_t)need * rp * 2));   // padding columns stay zero
+    TRY(make_map_2d(&st->ph_mat, st->ph_h, (uint64_t)need, 4096, 128));
+    TRY(make_map_2d(&st->pf_mat, st->pf_h, (uint64_t)need, rp, 128));
+    TRY(make_map_2d(&st->vh_conv_mat, st->vh_h, (uint64_t)need * 64, 128, 128));
+    TRY(make_map_2d(&st->vh_fc_mat, st->vh_h, (uint64_t)need, 8192, 128));
+  }
   M0_CUDA_TRY(cudaMemset(st->planes_h, 0, (size_t)need * 64 * 64 * 2));
   TRY(make_map_nhwc(&st->planes_conv, st->planes_h, need, 64));
   M0_CUDA_TRY(cudaMalloc((void**)&st->a1, (size_t)need * 64 * C * 2));
@@ -296,6 +317,25 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
       }
       if (rc != M0_OK) break;
     }
+    if (c.policy_factor_rank > 0 && c.policy_factor_rank % 16 == 0 && c.policy_factor_rank <= 320) {
+      // heads: 1x1 convolutions and the wide fully connected layers as tensor-core GEMMs
+      const int r = c.policy_factor_rank, rp = (r + 63) / 64 * 64;
+      st->pol_rank_pad = rp;
+      float* w2p = nullptr;   // policy_fc2 weights with the K dimension zero-padded to a multiple of 64
+      const int ps_pad = (c.policy_size + 319) / 320 * 320;   // whole 320-column launches; the padding rows are zero
+      if ((rc = m0_check_cuda(cudaMalloc((void**)&w2p, (size_t)ps_pad * rp * 4), "cudaMalloc pol_fc2")) != M0_OK) break;
+      st->allocs.push_back(w2p);
+      if ((rc = m0_check_cuda(cudaMemsetAsync(w2p, 0, (size_t)ps_pad * rp * 4, s), "memset")) != M0_OK) break;
+      if ((rc = m0_check_cuda(cudaMemcpy2DAsync(w2p, (size_t)rp * 4, n->w.pol_fc2_w, (size_t)r * 4, (size_t)r * 4, c.policy_size,
+                                                cudaMemcpyDeviceToDevice, s), "pad pol_fc2")) != M0_OK) break;
+      if ((rc = make_weight(st, &st->pol_conv, n->w.pol_conv_w, 64, C, 64, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->pol_fc1, n->w.pol_fc1_w, r, 4096, r, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->pol_fc2, w2p, ps_pad, rp, 320, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->val_conv1, n->w.val_conv1_w, 128, C, 128, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->val_conv2, n->w.val_conv2_w, 128, 128, 128, s)) != M0_OK) break;
+      if ((rc = make_weight(st, &st->val_fc1, n->w.val_fc1_w, 2 * C, 8192, C, s)) != M0_OK) break;
+      st->heads_tc = true;
+    }
     if (c.chess_features) {
       if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, C, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, C, s)) != M0_OK) break;
@@ -334,6 +374,9 @@ void tc_net_release(::m0_net* n) {
     if (st->se_gate) cudaFree(st->se_gate);
     if (st->planes_h) cudaFree(st->planes_h);
     if (st->qkv_h) cudaFree(st->qkv_h);
+    if (st->ph_h) cudaFree(st->ph_h);
+    if (st->pf_h) cudaFree(st->pf_h);
+    if (st->vh_h) cudaFree(st->vh_h);
     delete st;
   }
   delete all;
@@ -365,7 +408,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     TRY(nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
   }
   // a1 = act(GN1(x)) of the first block; later blocks get it from the fused SE / residual kernel of their predecessor
-  if (c.blocks > 0) TRY(nn_groupnorm_mixed(n->x, w.blocks[0].gn1_w, w.blocks[0].gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));
+  if (c.blocks > 0) TRY(nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[0].gn1_w, w.blocks[0].gn1_b, st->a1, B, C, act, s));
   int att_seen = 0;
   const int stride = c.infer_attention_stride > 1 ? c.infer_attention_stride : 1;
   for (int i = 0; i < c.blocks; ++i) {
@@ -406,10 +449,33 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
       }
       TRY(launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
       TRY(nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
-      if (!last) TRY(nn_groupnorm_mixed(n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, nullptr, 0, nullptr, st->a1, B, C, act, s));
+      if (!last) TRY(nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
     }
   }
-  return net_forward_heads_f32(n, B, logits, values, s);
+  if (!st->heads_tc) return net_forward_heads_f32(n, B, logits, values, s);
+  // ---- heads (resnet.py:697-753) on tensor cores; the three small value layers after fc1 stay in fp32 ----
+  const int vact = c.value_activation, r = c.policy_factor_rank, rp = st->pol_rank_pad;
+  TRY(nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
+  // policy: conv1x1 C->64, GN, act, fc1 + ReLU, fc2 * logit scale
+  TRY(launch_gemm(st, st->a1_mat, st->pol_conv, M, 0, 1, C, 0, 64, n->t1, nullptr, 64, 0, none, ACT_NONE, 1.0f, s));
+  TRY(nn_groupnorm_mixed(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
+  TRY(launch_gemm(st, st->ph_mat, st->pol_fc1, B, 0, 1, 4096, 0, r, nullptr, st->pf_h, rp, 0, w.pol_fc1_b, ACT_RELU, 1.0f, s));
+  for (int r0 = 0; r0 < c.policy_size; r0 += 320) {
+    const int nn = c.policy_size - r0 < 320 ? c.policy_size - r0 : 320;
+    TRY(launch_gemm(st, st->pf_mat, st->pol_fc2, B, 0, 1, rp, r0, 320, logits, nullptr, c.policy_size, r0, w.pol_fc2_b, ACT_NONE, w.policy_logit_scale, s,
+                    nullptr, nullptr, nullptr, nn));
+  }
+  // value: conv1x1 C->128, GN, act, conv1x1 128->128, GN, act, fc1 (+ activation) on tensor cores
+  TRY(launch_gemm(st, st->a1_mat, st->val_conv1, M, 0, 1, C, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
+  TRY(nn_groupnorm_mixed(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
+  TRY(launch_gemm(st, st->vh_conv_mat, st->val_conv2, M, 0, 1, 128, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
+  TRY(nn_groupnorm_mixed(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
+  for (int r0 = 0; r0 < 2 * C; r0 += C)
+    TRY(launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, r0, C, n->vf1, nullptr, 2 * C, r0, w.val_fc1_b, vact, 1.0f, s));
+  TRY(nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
+  TRY(nn_gemm_f32(A_DIRECT, n->vf2, w.val_gate_w, w.val_gate_b, n->vf2, n->vg, B, C, C, C, C, 0, ACT_SIGMOID, 1.0f, s));
+  TRY(nn_gemm_f32(A_DIRECT, n->vg, w.val_fc3_w, w.val_fc3_b, nullptr, values, B, 1, C, C, 1, 0, ACT_TANH, 1.0f, s));
+  return M0_OK;
 }
 
 }  // namespace m0

@@ -161,6 +161,7 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int f
 struct GemmParams {
   int M;            // valid rows of D (rows >= M are computed on zero / stale A rows and not stored)
   int N;            // output columns handled by this launch (<= 320, multiple of 16)
+  int n_store;      // columns actually stored (<= N; the rest are zero-padded weight rows)
   int n_part;       // columns per tcgen05.mma (N if N <= 256, else N / 2); multiple of 16
   int taps;         // 9 (3x3 convolution) or 1 (plain GEMM / 1x1 convolution)
   int kb_per_tap;   // k-blocks per tap = Cin / 64 (plain GEMM: K / 64)
@@ -404,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]);
-            if (bias && c0 + j < p.N) x += bias[j];
+            if (bias && c0 + j < p.n_store) x += bias[j];
             r[j] = __float_as_uint(tc_act(x, act) * scale);
           }
         }
@@ -413,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
         __syncwarp();
-        const int ncols = (p.N - c0) < 32 ? (p.N - c0) : 32;
+        const int ncols = (p.n_store - c0) < 32 ? (p.n_store - c0) : 32;
         if (p.pool_part && tile_row0 < p.M && lane < ncols) {
           // column sums of this half board (lane = column): conflict-free reads of the swizzled buffer
           float cs_sum = 0.f;
