@@ -45,11 +45,9 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     G = args.games
     cfg = reference_cfg(args.sims)
     net = PolicyValueNet.from_config(cfg["model"], device=f"cuda:{local}", precision=precision, seed=0)
-    if world > 1:  # identical weights everywhere: one NCCL broadcast of every parameter from rank 0
-        import torch.distributed as dist
-        for t in net._params.values():
-            dist.broadcast(t, src=0)
-    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=1234 + 7919 * rank, precision=precision, max_nodes=4096)
+    from matrix0_b200 import distributed as D
+    D.broadcast_parameters(net._params, src=0)  # identical weights everywhere: one NCCL broadcast per tensor
+    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=D.rank_seed(1234, rank), precision=precision, max_nodes=4096)
     stream = torch.cuda.current_stream()
     sp.start()
     per_move = 1 + sp.batches_per_move()
