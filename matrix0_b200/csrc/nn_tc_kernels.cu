@@ -188,6 +188,11 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   const int stage_bytes = tc::A_TILE_BYTES + N * tc::BK * 2;
   int stages = (st->max_smem - 2048 - tc::EPI_STAGE_BYTES) / stage_bytes;
   if (stages > 6) stages = 6;
+  {
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("M0_TC_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && stages > cap) stages = cap;
+  }
   if (stages < 2) { m0_set_error("tensor-core GEMM: tile does not fit in shared memory (N=%d)", N); return M0_ERR_ARG; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + tc::EPI_STAGE_BYTES + 1024 + 256;
