@@ -3,6 +3,7 @@
 // normalisation statistics, SE, softmax and the heads stay in fp32.
 #include "net_host.cuh"
 #include "tc_gemm.cuh"
+#include "tc_conv_pair.cuh"
 #include <new>
 #include <stdlib.h>
 #include <string.h>
@@ -67,12 +68,12 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
 }
 
 // 4-D view of NHWC activations [boards][8][8][C] bf16: dims {C, 8, 8, boards}, box {64, 8, 8, 2}
-int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C) {
+int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C, uint32_t box_x = 8) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { m0_set_error("cuTensorMapEncodeTiled is not available from the driver"); return M0_ERR_CUDA; }
   cuuint64_t dims[4] = {C, 8, 8, boards};
   cuuint64_t strides[3] = {C * 2, C * 2 * 8, C * 2 * 64};
-  cuuint32_t box[4] = {64, 8, 8, 2};
+  cuuint32_t box[4] = {64, box_x, 8, 2};   // box_x = 10: the CTA-pair kernel's x-padded box (tc_conv_pair.cuh)
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -83,6 +84,8 @@ int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C) 
 struct TcWeight {
   __nv_bfloat16* w = nullptr;  // [n][k] bf16
   CUtensorMap map;             // box {64, n_part / cluster}
+  CUtensorMap map_pair;        // box {64, n / 4}: a quarter of the output channels per CTA and accumulator (tc_conv_pair.cuh)
+  bool pair = false;
   int n = 0, k = 0, n_part = 0, cluster = 1;
 };
 
@@ -125,6 +128,7 @@ struct TcState {
   int cap = 0;
   __nv_bfloat16 *a1 = nullptr, *a2 = nullptr;
   CUtensorMap a1_conv, a2_conv, a1_mat, a2_mat;
+  CUtensorMap a1_convp, a2_convp, planes_convp;   // x-padded boxes of the CTA-pair kernel
   std::vector<void*> allocs;
 };
 
@@ -135,6 +139,68 @@ struct TcState {
   } while (0)
 
 int n_part_for(int n) { return n <= 256 ? n : n / 2; }
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// 3x3 convolutions whose output width suits the CTA-pair kernel (M0_TC_PAIR=0 keeps the single-CTA kernel)
+bool pair_ok(int n) {
+  static int on = -1;
+  if (on < 0) on = env_int("M0_TC_PAIR", 1);
+  return on && n % 32 == 0 && n >= 64 && n <= 512;
+}
+
+int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int boards, int cin, float* out_f32, __nv_bfloat16* out_half,
+                     int ldc, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr) {
+  tc::ConvPairParams p;
+  memset(&p, 0, sizeof(p));
+  p.boards = boards;
+  p.N = w.n;
+  p.kb_per_tap = cin / 64;
+  p.fp16 = nn_half_format();
+  p.out_f32 = out_f32;
+  p.out_half = out_half;
+  p.ldc = ldc;
+  p.act = act;
+  p.gn_gamma = gn_gamma;
+  p.gn_beta = gn_beta;
+  p.pool_part = pool_part;
+  static int em = -1, bo = -1, cap = -1;
+  if (em < 0) { em = env_int("M0_TC_EXP", 0); bo = env_int("M0_CP_BASEOFF", 0); cap = env_int("M0_TC_STAGES", 0); }
+  p.exp_mode = em;
+  p.base_offset = bo;
+  const int stage_bytes = tc::CP_A_SLOT + 3 * (w.n / 4) * 128;
+  int stages = (st->max_smem - 2048 - tc::CP_EPI_BYTES) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (cap > 0 && stages > cap) stages = cap;
+  if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n); return M0_ERR_ARG; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + tc::CP_EPI_BYTES + 1024 + 256;
+  static size_t configured = 0;
+  if (smem > configured) {
+    M0_CUDA_TRY(cudaFuncSetAttribute(tc::conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tiles = (boards + 3) / 4;
+  int clusters = st->sm_count / 2;
+  if (clusters > tiles) clusters = tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(tc::CP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::conv_pair_kernel, a_map, w.map_pair, p));
+  return m0_check_launch("conv_pair_kernel");
+}
 
 // n_launch: output channels per kernel launch (N <= 320 -> <= 512 TMEM columns); wider layers are split by rows
 int make_weight(TcState* st, TcWeight* out, const float* w_f32, int n, int k, int n_launch, cudaStream_t s) {
@@ -147,6 +213,8 @@ int make_weight(TcState* st, TcWeight* out, const float* w_f32, int n, int k, in
   st->allocs.push_back(p);
   out->w = (__nv_bfloat16*)p;
   TRY(nn_f32_to_bf16(w_f32, out->w, (size_t)n * k, s));
+  out->pair = pair_ok(n) && n == n_launch;
+  if (out->pair) TRY(make_map_2d(&out->map_pair, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)(n / 4)));
   return make_map_2d(&out->map, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)(out->n_part / out->cluster));
 }
 
@@ -182,6 +250,11 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   p.gn_gamma = gn_gamma;
   p.gn_beta = gn_beta;
   p.pool_part = pool_part;
+  {
+    static int em = -1;
+    if (em < 0) { const char* e = getenv("M0_TC_EXP"); em = e ? atoi(e) : 0; }
+    p.exp_mode = em;
+  }
   if ((gn_gamma || pool_part) && (w_row0 != 0 || N % 32 != 0)) { m0_set_error("fused epilogue needs the full channel range"); return M0_ERR_ARG; }
   p.cluster = w.cluster;
   p.fp16 = nn_half_format();
@@ -223,6 +296,14 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   return m0_check_launch("gemm_tc_kernel");
 }
 
+// 3x3 convolution of B boards with all C_out channels in one launch: CTA-pair kernel when the weight supports it
+int conv3x3(TcState* st, const CUtensorMap& a_map, const CUtensorMap& a_map_pair, const TcWeight& w, int B, int cin, float* out_f32,
+            __nv_bfloat16* out_half, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr,
+            float* pool_part = nullptr) {
+  if (w.pair) return launch_conv_pair(st, a_map_pair, w, B, cin, out_f32, out_half, w.n, act, s, gn_gamma, gn_beta, pool_part);
+  return launch_gemm(st, a_map, w, B * 64, 1, 9, cin, 0, w.n, out_f32, out_half, w.n, 0, nullptr, act, 1.0f, s, gn_gamma, gn_beta, pool_part);
+}
+
 int tc_reserve(m0_net* n, TcState* st, int B) {
   const int need = (B + 1) & ~1;  // tiles hold two boards
   if (need <= st->cap) return M0_OK;
@@ -260,12 +341,15 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   }
   M0_CUDA_TRY(cudaMemset(st->planes_h, 0, (size_t)need * 64 * 64 * 2));
   TRY(make_map_nhwc(&st->planes_conv, st->planes_h, need, 64));
+  TRY(make_map_nhwc(&st->planes_convp, st->planes_h, need, 64, 10));
   M0_CUDA_TRY(cudaMalloc((void**)&st->a1, (size_t)need * 64 * C * 2));
   M0_CUDA_TRY(cudaMalloc((void**)&st->a2, (size_t)need * 64 * C * 2));
   M0_CUDA_TRY(cudaMemset(st->a1, 0, (size_t)need * 64 * C * 2));
   M0_CUDA_TRY(cudaMemset(st->a2, 0, (size_t)need * 64 * C * 2));
   TRY(make_map_nhwc(&st->a1_conv, st->a1, need, C));
   TRY(make_map_nhwc(&st->a2_conv, st->a2, need, C));
+  TRY(make_map_nhwc(&st->a1_convp, st->a1, need, C, 10));
+  TRY(make_map_nhwc(&st->a2_convp, st->a2, need, C, 10));
   TRY(make_map_2d(&st->a1_mat, st->a1, (uint64_t)need * 64, C, 128));
   TRY(make_map_2d(&st->a2_mat, st->a2, (uint64_t)need * 64, C, 128));
   st->cap = need;
@@ -398,7 +482,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   const float* none = nullptr;
   // stem: planes -> NHWC half (64 channels, zero padded) -> tensor-core conv3x3 -> GN + act (+ position encoding)
   TRY(nn_planes_to_nhwc_half(planes, st->planes_h, B, c.planes, s));
-  TRY(launch_gemm(st, st->planes_conv, st->stem, M, 1, 9, 64, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+  TRY(conv3x3(st, st->planes_conv, st->planes_convp, st->stem, B, 64, n->t1, nullptr, ACT_NONE, s));
   if (c.chess_features) {
     TRY(nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
     float* cur = n->x;
@@ -407,7 +491,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
       TRY(nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
       cur = n->t2;
     }
-    TRY(launch_gemm(st, st->a1_conv, st->inter, M, 1, 9, C, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+    TRY(conv3x3(st, st->a1_conv, st->a1_convp, st->inter, B, C, n->t1, nullptr, ACT_NONE, s));
     TRY(nn_groupnorm_mixed(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
   } else {
     TRY(nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
@@ -426,10 +510,9 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     }
     const bool last = (i + 1 == c.blocks);
     // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
-    TRY(launch_gemm(st, st->a1_conv, tb.conv1, M, 1, 9, C, 0, C, nullptr, st->a2, C, 0, none, act, 1.0f, s, b.gn2_w, b.gn2_b, nullptr));
+    TRY(conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr));
     // conv2 with the SE squeeze (half-board column sums) fused into the epilogue
-    TRY(launch_gemm(st, st->a2_conv, tb.conv2, M, 1, 9, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s, nullptr, nullptr,
-                    c.se ? st->pool : nullptr));
+    TRY(conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, n->t2, nullptr, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr));
     const float* gate = nullptr;
     if (c.se) {
       TRY(nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
@@ -506,6 +589,12 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
   w.cluster = pick_cluster(w.n_part);
   TRY(make_map_2d(&w.map, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)(w.n_part / w.cluster)));
   CUtensorMap a;
+  if (taps == 9 && pair_ok(n)) {
+    w.pair = true;
+    TRY(make_map_2d(&w.map_pair, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)(n / 4)));
+    TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin, 10));
+    return launch_conv_pair(&st, a, w, boards, cin, d_out_f32, nullptr, n, ACT_NONE, (cudaStream_t)stream);
+  }
   if (taps == 9) TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin));
   else TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));
   return launch_gemm(&st, a, w, boards * 64, taps == 9 ? 1 : 0, taps, cin, 0, n, d_out_f32, nullptr, n, 0, nullptr, ACT_NONE, 1.0f, (cudaStream_t)stream);

@@ -1,0 +1,351 @@
+// 3x3 "same" convolution of an NHWC half-precision board tensor on a CTA PAIR (tcgen05 cta_group::2).
+//
+//   out[b*64 + y*8 + x][n] = sum_{dy,dx,c} act[b][y+dy][x+dx][c] * W[n][((dy+1)*3 + dx+1)*Cin + c]
+//
+// Why a second kernel next to tc_gemm.cuh: the single-CTA kernel is bound by what feeds the tensor pipe (its
+// 128 x 320 tile needs 56 KB of operands per 64-deep k-block) and by an epilogue that cannot overlap the next
+// tile (320 of the 512 TMEM columns hold one accumulator).  Here
+//   * two CTAs (one TPC) issue ONE 256 x N/2 x 16 MMA: each CTA stages only ITS 128 rows of A and a QUARTER of
+//     the W rows (the pair reads each other's half of B), which halves the W bytes per flop;
+//   * one A box {64 ch, 10 x, 8 y, 2 boards} per (k-chunk, dy) serves the three dx taps: the box starts at
+//     x = -1 and is 10 wide, so TMA zero-fills both borders, and tap dx is the SAME shared-memory box read
+//     through a descriptor that starts (dx + 1) rows later with a 10-row (1280 B) stride between 8-row groups
+//     -- A traffic drops 3x against one box per tap;
+//   * the N output channels are processed as two halves of N/2 columns in two TMEM accumulators (columns
+//     0.. and 256..), so the epilogue of one half overlaps the main loop of the next.
+//
+// Work item = (group of 4 boards, channel half).  CTA r of the pair owns boards 4t + 2r, 4t + 2r + 1 (TMEM lanes
+// 0..127 of its own tensor memory).  Warp 0 = TMA producer (both CTAs; every load signals the LEADER's full
+// barrier), warp 1 = MMA issuer (leader CTA only) and TMEM allocator, warps 2..9 = epilogue.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace m0 {
+namespace tc {
+
+struct ConvPairParams {
+  int boards;       // valid boards; rows b*64.. of the output are stored only for b < boards
+  int N;            // output channels: N % 32 == 0, 64 <= N <= 512
+  int kb_per_tap;   // Cin / 64
+  int stages;
+  int fp16;         // operands are IEEE fp16 instead of bf16
+  float* out_f32;   // [boards*64][ldc] or null
+  __nv_bfloat16* out_half;   // same shape, 16-bit storage in the operand format, or null
+  int ldc;
+  // fused epilogues (tc_gemm.cuh GemmParams): GroupNorm(16-channel groups over a board) + activation -> out_half,
+  // or the SE squeeze partial sums pool_part[(board*2 + half board)][n]
+  int act;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float* pool_part;
+  int exp_mode;     // timing experiments only: 4 = skip the epilogue body
+  int base_offset;  // set the descriptor base-offset field of the row-shifted A views
+};
+
+static constexpr int CP_THREADS = 320;
+static constexpr int CP_A_SLOT = 160 * 128;   // 2 boards x 8 y x 10 x rows of 64 channels
+static constexpr int CP_EPI_BYTES = 8 * 32 * 16 * 4 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4;   // transposers + gamma/beta + GN partial sums
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// loads issued by either CTA of the pair; the transaction bytes are credited to the barrier at cluster address bar
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D (128 lanes in EACH CTA of the pair) (+)= A (128 rows from each CTA) * B^T (N/2 rows from each CTA); leader CTA only
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// K-major 128-byte-swizzled operand whose 8-row groups are sbo_bytes apart (1024 for a dense tile)
+// base_offset [49,52) = (start address >> 7) & 7: the phase of the 8-row swizzle pattern when the start is not 1024-byte aligned
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t use_base_offset) {
+  const uint64_t base_off = use_base_offset ? (uint64_t)((smem_addr >> 7) & 7u) : 0ull;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (base_off << 49) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const ConvPairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nh = p.N >> 1, nq = p.N >> 2;
+  const int wq_bytes = nq * 128;
+  const int stage_bytes = CP_A_SLOT + 3 * wq_bytes;
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  float* s_gamma = epi_stage + 8 * 512;   // [512]
+  float* s_beta = s_gamma + 512;          // [512]
+  float* s_stats = s_beta + 512;          // [2 accumulators][4 quarters][16 groups][sum, sumsq]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 256);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], only the leader's are used
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int num_tiles = (p.boards + 3) >> 2;
+  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int steps = p.kb_per_tap * 3;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 16);   // one arrival per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int board0 = t * 4 + rank * 2;   // boards past the end are zero-filled by TMA
+        for (int h = 0; h < 2; ++h) {
+          const int w_row = h * nh + rank * nq;
+          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+              const uint32_t bar = lead_full + (uint32_t)stage * 8u;
+              uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+              tma_load_4d_pair(a_dst, &tma_a, bar, kc * BK, -1, dyi - 1, board0);
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi)
+                tma_load_2d_pair(a_dst + CP_A_SLOT + dxi * wq_bytes, &tma_w, bar, ((dyi * 3 + dxi) * p.kb_per_tap + kc) * BK, w_row);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA) =====
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, nh, p.fp16);
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0, unit = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        for (int h = 0; h < 2; ++h, ++unit) {
+          const uint32_t buf = unit & 1u;
+          mbar_wait(&tmem_empty_bar[buf], ((unit >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
+          tc_fence_after();
+          const uint32_t d = tmem_base + buf * 256u;
+          for (int step = 0; step < steps; ++step) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
+            if (elect_one()) {
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                const uint64_t adesc = make_smem_desc_sbo(a_addr + dxi * 128, 1280, p.base_offset);
+                const uint64_t bdesc = make_smem_desc_sbo(a_addr + CP_A_SLOT + dxi * wq_bytes, 1024, 0);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, (step > 0 || dxi > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit_pair(&empty_bar[stage], 3);   // frees the stage in both CTAs
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          if (elect_one()) umma_commit_pair(&tmem_full_bar[buf], 3);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): TMEM -> registers -> smem transpose -> coalesced stores, 16 columns at a time =====
+    const int quarter = warp & 3;
+    const int cset = (warp - 2) >> 2;
+    float* stg = epi_stage + (warp - 2) * 512;
+    const bool fused_gn = p.gn_gamma != nullptr;
+    const int epi_tid = ((warp - 2) << 5) | lane;
+    const uint32_t lead_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
+    const int nchunks = nh >> 4;
+    const int M = p.boards * 64;
+    if (fused_gn) {
+      for (int c = epi_tid; c < p.N; c += 256) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    uint32_t unit = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      for (int h = 0; h < 2; ++h, ++unit) {
+        const uint32_t buf = unit & 1u;
+        mbar_wait(&tmem_full_bar[buf], (unit >> 1) & 1u);
+        tc_fence_after();
+        const int row0 = t * 256 + rank * 128 + quarter * 32;
+        const uint32_t tmem_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
+        float* stats = s_stats + buf * 128;
+        if (!(p.exp_mode & 4)) {
+          if (fused_gn) {
+            for (int ci = cset; ci < nchunks; ci += 2) {
+              uint32_t r[16];
+              tmem_ld_32x16(tmem_row + (uint32_t)(ci * 16), r);
+              tmem_ld_wait();
+              float s0 = 0.f, q0 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(r[j]);
+                s0 += a;
+                q0 = fmaf(a, a, q0);
+              }
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+                s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, off);
+                q0 += __shfl_xor_sync(0xFFFFFFFFu, q0, off);
+              }
+              if (lane == 0) {
+                stats[(quarter * 16 + ci) * 2] = s0;
+                stats[(quarter * 16 + ci) * 2 + 1] = q0;
+              }
+            }
+            // the four warps that hold one board exchange their partial sums
+            if (quarter < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+            else asm volatile("bar.sync 3, 128;" ::: "memory");
+          }
+          for (int ci = cset; ci < nchunks; ci += 2) {
+            const int col = h * nh + ci * 16;
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_row + (uint32_t)(ci * 16), r);
+            tmem_ld_wait();
+            if (fused_gn) {
+              const float* sa = stats + ((quarter & 2) * 16 + ci) * 2;
+              const float* sb = stats + ((quarter | 1) * 16 + ci) * 2;
+              const float mean = (sa[0] + sb[0]) * (1.0f / 1024.0f);
+              const float var = fmaxf((sa[1] + sb[1]) * (1.0f / 1024.0f) - mean * mean, 0.0f);
+              const float rstd = rsqrtf(var + 1e-5f);
+              const int act = p.act;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float gm = s_gamma[col + j] * rstd;
+                const float y = fmaf(__uint_as_float(r[j]) - mean, gm, s_beta[col + j]);
+                r[j] = __float_as_uint(tc_act(y, act));
+              }
+            }
+            // lane = row; 16-byte chunk q of row i sits at chunk position q ^ ((i >> 1) & 3) (conflict-free both ways)
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(stg + lane * 16 + ((q ^ sw) << 2)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            __syncwarp();
+            if (p.pool_part && row0 < M) {
+              // column sums of this half board: lane = (row parity, column)
+              const int c = lane & 15, par = lane >> 4;
+              float cs_sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int rr = 2 * i + par;
+                cs_sum += stg[rr * 16 + ((((c >> 2) ^ ((rr >> 1) & 3)) << 2) | (c & 3))];
+              }
+              cs_sum += __shfl_xor_sync(0xFFFFFFFFu, cs_sum, 16);
+              if (par == 0) p.pool_part[(size_t)(row0 >> 5) * p.N + col + c] = cs_sum;
+            }
+            if (p.out_f32) {
+              const int q = lane & 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                const int m = row0 + rr;
+                if (m < M) {
+                  uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((q ^ ((rr >> 1) & 3)) << 2));
+                  *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + col + 4 * q) = v;
+                }
+              }
+            }
+            if (p.out_half) {
+              const int hq = lane & 1;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int rr = (lane >> 1) + 16 * i;
+                const int m = row0 + rr;
+                if (m < M) {
+                  const int sw2 = (rr >> 1) & 3;
+                  float4 lo = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq) ^ sw2) << 2));
+                  float4 hi = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq + 1) ^ sw2) << 2));
+                  uint4 pk;
+                  pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
+                  pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
+                  *reinterpret_cast<uint4*>(p.out_half + (size_t)m * p.ldc + col + 8 * hq) = pk;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_empty + buf * 8u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers or read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace m0
