@@ -8,7 +8,7 @@ namespace m0 {
 __device__ __forceinline__ float fk_act(float x, int act) {
   switch (act) {
     case ACT_RELU: return x > 0.0f ? x : 0.0f;
-    case ACT_SILU: return x / (1.0f + __expf(-x));
+    case ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));
     default: return x;
   }
 }
@@ -22,73 +22,126 @@ __device__ __forceinline__ __nv_bfloat16 fk_half(float x, int fp16) {
 
 // x_new = x + conv_out * gate   (SE excitation + residual add, resnet.py:68-80)
 // a_out = half(act(GroupNorm(x_new)))   (bn1 + activation of the NEXT pre-activation block, resnet.py:46-47), or half(x_new) when
-// gamma is null, or nothing when a_out is null.
-// One block per board.  Thread (rg, q) owns 4 consecutive channels (one float4) of 16 rows: x and conv_out are read once with
-// 16-byte loads, x_new / a_out written once.  GroupNorm statistics: 4 threads (= 16 channels) x 4 row groups per group.
+// gamma is null, or nothing when a_out is null.  conv_out is the 16-bit output of conv2 (operand format).
+// One block per board, C threads.  Thread (rg, q) owns 8 consecutive channels of 8 rows: every access is 16 bytes wide (8 halves or
+// one of two float4), x and conv_out are read once, x_new / a_out written once.  GroupNorm statistics: 2 adjacent threads (= 16
+// channels) x 8 row groups per group.
+__device__ __forceinline__ void unpack_half8(const uint4& u, int fp16, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fp16) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    } else {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ uint32_t fk_pack2(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 __global__ void __launch_bounds__(320, 2)
-se_apply_gn_kernel(const float* __restrict__ conv_out, const float* __restrict__ gate, float* __restrict__ x,
+se_apply_gn_kernel(const __nv_bfloat16* __restrict__ conv_out, const float* __restrict__ gate, float* __restrict__ x,
                    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ a_out, int C, int act, int fp16) {
-  __shared__ float s_part[4][80][2];
+  __shared__ float s_part[8][40][2];
   const int b = blockIdx.x;
-  const int nq = C >> 2;                       // float4 columns (<= 80)
-  const int q = threadIdx.x % nq, rg = threadIdx.x / nq;   // rg < 4 when blockDim == 4 * nq
-  const size_t base = (size_t)b * 64 * C + (size_t)rg * 16 * C + 4 * q;
-  float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (gate) e = *reinterpret_cast<const float4*>(gate + (size_t)b * C + 4 * q);
-  float4 v[16];
+  const int nq = C >> 3;                       // 8-channel columns (<= 40)
+  const int q = threadIdx.x % nq, rg = threadIdx.x / nq;   // rg < 8 when blockDim == C
+  const size_t base = (size_t)b * 64 * C + (size_t)rg * 8 * C + 8 * q;
+  float v[8][8];
   if (conv_out) {
+    float e[8];
+    if (gate) {
+      const float4 e0 = *reinterpret_cast<const float4*>(gate + (size_t)b * C + 8 * q);
+      const float4 e1 = *reinterpret_cast<const float4*>(gate + (size_t)b * C + 8 * q + 4);
+      e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
+    } else {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = __ldg(reinterpret_cast<const float4*>(conv_out + base + (size_t)r * C));
+      for (int j = 0; j < 8; ++j) e[j] = 1.0f;
+    }
+    uint4 cv[8];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
-      v[r].x = fmaf(v[r].x, e.x, xv.x); v[r].y = fmaf(v[r].y, e.y, xv.y);
-      v[r].z = fmaf(v[r].z, e.z, xv.z); v[r].w = fmaf(v[r].w, e.w, xv.w);
+    for (int r = 0; r < 8; ++r) cv[r] = __ldg(reinterpret_cast<const uint4*>(conv_out + base + (size_t)r * C));
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float4 x0 = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
+      const float4 x1 = *reinterpret_cast<const float4*>(x + base + (size_t)r * C + 4);
+      float c[8];
+      unpack_half8(cv[r], fp16, c);
+      v[r][0] = fmaf(c[0], e[0], x0.x); v[r][1] = fmaf(c[1], e[1], x0.y); v[r][2] = fmaf(c[2], e[2], x0.z); v[r][3] = fmaf(c[3], e[3], x0.w);
+      v[r][4] = fmaf(c[4], e[4], x1.x); v[r][5] = fmaf(c[5], e[5], x1.y); v[r][6] = fmaf(c[6], e[6], x1.z); v[r][7] = fmaf(c[7], e[7], x1.w);
     }
 #pragma unroll
-    for (int r = 0; r < 16; ++r) *reinterpret_cast<float4*>(x + base + (size_t)r * C) = v[r];
+    for (int r = 0; r < 8; ++r) {
+      *reinterpret_cast<float4*>(x + base + (size_t)r * C) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+      *reinterpret_cast<float4*>(x + base + (size_t)r * C + 4) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+    }
   } else {   // plain GroupNorm of x: nothing to add, nothing to write back
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
+    for (int r = 0; r < 8; ++r) {
+      const float4 x0 = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
+      const float4 x1 = *reinterpret_cast<const float4*>(x + base + (size_t)r * C + 4);
+      v[r][0] = x0.x; v[r][1] = x0.y; v[r][2] = x0.z; v[r][3] = x0.w; v[r][4] = x1.x; v[r][5] = x1.y; v[r][6] = x1.z; v[r][7] = x1.w;
+    }
   }
   if (!a_out) return;
   __nv_bfloat16* ao = a_out + base;
   if (!gamma) {  // the next consumer is the attention qkv GEMM: it takes the raw residual stream in half precision
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      __nv_bfloat16 h4[4] = {fk_half(v[r].x, fp16), fk_half(v[r].y, fp16), fk_half(v[r].z, fp16), fk_half(v[r].w, fp16)};
-      *reinterpret_cast<uint2*>(ao + (size_t)r * C) = *reinterpret_cast<uint2*>(h4);
-    }
+    for (int r = 0; r < 8; ++r)
+      *reinterpret_cast<uint4*>(ao + (size_t)r * C) = make_uint4(fk_pack2(v[r][0], v[r][1], fp16), fk_pack2(v[r][2], v[r][3], fp16),
+                                                                 fk_pack2(v[r][4], v[r][5], fp16), fk_pack2(v[r][6], v[r][7], fp16));
     return;
   }
   float s = 0.f;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) s += (v[r].x + v[r].y) + (v[r].z + v[r].w);
-  s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
-  s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);   // 4 adjacent threads = one group of 16 channels (nq % 4 == 0, warps hold whole groups)
+  for (int r = 0; r < 8; ++r) s += ((v[r][0] + v[r][1]) + (v[r][2] + v[r][3])) + ((v[r][4] + v[r][5]) + (v[r][6] + v[r][7]));
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);   // 2 adjacent threads = one group of 16 channels (C/8 is even: pairs never straddle a warp)
   s_part[rg][q][0] = s;
   __syncthreads();
-  const float mean = (s_part[0][q][0] + s_part[1][q][0] + s_part[2][q][0] + s_part[3][q][0]) * (1.0f / 1024.0f);
+  float tot = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) tot += s_part[g][q][0];
+  const float mean = tot * (1.0f / 1024.0f);
   float d2 = 0.f;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    float a0 = v[r].x - mean, a1 = v[r].y - mean, a2 = v[r].z - mean, a3 = v[r].w - mean;
-    d2 = fmaf(a0, a0, d2); d2 = fmaf(a1, a1, d2); d2 = fmaf(a2, a2, d2); d2 = fmaf(a3, a3, d2);
-  }
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = v[r][j] - mean;
+      d2 = fmaf(a, a, d2);
+    }
   d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 1);
-  d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 2);
   s_part[rg][q][1] = d2;
   __syncthreads();
-  const float var = (s_part[0][q][1] + s_part[1][q][1] + s_part[2][q][1] + s_part[3][q][1]) * (1.0f / 1024.0f);
-  const float rstd = rsqrtf(var + 1e-5f);
-  const float4 gm = *reinterpret_cast<const float4*>(gamma + 4 * q), bt = *reinterpret_cast<const float4*>(beta + 4 * q);
-  const float g0 = gm.x * rstd, g1 = gm.y * rstd, g2 = gm.z * rstd, g3 = gm.w * rstd;
-  const float b0 = bt.x - mean * g0, b1 = bt.y - mean * g1, b2 = bt.z - mean * g2, b3 = bt.w - mean * g3;
+  float vs = 0.f;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    __nv_bfloat16 h4[4] = {fk_half(fk_act(fmaf(v[r].x, g0, b0), act), fp16), fk_half(fk_act(fmaf(v[r].y, g1, b1), act), fp16),
-                           fk_half(fk_act(fmaf(v[r].z, g2, b2), act), fp16), fk_half(fk_act(fmaf(v[r].w, g3, b3), act), fp16)};
-    *reinterpret_cast<uint2*>(ao + (size_t)r * C) = *reinterpret_cast<uint2*>(h4);
+  for (int g = 0; g < 8; ++g) vs += s_part[g][q][1];
+  const float rstd = rsqrtf(vs * (1.0f / 1024.0f) + 1e-5f);
+  float gsc[8], bsh[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + 8 * q), g1 = *reinterpret_cast<const float4*>(gamma + 8 * q + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + 8 * q), b1 = *reinterpret_cast<const float4*>(beta + 8 * q + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gsc[j] = gg[j] * rstd; bsh[j] = bb[j] - mean * gsc[j]; }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = fk_act(fmaf(v[r][j], gsc[j], bsh[j]), act);
+    *reinterpret_cast<uint4*>(ao + (size_t)r * C) =
+        make_uint4(fk_pack2(y[0], y[1], fp16), fk_pack2(y[2], y[3], fp16), fk_pack2(y[4], y[5], fp16), fk_pack2(y[6], y[7], fp16));
   }
 }
 
@@ -104,50 +157,89 @@ __global__ void planes_to_nhwc_half_kernel(const float* __restrict__ planes, __n
 
 // SE excitation for 16 boards per block (resnet.py:61-64): s = avgpool, h = act(W1 s + b1), gate = sigmoid(W2 h + b2).
 // pool: half-board column sums [B][2][C]; w1t [C][hid] and w2t [hid][C] are transposed so that threads read them coalesced.
+// Both layers keep 16 board accumulators per thread, so every weight is loaded once per block and the loads of consecutive
+// iterations are independent (unrolled: the kernel is latency-bound, not bandwidth-bound).
 __global__ void __launch_bounds__(320)
 se_gate_kernel(const float* __restrict__ pool, const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
                const float* __restrict__ b2, float* __restrict__ gate, int B, int C, int hid, int act) {
   extern __shared__ float sm[];
-  float* s_pool = sm;              // [16][C]
-  float* s_hid = sm + 16 * C;      // [16][hid]
+  float* s_pool = sm;                      // [C][16]   (board index fastest: one 64-byte broadcast row per channel)
+  float* s_hid = sm + 16 * C;              // [hid][16]
+  float* s_red = s_hid + 16 * hid;         // [4][hid][16] partial sums of layer 1
   const int b0 = blockIdx.x * 16, t = threadIdx.x;
   const int nb = min(16, B - b0);
-  for (int i = t; i < nb * C; i += blockDim.x) {
+  for (int i = t; i < 16 * C; i += blockDim.x) {
     const int j = i / C, c = i - j * C;
-    const float* pp = pool + (size_t)(b0 + j) * 2 * C;
-    s_pool[j * C + c] = (pp[c] + pp[C + c]) * (1.0f / 64.0f);
+    float v = 0.f;
+    if (j < nb) {
+      const float* pp = pool + (size_t)(b0 + j) * 2 * C;
+      v = (pp[c] + pp[C + c]) * (1.0f / 64.0f);
+    }
+    s_pool[c * 16 + j] = v;
   }
   __syncthreads();
-  for (int o = t; o < nb * hid; o += blockDim.x) {
-    const int j = o / hid, u = o - j * hid;
-    float h = b1[u];
-    const float* sp = s_pool + j * C;
-    for (int c = 0; c < C; ++c) h = fmaf(w1t[c * hid + u], sp[c], h);
-    s_hid[j * hid + u] = fk_act(h, act);
+  // layer 1: thread (part, u) accumulates channels [part*C/4, (part+1)*C/4) of hidden unit u for the 16 boards
+  {
+    const int parts = blockDim.x / hid;        // 4 when blockDim = 320, hid = 80
+    const int part = t / hid, u = t - part * hid;
+    if (part < parts) {
+      float h[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = 0.f;
+      const int c0 = part * (C / parts), c1 = (part + 1 == parts) ? C : c0 + C / parts;
+#pragma unroll 4
+      for (int c = c0; c < c1; ++c) {
+        const float w = __ldg(w1t + c * hid + u);
+        const float4* sp = reinterpret_cast<const float4*>(s_pool + c * 16);
+        const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];
+        h[0] = fmaf(w, p0.x, h[0]); h[1] = fmaf(w, p0.y, h[1]); h[2] = fmaf(w, p0.z, h[2]); h[3] = fmaf(w, p0.w, h[3]);
+        h[4] = fmaf(w, p1.x, h[4]); h[5] = fmaf(w, p1.y, h[5]); h[6] = fmaf(w, p1.z, h[6]); h[7] = fmaf(w, p1.w, h[7]);
+        h[8] = fmaf(w, p2.x, h[8]); h[9] = fmaf(w, p2.y, h[9]); h[10] = fmaf(w, p2.z, h[10]); h[11] = fmaf(w, p2.w, h[11]);
+        h[12] = fmaf(w, p3.x, h[12]); h[13] = fmaf(w, p3.y, h[13]); h[14] = fmaf(w, p3.z, h[14]); h[15] = fmaf(w, p3.w, h[15]);
+      }
+      float4* dst = reinterpret_cast<float4*>(s_red + (part * hid + u) * 16);
+      dst[0] = make_float4(h[0], h[1], h[2], h[3]); dst[1] = make_float4(h[4], h[5], h[6], h[7]);
+      dst[2] = make_float4(h[8], h[9], h[10], h[11]); dst[3] = make_float4(h[12], h[13], h[14], h[15]);
+    }
+    __syncthreads();
+    for (int o = t; o < hid * 16; o += blockDim.x) {
+      const int u2 = o >> 4;
+      float a = b1[u2];
+      for (int pp = 0; pp < parts; ++pp) a += s_red[pp * hid * 16 + o];
+      s_hid[o] = fk_act(a, act);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int c = t; c < C; c += blockDim.x) {
     float z[16];
+    const float bias = b2[c];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) z[j] = b2[c];
+    for (int j = 0; j < 16; ++j) z[j] = bias;
+#pragma unroll 4
     for (int u = 0; u < hid; ++u) {
-      const float w = w2t[u * C + c];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) z[j] = fmaf(w, s_hid[j * hid + u], z[j]);
+      const float w = __ldg(w2t + u * C + c);
+      const float4* sh = reinterpret_cast<const float4*>(s_hid + u * 16);
+      const float4 p0 = sh[0], p1 = sh[1], p2 = sh[2], p3 = sh[3];
+      z[0] = fmaf(w, p0.x, z[0]); z[1] = fmaf(w, p0.y, z[1]); z[2] = fmaf(w, p0.z, z[2]); z[3] = fmaf(w, p0.w, z[3]);
+      z[4] = fmaf(w, p1.x, z[4]); z[5] = fmaf(w, p1.y, z[5]); z[6] = fmaf(w, p1.z, z[6]); z[7] = fmaf(w, p1.w, z[7]);
+      z[8] = fmaf(w, p2.x, z[8]); z[9] = fmaf(w, p2.y, z[9]); z[10] = fmaf(w, p2.z, z[10]); z[11] = fmaf(w, p2.w, z[11]);
+      z[12] = fmaf(w, p3.x, z[12]); z[13] = fmaf(w, p3.y, z[13]); z[14] = fmaf(w, p3.z, z[14]); z[15] = fmaf(w, p3.w, z[15]);
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (j < nb) gate[(size_t)(b0 + j) * C + c] = 1.0f / (1.0f + __expf(-z[j]));
+      if (j < nb) gate[(size_t)(b0 + j) * C + c] = __fdividef(1.0f, 1.0f + __expf(-z[j]));
   }
 }
 
 int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float* w2t, const float* b2, float* gate, int B, int C, int hid, int act,
                cudaStream_t s) {
-  se_gate_kernel<<<(B + 15) / 16, 320, (size_t)16 * (C + hid) * sizeof(float), s>>>(pool, w1t, b1, w2t, b2, gate, B, C, hid, act);
+  if (hid <= 0 || hid > 320) { m0_set_error("se_gate: unsupported hidden width %d", hid); return M0_ERR_ARG; }
+  const int parts = 320 / hid;
+  se_gate_kernel<<<(B + 15) / 16, 320, (size_t)16 * (C + hid + (size_t)parts * hid) * sizeof(float), s>>>(pool, w1t, b1, w2t, b2, gate, B, C, hid, act);
   return m0_check_launch("se_gate");
 }
 
-int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
+int nn_se_apply_gn(const __nv_bfloat16* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
                    int C, int act, cudaStream_t s) {
   if (C > 320 || C % 32 != 0) { m0_set_error("se_apply_gn: unsupported channel count %d", C); return M0_ERR_ARG; }
   if (C % 16 != 0) { m0_set_error("se_apply_gn: channels must be a multiple of 16"); return M0_ERR_ARG; }

@@ -7,12 +7,15 @@
 #include <new>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <string>
+#include <utility>
 #include <vector>
 
 using namespace m0;
 
 namespace m0 {
-int nn_se_apply_gn(const float* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
+int nn_se_apply_gn(const __nv_bfloat16* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
                    int C, int act, cudaStream_t s);
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s);
 int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half, int B, int C, int heads, float mix, cudaStream_t s);
@@ -132,6 +135,64 @@ struct TcState {
   std::vector<void*> allocs;
 };
 
+// M0_TC_PROFILE=1: CUDA-event timing of every launch of the forward, by kernel class, printed at exit (diagnostics only)
+struct TcProfiler {
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  std::vector<Rec> pending;
+  std::vector<std::pair<std::string, std::pair<double, long>>> acc;
+  int on = -1;
+  bool enabled() {
+    if (on < 0) {
+      const char* e = getenv("M0_TC_PROFILE");
+      on = (e && atoi(e)) ? 1 : 0;
+      if (on) atexit(&TcProfiler::dump_static);
+    }
+    return on == 1;
+  }
+  static TcProfiler& get() { static TcProfiler p; return p; }
+  void begin(const char* name, cudaStream_t s) {
+    Rec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    pending.push_back(r);
+  }
+  void end(cudaStream_t s) { cudaEventRecord(pending.back().b, s); }
+  void collect() {
+    for (Rec& r : pending) {
+      cudaEventSynchronize(r.b);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      bool found = false;
+      for (auto& kv : acc) if (kv.first == r.name) { kv.second.first += ms; kv.second.second++; found = true; break; }
+      if (!found) acc.push_back({r.name, {ms, 1}});
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    pending.clear();
+  }
+  static void dump_static() {
+    TcProfiler& p = get();
+    double tot = 0;
+    for (auto& kv : p.acc) tot += kv.second.first;
+    fprintf(stderr, "[m0 tc profile] total %.3f ms\n", tot);
+    for (auto& kv : p.acc)
+      fprintf(stderr, "[m0 tc profile] %5.1f%%  n=%5ld  avg=%9.1f us  %s\n", 100.0 * kv.second.first / tot, kv.second.second,
+              1e3 * kv.second.first / kv.second.second, kv.first.c_str());
+  }
+};
+#define PROF(name, call)                                   \
+  do {                                                     \
+    TcProfiler& _p = TcProfiler::get();                    \
+    if (_p.enabled()) {                                    \
+      _p.begin(name, s);                                   \
+      int _r = (call);                                     \
+      _p.end(s);                                           \
+      if (_r != M0_OK) return _r;                          \
+    } else {                                               \
+      int _r = (call);                                     \
+      if (_r != M0_OK) return _r;                          \
+    }                                                      \
+  } while (0)
+
 #define TRY(x)            \
   do {                    \
     int _r = (x);         \
@@ -177,10 +238,14 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n); return M0_ERR_ARG; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + tc::CP_EPI_BYTES + 1024 + 256;
-  static size_t configured = 0;
-  if (smem > configured) {
-    M0_CUDA_TRY(cudaFuncSetAttribute(tc::conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
+  const int nch = (w.n + 63) / 64;
+  auto kernel = nch <= 2 ? tc::conv_pair_kernel<2> : nch <= 5 ? tc::conv_pair_kernel<5> : tc::conv_pair_kernel<8>;
+  const int kidx = nch <= 2 ? 0 : nch <= 5 ? 1 : 2;
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > configured[kidx]) {
+    M0_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[kidx] = smem;
   }
   const int tiles = (boards + 3) / 4;
   int clusters = st->sm_count / 2;
@@ -198,7 +263,7 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::conv_pair_kernel, a_map, w.map_pair, p));
+  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a_map, w.map_pair, p));
   return m0_check_launch("conv_pair_kernel");
 }
 
@@ -481,23 +546,23 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   const int C = c.channels, M = B * 64, act = c.activation;
   const float* none = nullptr;
   // stem: planes -> NHWC half (64 channels, zero padded) -> tensor-core conv3x3 -> GN + act (+ position encoding)
-  TRY(nn_planes_to_nhwc_half(planes, st->planes_h, B, c.planes, s));
-  TRY(conv3x3(st, st->planes_conv, st->planes_convp, st->stem, B, 64, n->t1, nullptr, ACT_NONE, s));
+  PROF("planes_to_nhwc_half", nn_planes_to_nhwc_half(planes, st->planes_h, B, c.planes, s));
+  PROF("conv_other", conv3x3(st, st->planes_conv, st->planes_convp, st->stem, B, 64, n->t1, nullptr, ACT_NONE, s));
   if (c.chess_features) {
-    TRY(nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
+    PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
     float* cur = n->x;
     if (c.piece_square_tables) {
-      TRY(launch_gemm(st, st->a1_mat, st->pst, M, 0, 1, C, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
-      TRY(nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
+      PROF("gemm_pst", launch_gemm(st, st->a1_mat, st->pst, M, 0, 1, C, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+      PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
       cur = n->t2;
     }
-    TRY(conv3x3(st, st->a1_conv, st->a1_convp, st->inter, B, C, n->t1, nullptr, ACT_NONE, s));
-    TRY(nn_groupnorm_mixed(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
+    PROF("conv_other", conv3x3(st, st->a1_conv, st->a1_convp, st->inter, B, C, n->t1, nullptr, ACT_NONE, s));
+    PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
   } else {
-    TRY(nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
+    PROF("groupnorm_f32", nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
   }
   // a1 = act(GN1(x)) of the first block; later blocks get it from the fused SE / residual kernel of their predecessor
-  if (c.blocks > 0) TRY(nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[0].gn1_w, w.blocks[0].gn1_b, st->a1, B, C, act, s));
+  if (c.blocks > 0) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[0].gn1_w, w.blocks[0].gn1_b, st->a1, B, C, act, s));
   int att_seen = 0;
   const int stride = c.infer_attention_stride > 1 ? c.infer_attention_stride : 1;
   for (int i = 0; i < c.blocks; ++i) {
@@ -510,59 +575,62 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     }
     const bool last = (i + 1 == c.blocks);
     // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
-    TRY(conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr));
+    PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr));
     // conv2 with the SE squeeze (half-board column sums) fused into the epilogue
-    TRY(conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, n->t2, nullptr, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr));
+    // (conv2's output is kept in the 16-bit operand format, as under the reference's autocast; the fp32 buffer t2 is reused for it)
+    __nv_bfloat16* t2h = reinterpret_cast<__nv_bfloat16*>(n->t2);
+    PROF("conv2+pool", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, t2h, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr));
     const float* gate = nullptr;
     if (c.se) {
-      TRY(nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
+      PROF("se_gate", nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
       gate = st->se_gate;
     }
     // x += conv2 * gate ; a1 = act(GN1_{i+1}(x)), or half(x) when the attention qkv GEMM consumes x next
     const bool fuse_next = !last && !run_att;
     const bool tc_att = run_att && C == c.attention_heads * 16;
-    TRY(nn_se_apply_gn(n->t2, gate, n->x, fuse_next ? w.blocks[i + 1].gn1_w : nullptr, fuse_next ? w.blocks[i + 1].gn1_b : nullptr,
+    PROF("se_apply_gn", nn_se_apply_gn(t2h, gate, n->x, fuse_next ? w.blocks[i + 1].gn1_w : nullptr, fuse_next ? w.blocks[i + 1].gn1_b : nullptr,
                        (fuse_next || run_att) ? st->a1 : nullptr, B, C, act, s));
     if (run_att) {
       const float* rb = c.attention_relbias ? b.att_rel_bias : nullptr;
       if (tc_att) {
         for (int r0 = 0; r0 < 3 * C; r0 += C)
-          TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, nullptr, st->qkv_h, 3 * C, r0, none, ACT_NONE, 1.0f, s));
-        TRY(nn_attention_tc(st->qkv_h, rb, st->a2, B, C, c.attention_heads, c.attention_unmasked_mix, s));
+          PROF("gemm_qkv", launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, nullptr, st->qkv_h, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+        PROF("attention_tc", nn_attention_tc(st->qkv_h, rb, st->a2, B, C, c.attention_heads, c.attention_unmasked_mix, s));
       } else {
         for (int r0 = 0; r0 < 3 * C; r0 += C)
-          TRY(launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, none, ACT_NONE, 1.0f, s));
-        TRY(nn_attention_f32(n->qkv, rb, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
-        TRY(nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
+          PROF("gemm_qkv", launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+        PROF("attention_f32", nn_attention_f32(n->qkv, rb, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
+        PROF("f32_to_bf16", nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
       }
-      TRY(launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
-      TRY(nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
-      if (!last) TRY(nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
+      PROF("gemm_proj", launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+      PROF("layernorm_residual_f32", nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
+      if (!last) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
     }
   }
   if (!st->heads_tc) return net_forward_heads_f32(n, B, logits, values, s);
   // ---- heads (resnet.py:697-753) on tensor cores; the three small value layers after fc1 stay in fp32 ----
   const int vact = c.value_activation, r = c.policy_factor_rank, rp = st->pol_rank_pad;
-  TRY(nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
+  PROF("f32_to_bf16", nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
   // policy: conv1x1 C->64, GN, act, fc1 + ReLU, fc2 * logit scale
-  TRY(launch_gemm(st, st->a1_mat, st->pol_conv, M, 0, 1, C, 0, 64, n->t1, nullptr, 64, 0, none, ACT_NONE, 1.0f, s));
-  TRY(nn_groupnorm_mixed(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
-  TRY(launch_gemm(st, st->ph_mat, st->pol_fc1, B, 0, 1, 4096, 0, r, nullptr, st->pf_h, rp, 0, w.pol_fc1_b, ACT_RELU, 1.0f, s));
+  PROF("gemm_pol_conv", launch_gemm(st, st->a1_mat, st->pol_conv, M, 0, 1, C, 0, 64, n->t1, nullptr, 64, 0, none, ACT_NONE, 1.0f, s));
+  PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
+  PROF("gemm_pol_fc1", launch_gemm(st, st->ph_mat, st->pol_fc1, B, 0, 1, 4096, 0, r, nullptr, st->pf_h, rp, 0, w.pol_fc1_b, ACT_RELU, 1.0f, s));
   for (int r0 = 0; r0 < c.policy_size; r0 += 320) {
     const int nn = c.policy_size - r0 < 320 ? c.policy_size - r0 : 320;
-    TRY(launch_gemm(st, st->pf_mat, st->pol_fc2, B, 0, 1, rp, r0, 320, logits, nullptr, c.policy_size, r0, w.pol_fc2_b, ACT_NONE, w.policy_logit_scale, s,
+    PROF("gemm_pol_fc2", launch_gemm(st, st->pf_mat, st->pol_fc2, B, 0, 1, rp, r0, 320, logits, nullptr, c.policy_size, r0, w.pol_fc2_b, ACT_NONE, w.policy_logit_scale, s,
                     nullptr, nullptr, nullptr, nn));
   }
   // value: conv1x1 C->128, GN, act, conv1x1 128->128, GN, act, fc1 (+ activation) on tensor cores
-  TRY(launch_gemm(st, st->a1_mat, st->val_conv1, M, 0, 1, C, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
-  TRY(nn_groupnorm_mixed(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
-  TRY(launch_gemm(st, st->vh_conv_mat, st->val_conv2, M, 0, 1, 128, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
-  TRY(nn_groupnorm_mixed(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
+  PROF("gemm_val_conv1", launch_gemm(st, st->a1_mat, st->val_conv1, M, 0, 1, C, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
+  PROF("groupnorm_mixed", nn_groupnorm_mixed(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
+  PROF("gemm_val_conv2", launch_gemm(st, st->vh_conv_mat, st->val_conv2, M, 0, 1, 128, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
+  PROF("groupnorm_mixed", nn_groupnorm_mixed(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
   for (int r0 = 0; r0 < 2 * C; r0 += C)
-    TRY(launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, r0, C, n->vf1, nullptr, 2 * C, r0, w.val_fc1_b, vact, 1.0f, s));
-  TRY(nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
-  TRY(nn_gemm_f32(A_DIRECT, n->vf2, w.val_gate_w, w.val_gate_b, n->vf2, n->vg, B, C, C, C, C, 0, ACT_SIGMOID, 1.0f, s));
-  TRY(nn_gemm_f32(A_DIRECT, n->vg, w.val_fc3_w, w.val_fc3_b, nullptr, values, B, 1, C, C, 1, 0, ACT_TANH, 1.0f, s));
+    PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, r0, C, n->vf1, nullptr, 2 * C, r0, w.val_fc1_b, vact, 1.0f, s));
+  PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
+  PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf2, w.val_gate_w, w.val_gate_b, n->vf2, n->vg, B, C, C, C, C, 0, ACT_SIGMOID, 1.0f, s));
+  PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vg, w.val_fc3_w, w.val_fc3_b, nullptr, values, B, 1, C, C, 1, 0, ACT_TANH, 1.0f, s));
+  if (TcProfiler::get().enabled()) TcProfiler::get().collect();
   return M0_OK;
 }
 

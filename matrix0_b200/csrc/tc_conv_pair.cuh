@@ -16,7 +16,8 @@
 //
 // Work item = (group of 4 boards, channel half).  CTA r of the pair owns boards 4t + 2r, 4t + 2r + 1 (TMEM lanes
 // 0..127 of its own tensor memory).  Warp 0 = TMA producer (both CTAs; every load signals the LEADER's full
-// barrier), warp 1 = MMA issuer (leader CTA only) and TMEM allocator, warps 2..9 = epilogue.
+// barrier), warp 1 = MMA issuer (leader CTA only) and TMEM allocator, warps 4..11 = epilogue (setmaxnreg gives
+// the two epilogue warpgroups 232 registers per thread so a warp's whole share of the accumulator stays in registers).
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -38,11 +39,13 @@ struct ConvPairParams {
   const float* gn_gamma;
   const float* gn_beta;
   float* pool_part;
-  int exp_mode;     // timing experiments only: 4 = skip the epilogue body
+  int exp_mode;     // timing experiments only: 4 = drop the accumulator instead of storing it
   int base_offset;  // set the descriptor base-offset field of the row-shifted A views
 };
 
-static constexpr int CP_THREADS = 320;
+static constexpr int CP_THREADS = 384;   // warpgroup 0: TMA producer, MMA issuer, two idle warps; warpgroups 1-2: epilogue
+static constexpr int CP_EPI_WARP0 = 4;
+static constexpr int CP_REGS_CTRL = 40, CP_REGS_EPI = 232;   // setmaxnreg split of the 64K register file (128*40 + 256*232)
 static constexpr int CP_A_SLOT = 160 * 128;   // 2 boards x 8 y x 10 x rows of 64 channels
 static constexpr int CP_EPI_BYTES = 8 * 32 * 16 * 4 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4;   // transposers + gamma/beta + GN partial sums
 
@@ -105,6 +108,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (base_off << 49) | (2ull << 61);
 }
 
+// NCH = 16-column chunks per epilogue warp held in registers: ceil(N / 64)
+template <int NCH>
 __global__ void __launch_bounds__(CP_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const ConvPairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -152,7 +157,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp < CP_EPI_WARP0) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CP_REGS_CTRL));
+   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
     if (lane == 0) {
       const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
@@ -213,16 +220,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
+   }
   } else {
-    // ===== epilogue (both CTAs): TMEM -> registers -> smem transpose -> coalesced stores, 16 columns at a time =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CP_REGS_EPI));
+    // ===== epilogue (both CTAs): TMEM -> registers (whole share of the warp, then the accumulator is released at once)
+    //       -> GroupNorm / activation in registers -> smem transpose -> coalesced stores, 16 columns at a time =====
     const int quarter = warp & 3;
-    const int cset = (warp - 2) >> 2;
-    float* stg = epi_stage + (warp - 2) * 512;
+    const int cset = (warp - CP_EPI_WARP0) >> 2;        // the two warps of a lane quarter take alternate 16-column chunks
+    float* stg = epi_stage + (warp - CP_EPI_WARP0) * 512;
     const bool fused_gn = p.gn_gamma != nullptr;
-    const int epi_tid = ((warp - 2) << 5) | lane;
+    const int epi_tid = ((warp - CP_EPI_WARP0) << 5) | lane;
     const uint32_t lead_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
     const int nchunks = nh >> 4;
     const int M = p.boards * 64;
+    const int act = p.act;
     if (fused_gn) {
       for (int c = epi_tid; c < p.N; c += 256) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -236,16 +247,26 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int row0 = t * 256 + rank * 128 + quarter * 32;
         const uint32_t tmem_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
         float* stats = s_stats + buf * 128;
-        if (!(p.exp_mode & 4)) {
-          if (fused_gn) {
-            for (int ci = cset; ci < nchunks; ci += 2) {
-              uint32_t r[16];
-              tmem_ld_32x16(tmem_row + (uint32_t)(ci * 16), r);
-              tmem_ld_wait();
+        uint32_t r[NCH][16];
+        const bool live = !(p.exp_mode & 4);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          if (live && cset + 2 * k < nchunks) tmem_ld_32x16(tmem_row + (uint32_t)((cset + 2 * k) * 16), r[k]);
+        tmem_ld_wait();
+        // the accumulator is free again: the MMAs of the work item after next may overwrite it while this one is stored
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_empty + buf * 8u);
+        if (!live) continue;
+        if (fused_gn) {
+          // per (half board = this warp, group of 16 channels = one chunk) sum and sum of squares
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            if (cset + 2 * k < nchunks) {
               float s0 = 0.f, q0 = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float a = __uint_as_float(r[j]);
+                const float a = __uint_as_float(r[k][j]);
                 s0 += a;
                 q0 = fmaf(a, a, q0);
               }
@@ -254,87 +275,93 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, off);
                 q0 += __shfl_xor_sync(0xFFFFFFFFu, q0, off);
               }
-              if (lane == 0) {
-                stats[(quarter * 16 + ci) * 2] = s0;
-                stats[(quarter * 16 + ci) * 2 + 1] = q0;
-              }
+              if (lane == 0) *reinterpret_cast<float2*>(stats + (quarter * 16 + cset + 2 * k) * 2) = make_float2(s0, q0);
             }
-            // the four warps that hold one board exchange their partial sums
-            if (quarter < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
-            else asm volatile("bar.sync 3, 128;" ::: "memory");
           }
-          for (int ci = cset; ci < nchunks; ci += 2) {
-            const int col = h * nh + ci * 16;
-            uint32_t r[16];
-            tmem_ld_32x16(tmem_row + (uint32_t)(ci * 16), r);
-            tmem_ld_wait();
-            if (fused_gn) {
-              const float* sa = stats + ((quarter & 2) * 16 + ci) * 2;
-              const float* sb = stats + ((quarter | 1) * 16 + ci) * 2;
-              const float mean = (sa[0] + sb[0]) * (1.0f / 1024.0f);
-              const float var = fmaxf((sa[1] + sb[1]) * (1.0f / 1024.0f) - mean * mean, 0.0f);
-              const float rstd = rsqrtf(var + 1e-5f);
-              const int act = p.act;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float gm = s_gamma[col + j] * rstd;
-                const float y = fmaf(__uint_as_float(r[j]) - mean, gm, s_beta[col + j]);
-                r[j] = __float_as_uint(tc_act(y, act));
-              }
-            }
-            // lane = row; 16-byte chunk q of row i sits at chunk position q ^ ((i >> 1) & 3) (conflict-free both ways)
-            const int sw = (lane >> 1) & 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(stg + lane * 16 + ((q ^ sw) << 2)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-            __syncwarp();
-            if (p.pool_part && row0 < M) {
-              // column sums of this half board: lane = (row parity, column)
-              const int c = lane & 15, par = lane >> 4;
-              float cs_sum = 0.f;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int rr = 2 * i + par;
-                cs_sum += stg[rr * 16 + ((((c >> 2) ^ ((rr >> 1) & 3)) << 2) | (c & 3))];
-              }
-              cs_sum += __shfl_xor_sync(0xFFFFFFFFu, cs_sum, 16);
-              if (par == 0) p.pool_part[(size_t)(row0 >> 5) * p.N + col + c] = cs_sum;
-            }
-            if (p.out_f32) {
-              const int q = lane & 3;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = (lane >> 2) + 8 * i;
-                const int m = row0 + rr;
-                if (m < M) {
-                  uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((q ^ ((rr >> 1) & 3)) << 2));
-                  *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + col + 4 * q) = v;
-                }
-              }
-            }
-            if (p.out_half) {
-              const int hq = lane & 1;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const int rr = (lane >> 1) + 16 * i;
-                const int m = row0 + rr;
-                if (m < M) {
-                  const int sw2 = (rr >> 1) & 3;
-                  float4 lo = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq) ^ sw2) << 2));
-                  float4 hi = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq + 1) ^ sw2) << 2));
-                  uint4 pk;
-                  pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
-                  pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
-                  *reinterpret_cast<uint4*>(p.out_half + (size_t)m * p.ldc + col + 8 * hq) = pk;
-                }
-              }
-            }
-            __syncwarp();
-          }
+          // the four warps that hold one board exchange their partial sums
+          if (quarter < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+          else asm volatile("bar.sync 3, 128;" ::: "memory");
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_empty + buf * 8u);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int ci = cset + 2 * k;
+          if (ci >= nchunks) break;
+          const int col = h * nh + ci * 16;
+          if (fused_gn) {
+            const float2 sa = *reinterpret_cast<const float2*>(stats + ((quarter & 2) * 16 + ci) * 2);
+            const float2 sb = *reinterpret_cast<const float2*>(stats + ((quarter | 1) * 16 + ci) * 2);
+            const float mean = (sa.x + sb.x) * (1.0f / 1024.0f);
+            const float var = fmaxf((sa.y + sb.y) * (1.0f / 1024.0f) - mean * mean, 0.0f);
+            const float rstd = rsqrtf(var + 1e-5f);
+            float y[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + col + 4 * q);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_beta + col + 4 * q);
+              y[4 * q + 0] = fmaf(__uint_as_float(r[k][4 * q + 0]) - mean, g4.x * rstd, b4.x);
+              y[4 * q + 1] = fmaf(__uint_as_float(r[k][4 * q + 1]) - mean, g4.y * rstd, b4.y);
+              y[4 * q + 2] = fmaf(__uint_as_float(r[k][4 * q + 2]) - mean, g4.z * rstd, b4.z);
+              y[4 * q + 3] = fmaf(__uint_as_float(r[k][4 * q + 3]) - mean, g4.w * rstd, b4.w);
+            }
+            if (act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) y[j] = __fdividef(y[j], 1.0f + __expf(-y[j]));
+            } else if (act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(y[j]);
+          }
+          // lane = row; 16-byte chunk q of row i sits at chunk position q ^ ((i >> 1) & 3) (conflict-free both ways)
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 16 + ((q ^ sw) << 2)) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
+          __syncwarp();
+          if (p.pool_part && row0 < M) {
+            // column sums of this half board: lane = (row parity, column)
+            const int c = lane & 15, par = lane >> 4;
+            float cs_sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int rr = 2 * i + par;
+              cs_sum += stg[rr * 16 + ((((c >> 2) ^ ((rr >> 1) & 3)) << 2) | (c & 3))];
+            }
+            cs_sum += __shfl_xor_sync(0xFFFFFFFFu, cs_sum, 16);
+            if (par == 0) p.pool_part[(size_t)(row0 >> 5) * p.N + col + c] = cs_sum;
+          }
+          if (p.out_f32) {
+            const int q = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (lane >> 2) + 8 * i;
+              const int m = row0 + rr;
+              if (m < M) {
+                uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((q ^ ((rr >> 1) & 3)) << 2));
+                *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + col + 4 * q) = v;
+              }
+            }
+          }
+          if (p.out_half) {
+            const int hq = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int rr = (lane >> 1) + 16 * i;
+              const int m = row0 + rr;
+              if (m < M) {
+                const int sw2 = (rr >> 1) & 3;
+                float4 lo = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq) ^ sw2) << 2));
+                float4 hi = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq + 1) ^ sw2) << 2));
+                uint4 pk;
+                pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
+                pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
+                *reinterpret_cast<uint4*>(p.out_half + (size_t)m * p.ldc + col + 8 * hq) = pk;
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
     }
   }

@@ -201,10 +201,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b, int fp16) {
 __device__ __forceinline__ float tc_act(float x, int act) {
   switch (act) {
     case ACT_RELU: return x > 0.0f ? x : 0.0f;
-    case ACT_SILU: return x / (1.0f + __expf(-x));
+    case ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));   // 16-bit outputs: MUFU reciprocal instead of the IEEE division
     case ACT_LEAKY: return x > 0.0f ? x : 0.05f * x;
     case ACT_TANH: return tanhf(x);
-    case ACT_SIGMOID: return 1.0f / (1.0f + __expf(-x));
+    case ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-x));
     default: return x;
   }
 }
