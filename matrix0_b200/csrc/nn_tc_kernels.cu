@@ -38,6 +38,48 @@ __global__ void pad_stem_kernel(const float* __restrict__ w, float* __restrict__
   int ci = i & 63, tap = (i >> 6) % 9, co = i / (9 * 64);
   out[i] = ci < P ? w[(co * 9 + tap) * P + ci] : 0.0f;
 }
+// SE squeeze folded through conv2 (tc_conv_pair.cuh, ConvPairParams::prims).  With P = the 12 x C half-board sums of conv2's INPUT
+// (k = (half*6 + j)*C + ci), the board mean of conv2's output channel c is (1/64) sum_k Wcomb[c][k] P[k], where zero padding turns
+// each tap (dy, dx) into "all squares minus an edge rank minus an edge file plus their corner":
+//   j = 0 total: + all 9 taps | j = 1 edge rank (rank 1 in half 0, rank 8 in half 1): - the taps that look past it
+//   j = 2 file a: - taps dx=+1 | j = 3 file h: - taps dx=-1 | j = 4, 5 corners on file a / h: + the one diagonal tap.
+// The first SE layer is linear in the mean, so it is folded in as well: out[u][k] = (1/64) sum_c W1[u][c] Wcomb[c][k].
+__global__ void se_fold_kernel(const float* __restrict__ conv_w, const float* __restrict__ w1, float* __restrict__ out, int C, int hid) {
+  const int K = 12 * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hid * K) return;
+  const int u = i / K, k = i - u * K;
+  const int ci = k % C, j = (k / C) % 6, hb = k / (6 * C);
+  // signed tap set of this (half, j): bit t of plus / minus
+  unsigned plus = 0, minus = 0;
+  switch (j) {
+    case 0: plus = 0x1FF; break;
+    case 1: minus = hb ? 0x007 : 0x1C0; break;          // rank 8 is lost by dy = -1 (taps 0..2), rank 1 by dy = +1 (taps 6..8)
+    case 2: minus = 0x124; break;                       // file a is lost by dx = +1 (taps 2, 5, 8)
+    case 3: minus = 0x049; break;                       // file h is lost by dx = -1 (taps 0, 3, 6)
+    case 4: plus = hb ? (1u << 2) : (1u << 8); break;   // a8 comes back for (dy -1, dx +1), a1 for (dy +1, dx +1)
+    default: plus = hb ? (1u << 0) : (1u << 6); break;  // h8 for (dy -1, dx -1), h1 for (dy +1, dx -1)
+  }
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* wr = conv_w + (size_t)c * 9 * C + ci;
+    float wsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (plus & (1u << t)) wsum += wr[t * C];
+      if (minus & (1u << t)) wsum -= wr[t * C];
+    }
+    acc = fmaf(w1[u * C + c], wsum, acc);
+  }
+  out[i] = acc * (1.0f / 64.0f);
+}
+// in [rows][cols] -> out [rows][cols_pad] with zero padding columns
+__global__ void pad_cols_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int cols_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols_pad) return;
+  const int r = i / cols_pad, c = i - r * cols_pad;
+  out[i] = c < cols ? in[r * cols + c] : 0.0f;
+}
 }  // namespace m0
 
 namespace {
@@ -106,6 +148,7 @@ int pick_cluster(int n_part) {
 
 struct TcBlock {
   TcWeight conv1, conv2, qkv, proj;
+  TcWeight se_fold, se_w2;   // [hid][12C] first SE layer folded through conv2, [C][hid padded to 64] second SE layer
 };
 
 struct TcState {
@@ -116,6 +159,11 @@ struct TcState {
   // SE: pooled half-board sums [cap][2][C], hidden [cap][hid], gate [cap][C]; W1 duplicated over the two halves and scaled by 1/64
   float *pool = nullptr, *se_hid = nullptr, *se_gate = nullptr;
   std::vector<float*> se_w1t, se_w2t;   // per block [C][hid], [hid][C]
+  // fused SE path: half-board sums of conv2's input [cap][12C] and the hidden layer [cap][hid_pad] in half precision
+  bool se_fused = false;
+  int hid_pad = 0;
+  __nv_bfloat16 *prims = nullptr, *se_hid_h = nullptr;
+  CUtensorMap prims_mat, se_hid_mat;
   // stem on tensor cores: planes as NHWC half with 64 channels, weights [C][9*64]
   __nv_bfloat16* planes_h = nullptr;
   __nv_bfloat16* qkv_h = nullptr;   // [cap][64][3C] half (attention input)
@@ -212,8 +260,15 @@ bool pair_ok(int n) {
   return on && n % 32 == 0 && n >= 64 && n <= 512;
 }
 
+struct ConvFusion {   // optional fused epilogue inputs / outputs of the CTA-pair convolution (tc_conv_pair.cuh)
+  float* resid_x = nullptr;
+  const float* gate = nullptr;
+  __nv_bfloat16* prims = nullptr;
+};
+
 int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int boards, int cin, float* out_f32, __nv_bfloat16* out_half,
-                     int ldc, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr) {
+                     int ldc, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr,
+                     const ConvFusion* fuse = nullptr) {
   tc::ConvPairParams p;
   memset(&p, 0, sizeof(p));
   p.boards = boards;
@@ -227,6 +282,7 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   p.gn_gamma = gn_gamma;
   p.gn_beta = gn_beta;
   p.pool_part = pool_part;
+  if (fuse) { p.resid_x = fuse->resid_x; p.gate = fuse->gate; p.prims = fuse->prims; }
   static int em = -1, bo = -1, cap = -1;
   if (em < 0) { em = env_int("M0_TC_EXP", 0); bo = env_int("M0_CP_BASEOFF", 0); cap = env_int("M0_TC_STAGES", 0); }
   p.exp_mode = em;
@@ -240,9 +296,11 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   const size_t smem = (size_t)stages * stage_bytes + tc::CP_EPI_BYTES + 1024 + 256;
   // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
   const int nch = (w.n + 63) / 64;
-  auto kernel = nch <= 2 ? tc::conv_pair_kernel<2> : nch <= 5 ? tc::conv_pair_kernel<5> : tc::conv_pair_kernel<8>;
-  const int kidx = nch <= 2 ? 0 : nch <= 5 ? 1 : 2;
-  static size_t configured[3] = {0, 0, 0};
+  const bool fz = fuse && (fuse->resid_x || fuse->prims);
+  auto kernel = fz ? (nch <= 2 ? tc::conv_pair_kernel<2, true> : nch <= 5 ? tc::conv_pair_kernel<5, true> : tc::conv_pair_kernel<8, true>)
+                   : (nch <= 2 ? tc::conv_pair_kernel<2, false> : nch <= 5 ? tc::conv_pair_kernel<5, false> : tc::conv_pair_kernel<8, false>);
+  const int kidx = (nch <= 2 ? 0 : nch <= 5 ? 1 : 2) + (fz ? 3 : 0);
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
   if (smem > configured[kidx]) {
     M0_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[kidx] = smem;
@@ -364,8 +422,9 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
 // 3x3 convolution of B boards with all C_out channels in one launch: CTA-pair kernel when the weight supports it
 int conv3x3(TcState* st, const CUtensorMap& a_map, const CUtensorMap& a_map_pair, const TcWeight& w, int B, int cin, float* out_f32,
             __nv_bfloat16* out_half, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr,
-            float* pool_part = nullptr) {
-  if (w.pair) return launch_conv_pair(st, a_map_pair, w, B, cin, out_f32, out_half, w.n, act, s, gn_gamma, gn_beta, pool_part);
+            float* pool_part = nullptr, const ConvFusion* fuse = nullptr) {
+  if (w.pair) return launch_conv_pair(st, a_map_pair, w, B, cin, out_f32, out_half, w.n, act, s, gn_gamma, gn_beta, pool_part, fuse);
+  if (fuse) { m0_set_error("fused SE / residual epilogue needs the CTA-pair convolution"); return M0_ERR_ARG; }
   return launch_gemm(st, a_map, w, B * 64, 1, 9, cin, 0, w.n, out_f32, out_half, w.n, 0, nullptr, act, 1.0f, s, gn_gamma, gn_beta, pool_part);
 }
 
@@ -383,6 +442,9 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   if (st->ph_h) cudaFree(st->ph_h);
   if (st->pf_h) cudaFree(st->pf_h);
   if (st->vh_h) cudaFree(st->vh_h);
+  if (st->prims) cudaFree(st->prims);
+  if (st->se_hid_h) cudaFree(st->se_hid_h);
+  st->prims = st->se_hid_h = nullptr;
   st->qkv_h = st->ph_h = st->pf_h = st->vh_h = nullptr;
   st->a1 = st->a2 = nullptr;
   st->pool = st->se_hid = st->se_gate = nullptr;
@@ -403,6 +465,16 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
     TRY(make_map_2d(&st->pf_mat, st->pf_h, (uint64_t)need, rp, 128));
     TRY(make_map_2d(&st->vh_conv_mat, st->vh_h, (uint64_t)need * 64, 128, 128));
     TRY(make_map_2d(&st->vh_fc_mat, st->vh_h, (uint64_t)need, 8192, 128));
+  }
+  if (st->se_fused && n->cfg.se) {
+    // rows are padded to whole 128-row GEMM tiles; the padding columns of the hidden layer stay zero
+    const size_t rows = ((size_t)need + 127) / 128 * 128;
+    M0_CUDA_TRY(cudaMalloc((void**)&st->prims, rows * 12 * C * 2));
+    M0_CUDA_TRY(cudaMalloc((void**)&st->se_hid_h, rows * st->hid_pad * 2));
+    M0_CUDA_TRY(cudaMemset(st->prims, 0, rows * 12 * C * 2));
+    M0_CUDA_TRY(cudaMemset(st->se_hid_h, 0, rows * st->hid_pad * 2));
+    TRY(make_map_2d(&st->prims_mat, st->prims, rows, 12 * C, 128));
+    TRY(make_map_2d(&st->se_hid_mat, st->se_hid_h, rows, (uint64_t)st->hid_pad, 128));
   }
   M0_CUDA_TRY(cudaMemset(st->planes_h, 0, (size_t)need * 64 * 64 * 2));
   TRY(make_map_nhwc(&st->planes_conv, st->planes_h, need, 64));
@@ -494,11 +566,27 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
       if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, C, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, C, s)) != M0_OK) break;
     }
+    // fused SE + residual epilogue of conv2 (M0_TC_FUSE_SE=0 keeps the separate SE / residual kernels)
+    st->hid_pad = (c.se_hidden + 63) / 64 * 64;
+    st->se_fused = env_int("M0_TC_FUSE_SE", 0) != 0 && pair_ok(C) && (!c.se || (c.se_hidden % 16 == 0 && c.se_hidden <= 256));
     st->blocks.resize(c.blocks);
     for (int i = 0; i < c.blocks && rc == M0_OK; ++i) {
       const m0_block_weights& b = n->w.blocks[i];
       if ((rc = make_weight(st, &st->blocks[i].conv1, b.conv1_w, C, 9 * C, C, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->blocks[i].conv2, b.conv2_w, C, 9 * C, C, s)) != M0_OK) break;
+      if (st->se_fused && c.se) {
+        const int hid = c.se_hidden, K = 12 * C, hp = st->hid_pad;
+        float *fold = nullptr, *w2p = nullptr;
+        if ((rc = m0_check_cuda(cudaMalloc((void**)&fold, (size_t)hid * K * 4), "cudaMalloc se_fold")) != M0_OK) break;
+        st->allocs.push_back(fold);
+        if ((rc = m0_check_cuda(cudaMalloc((void**)&w2p, (size_t)C * hp * 4), "cudaMalloc se_w2")) != M0_OK) break;
+        st->allocs.push_back(w2p);
+        se_fold_kernel<<<(hid * K + 255) / 256, 256, 0, s>>>(b.conv2_w, b.se_w1, fold, C, hid);
+        pad_cols_kernel<<<(C * hp + 255) / 256, 256, 0, s>>>(b.se_w2, w2p, C, hid, hp);
+        if ((rc = m0_check_launch("se_fold")) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].se_fold, fold, hid, K, hid, s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].se_w2, w2p, C, hp, C, s)) != M0_OK) break;
+      }
       if (b.has_attention) {
         if ((rc = make_weight(st, &st->blocks[i].qkv, b.att_qkv_w, 3 * C, C, C, s)) != M0_OK) break;
         if ((rc = make_weight(st, &st->blocks[i].proj, b.att_proj_w, C, C, C, s)) != M0_OK) break;
@@ -531,6 +619,8 @@ void tc_net_release(::m0_net* n) {
     if (st->ph_h) cudaFree(st->ph_h);
     if (st->pf_h) cudaFree(st->pf_h);
     if (st->vh_h) cudaFree(st->vh_h);
+    if (st->prims) cudaFree(st->prims);
+    if (st->se_hid_h) cudaFree(st->se_hid_h);
     delete st;
   }
   delete all;
@@ -574,22 +664,41 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
       run_att = (att_seen % stride) == 0;
     }
     const bool last = (i + 1 == c.blocks);
-    // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
-    PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr));
-    // conv2 with the SE squeeze (half-board column sums) fused into the epilogue
-    // (conv2's output is kept in the 16-bit operand format, as under the reference's autocast; the fp32 buffer t2 is reused for it)
-    __nv_bfloat16* t2h = reinterpret_cast<__nv_bfloat16*>(n->t2);
-    PROF("conv2+pool", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, t2h, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr));
-    const float* gate = nullptr;
-    if (c.se) {
-      PROF("se_gate", nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
-      gate = st->se_gate;
-    }
-    // x += conv2 * gate ; a1 = act(GN1_{i+1}(x)), or half(x) when the attention qkv GEMM consumes x next
     const bool fuse_next = !last && !run_att;
     const bool tc_att = run_att && C == c.attention_heads * 16;
-    PROF("se_apply_gn", nn_se_apply_gn(t2h, gate, n->x, fuse_next ? w.blocks[i + 1].gn1_w : nullptr, fuse_next ? w.blocks[i + 1].gn1_b : nullptr,
-                       (fuse_next || run_att) ? st->a1 : nullptr, B, C, act, s));
+    __nv_bfloat16* next_a = (fuse_next || run_att) ? st->a1 : nullptr;
+    if (st->se_fused) {
+      // conv1: a2 = act(GN2(conv1(a1))) and, for SE, the half-board sums of a2 that determine conv2's pooled output
+      ConvFusion f1;
+      f1.prims = c.se ? st->prims : nullptr;
+      PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr, &f1));
+      if (c.se) {
+        // SE excitation before conv2 runs: hidden = act(fold * sums + b1), gate = sigmoid(W2 hidden + b2)  (resnet.py:61-64)
+        PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, nullptr, st->se_hid_h, st->hid_pad, 0, b.se_b1, act, 1.0f, s));
+        PROF("se_fc2", launch_gemm(st, st->se_hid_mat, tb.se_w2, B, 0, 1, st->hid_pad, 0, C, st->se_gate, nullptr, C, 0, b.se_b2, ACT_SIGMOID, 1.0f, s));
+      }
+      // conv2 with the whole block tail in its epilogue: x += gate * conv2 ; a1 = act(GN1_{i+1}(x)) (or half(x) before attention)
+      ConvFusion f2;
+      f2.resid_x = n->x;
+      f2.gate = c.se ? st->se_gate : nullptr;
+      PROF("conv2+se+res+gn", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, next_a, act, s, fuse_next ? w.blocks[i + 1].gn1_w : nullptr,
+                                      fuse_next ? w.blocks[i + 1].gn1_b : nullptr, nullptr, &f2));
+    } else {
+      // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
+      PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr));
+      // conv2 with the SE squeeze (half-board column sums) fused into the epilogue
+      // (conv2's output is kept in the 16-bit operand format, as under the reference's autocast; the fp32 buffer t2 is reused for it)
+      __nv_bfloat16* t2h = reinterpret_cast<__nv_bfloat16*>(n->t2);
+      PROF("conv2+pool", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, t2h, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr));
+      const float* gate = nullptr;
+      if (c.se) {
+        PROF("se_gate", nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
+        gate = st->se_gate;
+      }
+      // x += conv2 * gate ; a1 = act(GN1_{i+1}(x)), or half(x) when the attention qkv GEMM consumes x next
+      PROF("se_apply_gn", nn_se_apply_gn(t2h, gate, n->x, fuse_next ? w.blocks[i + 1].gn1_w : nullptr, fuse_next ? w.blocks[i + 1].gn1_b : nullptr,
+                                         next_a, B, C, act, s));
+    }
     if (run_att) {
       const float* rb = c.attention_relbias ? b.att_rel_bias : nullptr;
       if (tc_att) {

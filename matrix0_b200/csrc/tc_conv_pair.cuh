@@ -39,6 +39,18 @@ struct ConvPairParams {
   const float* gn_gamma;
   const float* gn_beta;
   float* pool_part;
+  // SE + residual fusion (conv2 of a residual block):
+  //   resid_x != null: x_new = resid_x + gate[board][n] * acc (gate null -> 1), written back to resid_x (fp32, same ldc); then
+  //                    gn_gamma != null -> out_half = half(act(GroupNorm(x_new))) (bn1 + activation of the NEXT block),
+  //                    else out_half (if any) = half(x_new)
+  //   prims != null  : (on the GroupNorm'ed output of conv1 = the input of conv2) prims[(board*2 + half)][6][N], half precision:
+  //                    per half board and channel {sum of the 32 squares, sum of the board-edge rank, sum of file a, sum of file h,
+  //                    corner on file a, corner on file h}.  The mean over the board of the NEXT 3x3 convolution's output is a
+  //                    linear function of these (zero padding only removes edge ranks / files), which lets the SE gate of
+  //                    conv2 be computed BEFORE conv2 runs (nn_tc_kernels.cu: se_fold_kernel).
+  float* resid_x;
+  const float* gate;
+  __nv_bfloat16* prims;
   int exp_mode;     // timing experiments only: 4 = drop the accumulator instead of storing it
   int base_offset;  // set the descriptor base-offset field of the row-shifted A views
 };
@@ -47,7 +59,7 @@ static constexpr int CP_THREADS = 384;   // warpgroup 0: TMA producer, MMA issue
 static constexpr int CP_EPI_WARP0 = 4;
 static constexpr int CP_REGS_CTRL = 40, CP_REGS_EPI = 232;   // setmaxnreg split of the 64K register file (128*40 + 256*232)
 static constexpr int CP_A_SLOT = 160 * 128;   // 2 boards x 8 y x 10 x rows of 64 channels
-static constexpr int CP_EPI_BYTES = 8 * 32 * 16 * 4 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4;   // transposers + gamma/beta + GN partial sums
+static constexpr int CP_EPI_BYTES = 8 * 32 * 16 * 4 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4 + 8 * 128 * 4;   // transposers + gamma/beta + GN partial sums + SE gates
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -109,7 +121,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
 }
 
 // NCH = 16-column chunks per epilogue warp held in registers: ceil(N / 64)
-template <int NCH>
+// FUSE compiles the SE / residual / half-board-sum epilogues in (kept out of the plain kernels: code size costs instruction fetch)
+template <int NCH, bool FUSE>
 __global__ void __launch_bounds__(CP_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const ConvPairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -121,7 +134,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   float* s_gamma = epi_stage + 8 * 512;   // [512]
   float* s_beta = s_gamma + 512;          // [512]
   float* s_stats = s_beta + 512;          // [2 accumulators][4 quarters][16 groups][sum, sumsq]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stats + 256);
+  float* s_gate = s_stats + 256;          // [8 epilogue warps][NCH * 16]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_gate + 8 * 128);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], only the leader's are used
@@ -228,7 +242,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int quarter = warp & 3;
     const int cset = (warp - CP_EPI_WARP0) >> 2;        // the two warps of a lane quarter take alternate 16-column chunks
     float* stg = epi_stage + (warp - CP_EPI_WARP0) * 512;
+    float* wgate = s_gate + (warp - CP_EPI_WARP0) * (NCH * 16);   // this warp's SE gates of the current work item
     const bool fused_gn = p.gn_gamma != nullptr;
+    const bool resid = FUSE && p.resid_x != nullptr;
+    const bool want_prims = FUSE && p.prims != nullptr;
     const int epi_tid = ((warp - CP_EPI_WARP0) << 5) | lane;
     const uint32_t lead_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
     const int nchunks = nh >> 4;
@@ -242,13 +259,46 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       for (int h = 0; h < 2; ++h, ++unit) {
         const uint32_t buf = unit & 1u;
+        const int row0 = t * 256 + rank * 128 + quarter * 32;
+        const int m_lane = row0 + lane;
+        const bool live = !(p.exp_mode & 4);
+        // residual stream of this warp's rows and the SE gates of its board: requested before the accumulator is ready
+        float xr[NCH][16];
+        if (resid && live) {
+          const float* xrow = p.resid_x + (size_t)m_lane * p.ldc + h * nh;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const int ci = cset + 2 * k;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ci < nchunks && m_lane < M && !(p.exp_mode & 32)) v = *reinterpret_cast<const float4*>(xrow + ci * 16 + 4 * q);
+              xr[k][4 * q] = v.x; xr[k][4 * q + 1] = v.y; xr[k][4 * q + 2] = v.z; xr[k][4 * q + 3] = v.w;
+            }
+          }
+          if (p.gate) {
+            const int bq = row0 >> 6;
+            const int k = lane >> 2, q = lane & 3, ci = cset + 2 * k;
+            if (k < NCH && ci < nchunks && row0 < M)
+              *reinterpret_cast<float4*>(wgate + k * 16 + 4 * q) = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bq * p.N + h * nh + ci * 16 + 4 * q));
+          }
+        }
+        if (resid && live) {
+          // pull the residual rows of the NEXT work item into L2 while this one is processed (its loads above then hit L2)
+          const int nt = h ? t + num_clusters : t, nh2 = h ? 0 : 1;
+          const int nm = nt * 256 + rank * 128 + quarter * 32 + lane;
+          if (nt < num_tiles && nm < M) {
+            const float* nx = p.resid_x + (size_t)nm * p.ldc + nh2 * nh;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+              if (cset + 2 * k < nchunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (cset + 2 * k) * 16));
+          }
+        }
         mbar_wait(&tmem_full_bar[buf], (unit >> 1) & 1u);
         tc_fence_after();
-        const int row0 = t * 256 + rank * 128 + quarter * 32;
         const uint32_t tmem_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
         float* stats = s_stats + buf * 128;
         uint32_t r[NCH][16];
-        const bool live = !(p.exp_mode & 4);
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
           if (live && cset + 2 * k < nchunks) tmem_ld_32x16(tmem_row + (uint32_t)((cset + 2 * k) * 16), r[k]);
@@ -258,6 +308,64 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_empty + buf * 8u);
         if (!live) continue;
+        if (resid) {
+          // x_new = x + gate * conv  (SE excitation + residual add, resnet.py:68-80), written back in place
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const int ci = cset + 2 * k;
+            if (ci >= nchunks) break;
+            const int col = h * nh + ci * 16;
+            if (p.gate) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 g4 = *reinterpret_cast<const float4*>(wgate + k * 16 + 4 * q);
+                r[k][4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 0]), g4.x, xr[k][4 * q + 0]));
+                r[k][4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 1]), g4.y, xr[k][4 * q + 1]));
+                r[k][4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 2]), g4.z, xr[k][4 * q + 2]));
+                r[k][4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 3]), g4.w, xr[k][4 * q + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(__uint_as_float(r[k][j]) + xr[k][j]);
+            }
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(stg + lane * 16 + ((q ^ sw) << 2)) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
+            __syncwarp();
+            {
+              const int q = lane & 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                const int m = row0 + rr;
+                if (m < M && !(p.exp_mode & 64)) {
+                  uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((q ^ ((rr >> 1) & 3)) << 2));
+                  *reinterpret_cast<uint4*>(p.resid_x + (size_t)m * p.ldc + col + 4 * q) = v;
+                }
+              }
+            }
+            if (!fused_gn && p.out_half) {   // the attention qkv GEMM takes the raw residual stream in half precision
+              const int hq = lane & 1;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int rr = (lane >> 1) + 16 * i;
+                const int m = row0 + rr;
+                if (m < M) {
+                  const int sw2 = (rr >> 1) & 3;
+                  float4 lo = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq) ^ sw2) << 2));
+                  float4 hi = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq + 1) ^ sw2) << 2));
+                  uint4 pk;
+                  pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
+                  pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
+                  *reinterpret_cast<uint4*>(p.out_half + (size_t)m * p.ldc + col + 8 * hq) = pk;
+                }
+              }
+            }
+            __syncwarp();
+          }
+          if (!fused_gn) continue;
+        }
         if (fused_gn) {
           // per (half board = this warp, group of 16 channels = one chunk) sum and sum of squares
 #pragma unroll
@@ -330,6 +438,33 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             cs_sum += __shfl_xor_sync(0xFFFFFFFFu, cs_sum, 16);
             if (par == 0) p.pool_part[(size_t)(row0 >> 5) * p.N + col + c] = cs_sum;
+          }
+          if (want_prims && row0 < M) {
+            // sums of this half board that determine the SE squeeze of the NEXT convolution's output (see ConvPairParams::prims):
+            // lane = (row parity, column); row rr = 2i + par is square (y = rr >> 3, x = rr & 7) of the half board
+            const int c = lane & 15, par = lane >> 4, hb = quarter & 1;
+            const int edge = hb ? 3 : 0;   // the board's first / last rank inside this half
+            float tsum = 0.f, rsum = 0.f, c0 = 0.f, c7 = 0.f, k0 = 0.f, k7 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int rr = 2 * i + par;
+              const float v = stg[rr * 16 + ((((c >> 2) ^ ((rr >> 1) & 3)) << 2) | (c & 3))];
+              tsum += v;
+              const bool on_edge = (i >> 2) == edge;
+              rsum += on_edge ? v : 0.f;
+              if ((i & 3) == 0) { c0 += par == 0 ? v : 0.f; k0 += (on_edge && par == 0) ? v : 0.f; }
+              if ((i & 3) == 3) { c7 += par == 1 ? v : 0.f; k7 += (on_edge && par == 1) ? v : 0.f; }
+            }
+            tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, 16); rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, 16);
+            c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, 16); c7 += __shfl_xor_sync(0xFFFFFFFFu, c7, 16);
+            k0 += __shfl_xor_sync(0xFFFFFFFFu, k0, 16); k7 += __shfl_xor_sync(0xFFFFFFFFu, k7, 16);
+            __nv_bfloat16* pp = p.prims + (size_t)(row0 >> 5) * 6 * p.N + col + c;
+            const float v0 = par ? c7 : tsum, v1 = par ? k0 : rsum, v2 = par ? k7 : c0;
+            const int j0 = par ? 3 : 0, j1 = par ? 4 : 1, j2 = par ? 5 : 2;
+            const uint32_t h01 = pack_half2(v0, v1, p.fp16), h2 = pack_half2(v2, 0.f, p.fp16);
+            reinterpret_cast<uint16_t*>(pp)[(size_t)j0 * p.N] = (uint16_t)(h01 & 0xFFFFu);
+            reinterpret_cast<uint16_t*>(pp)[(size_t)j1 * p.N] = (uint16_t)(h01 >> 16);
+            reinterpret_cast<uint16_t*>(pp)[(size_t)j2 * p.N] = (uint16_t)(h2 & 0xFFFFu);
           }
           if (p.out_f32) {
             const int q = lane & 3;
