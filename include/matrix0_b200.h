@@ -183,6 +183,12 @@ int m0_net_forward(m0_net* net, const float* d_planes, int B, float* d_logits, f
  * (k = (ky*3+kx)*cin + ci, nn.Conv2d of resnet.py:32-34); taps = 1: d_act_bf16[boards*64][cin] x d_w_bf16[n][cin]^T.
  * d_out_f32[boards*64][n].  boards even, cin % 64 == 0, n % 16 == 0, n <= 320. */
 int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, int boards, int cin, int n, int taps, float* d_out_f32, void* stream);
+/* Per-launch-site CUDA-event timing of the tensor-core forward (measurement aid, no reference counterpart): after
+ * m0_profile_enable(1) every kernel launch of m0_net_forward (precision 1, 2) is bracketed by events on its stream;
+ * m0_profile_get returns the accumulated milliseconds and launch count of one site ("conv1+gn", "conv2+pool",
+ * "se_apply_gn", "attention_tc", ... ; NULL = all sites).  m0_profile_enable(0) switches it off and clears the table. */
+int m0_profile_enable(int enable);
+int m0_profile_get(const char* name, double* total_ms, long long* launches);
 /* forward(x, return_ssl=True) (resnet.py:736-745): d_ssl_out[h] float32[B][k_h][8][8] for each SSL head (fp32 path) */
 int m0_net_forward_ssl(m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, float* const* d_ssl_out, void* stream);
 

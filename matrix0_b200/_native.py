@@ -61,6 +61,8 @@ SIGNATURES = {
     "m0_net_destroy": (c_int, [c_void_p]),
     "m0_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "m0_tc_conv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "m0_profile_enable": (c_int, [c_int]),
+    "m0_profile_get": (c_int, [c_char_p, ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_longlong)]),
     "m0_net_forward_ssl": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

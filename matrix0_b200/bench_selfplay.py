@@ -34,6 +34,17 @@ def reference_cfg(sims: int):
     return {"model": model, "selfplay": selfplay, "mcts": mcts}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py); None when no capture is committed."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["conv_pair_kernel"]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ranks):
     import numpy as np
     import torch
@@ -115,6 +126,32 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     nn_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
     peaks = load_peaks()
     achieved = FLOP_PER_POSITION * G / (nn_ms * 1e-3) / 1e12
+    # the dominant kernel (CTA-pair 3x3 convolution C -> C, 2 launches per residual block) timed per launch inside the running
+    # forward: CUDA events around every launch of its two sites
+    import ctypes
+    _native.check(lib.m0_profile_enable(1))
+    for _ in range(3):
+        net.forward_planes(planes, precision)
+    torch.cuda.synchronize()
+    conv_ms, conv_n, site_ms = 0.0, 0, {}
+    for site in ("conv1+gn", "conv2+pool", "conv2+se+res+gn", "se_apply_gn", "se_gate", "attention_tc", "gemm_qkv", "gemm_proj",
+                 "layernorm_residual_f32", "groupnorm_mixed", "conv_other"):
+        ms, cnt = ctypes.c_double(0), ctypes.c_longlong(0)
+        _native.check(lib.m0_profile_get(site.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
+        if cnt.value:
+            site_ms[site] = {"launches_per_forward": cnt.value / 3, "us_per_launch": 1e3 * ms.value / cnt.value}
+        if site.startswith("conv1") or site.startswith("conv2"):
+            conv_ms += ms.value
+            conv_n += cnt.value
+    ms, cnt = ctypes.c_double(0), ctypes.c_longlong(0)
+    _native.check(lib.m0_profile_get(None, ctypes.byref(ms), ctypes.byref(cnt)))
+    fwd_profiled_ms = ms.value / 3
+    _native.check(lib.m0_profile_enable(0))
+    C = cfg["model"]["channels"]
+    conv_flops = 2.0 * G * 64 * C * 9 * C
+    conv_launch_ms = conv_ms / max(conv_n, 1)
+    conv_tflops = conv_flops / (conv_launch_ms * 1e-3) / 1e12 if conv_n else 0.0
+    traffic = load_traffic()
 
     # end to end with HOST buffers: root positions come from pinned host memory every move and the search
     # results (moves, visit counts, pi, root value) go back to pinned host memory
@@ -167,10 +204,16 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
         "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": int(G * 72 / per_move),
                 "d2h_bytes_per_step": int(G * (4672 * 4 + 256 * 6 + 8) / per_move), "moves_timed": n_e2e},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
-                     "kernel": "m0_net_forward (3x3 implicit-GEMM convolutions = 93% of the FLOPs)", "algorithmic_flops_per_launch": FLOP_PER_POSITION * G,
-                     "kernel_ms": nn_ms, "share_of_step": nn_ms / (total_ms / args.steps)},
+        "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                     "peak_source": peaks["source"] + " (sustained bf16: the kernel is timed inside the running forward)",
+                     "kernel": f"tc::conv_pair_kernel, 3x3 convolution {C}->{C} over {G} boards (tcgen05 cta_group::2 implicit GEMM, 2 launches per residual block)",
+                     "algorithmic_flops_per_launch": conv_flops, "kernel_us": 1e3 * conv_launch_ms, "launches_timed": conv_n,
+                     "share_of_step": (conv_ms / 3) / (total_ms / args.steps),
+                     "timing": "CUDA events around each launch on the launching stream, 3 forwards after the timed region"},
+        "forward": {"achieved": achieved, "unit": "TFLOP/s", "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+                    "algorithmic_flops": FLOP_PER_POSITION * G, "ms": nn_ms, "share_of_step": nn_ms / (total_ms / args.steps),
+                    "launch_sites": site_ms, "sum_of_sites_ms": fwd_profiled_ms},
         "tree": {"children_scanned": d["children_scanned"], "path_nodes": d["path_nodes"], "children_created": d["children_created"],
                  "terminal_sims": d["terminal_sims"], "tt_hops": d["tt_hops"],
                  "algorithmic_bytes": 24 * d["children_scanned"] + 24 * d["path_nodes"] + 44 * d["children_created"]},

@@ -183,7 +183,8 @@ struct TcState {
   std::vector<void*> allocs;
 };
 
-// M0_TC_PROFILE=1: CUDA-event timing of every launch of the forward, by kernel class, printed at exit (diagnostics only)
+// CUDA-event timing of every launch of the tensor-core forward, by launch site: M0_TC_PROFILE=1 prints the table at exit,
+// m0_profile_enable / m0_profile_get expose it to bench.py (per-kernel durations inside the running pipeline)
 struct TcProfiler {
   struct Rec { const char* name; cudaEvent_t a, b; };
   std::vector<Rec> pending;
@@ -195,8 +196,10 @@ struct TcProfiler {
       on = (e && atoi(e)) ? 1 : 0;
       if (on) atexit(&TcProfiler::dump_static);
     }
-    return on == 1;
+    return on >= 1;
   }
+  void set(int enable) { enabled(); on = enable ? 2 : 0; }   // programmatic switch (m0_profile_enable): no dump at exit
+  void reset() { collect(); acc.clear(); }
   static TcProfiler& get() { static TcProfiler p; return p; }
   void begin(const char* name, cudaStream_t s) {
     Rec r; r.name = name;
@@ -775,4 +778,24 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
   if (taps == 9) TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin));
   else TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));
   return launch_gemm(&st, a, w, boards * 64, taps == 9 ? 1 : 0, taps, cin, 0, n, d_out_f32, nullptr, n, 0, nullptr, ACT_NONE, 1.0f, (cudaStream_t)stream);
+}
+
+// ---- per-launch-site timing of the tensor-core forward (bench.py roofline; diagnostics) -------------------------------------------
+extern "C" int m0_profile_enable(int enable) {
+  TcProfiler& p = TcProfiler::get();
+  p.reset();
+  p.set(enable);
+  return M0_OK;
+}
+// accumulated milliseconds and launch count of one launch site ("conv1+gn", "conv2+pool", "se_apply_gn", ...); name == NULL sums all
+extern "C" int m0_profile_get(const char* name, double* total_ms, long long* launches) {
+  TcProfiler& p = TcProfiler::get();
+  p.collect();
+  double ms = 0;
+  long long cnt = 0;
+  for (auto& kv : p.acc)
+    if (!name || kv.first == name) { ms += kv.second.first; cnt += kv.second.second; }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = cnt;
+  return M0_OK;
 }
