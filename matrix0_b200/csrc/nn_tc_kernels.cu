@@ -132,6 +132,7 @@ struct TcWeight {
   CUtensorMap map_pair;        // box {64, n / 4}: a quarter of the output channels per CTA and accumulator (tc_conv_pair.cuh)
   bool pair = false;
   int n = 0, k = 0, n_part = 0, cluster = 1;
+  int n_launch = 0;            // output channels per launch / slice
 };
 
 // CTAs per cluster for a launch: the W tile is multicast within the cluster (M0_TC_CLUSTER overrides)
@@ -271,12 +272,15 @@ struct ConvFusion {   // optional fused epilogue inputs / outputs of the CTA-pai
 
 int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int boards, int cin, float* out_f32, __nv_bfloat16* out_half,
                      int ldc, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr,
-                     const ConvFusion* fuse = nullptr) {
+                     const ConvFusion* fuse = nullptr, int conv = 1, int n_slices = 1) {
   tc::ConvPairParams p;
   memset(&p, 0, sizeof(p));
   p.boards = boards;
-  p.N = w.n;
+  p.N = w.n_launch;
   p.kb_per_tap = cin / 64;
+  p.conv = conv;
+  p.n_slices = n_slices;
+  if (n_slices > 1 && (gn_gamma || pool_part || fuse)) { m0_set_error("pair kernel: fused epilogues need a single slice"); return M0_ERR_ARG; }
   p.fp16 = nn_half_format();
   p.out_f32 = out_f32;
   p.out_half = out_half;
@@ -290,15 +294,15 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   if (em < 0) { em = env_int("M0_TC_EXP", 0); bo = env_int("M0_CP_BASEOFF", 0); cap = env_int("M0_TC_STAGES", 0); }
   p.exp_mode = em;
   p.base_offset = bo;
-  const int stage_bytes = tc::CP_A_SLOT + 3 * (w.n / 4) * 128;
+  const int stage_bytes = conv ? tc::CP_A_SLOT + 3 * (w.n_launch / 4) * 128 : tc::A_TILE_BYTES + (w.n_launch / 4) * 128;
   int stages = (st->max_smem - 2048 - tc::CP_EPI_BYTES) / stage_bytes;
   if (stages > 8) stages = 8;
   if (cap > 0 && stages > cap) stages = cap;
-  if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n); return M0_ERR_ARG; }
+  if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n_launch); return M0_ERR_ARG; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + tc::CP_EPI_BYTES + 1024 + 256;
   // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
-  const int nch = (w.n + 63) / 64;
+  const int nch = (w.n_launch + 63) / 64;
   const bool fz = fuse && (fuse->resid_x || fuse->prims);
   auto kernel = fz ? (nch <= 2 ? tc::conv_pair_kernel<2, true> : nch <= 5 ? tc::conv_pair_kernel<5, true> : tc::conv_pair_kernel<8, true>)
                    : (nch <= 2 ? tc::conv_pair_kernel<2, false> : nch <= 5 ? tc::conv_pair_kernel<5, false> : tc::conv_pair_kernel<8, false>);
@@ -339,8 +343,9 @@ int make_weight(TcState* st, TcWeight* out, const float* w_f32, int n, int k, in
   st->allocs.push_back(p);
   out->w = (__nv_bfloat16*)p;
   TRY(nn_f32_to_bf16(w_f32, out->w, (size_t)n * k, s));
-  out->pair = pair_ok(n) && n == n_launch;
-  if (out->pair) TRY(make_map_2d(&out->map_pair, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)(n / 4)));
+  out->n_launch = n_launch;
+  out->pair = pair_ok(n_launch) && n % n_launch == 0;
+  if (out->pair) TRY(make_map_2d(&out->map_pair, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)(n_launch / 4)));
   return make_map_2d(&out->map, out->w, (uint64_t)n, (uint64_t)k, (uint32_t)(out->n_part / out->cluster));
 }
 
@@ -353,12 +358,13 @@ int pow2_cols(int n) {
 // one launch of the tensor-core GEMM: rows [0, M), output columns [w_row0, w_row0 + N) of the layer
 int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M, int conv, int taps, int cin, int w_row0, int N, float* out_f32,
                 __nv_bfloat16* out_bf16, int ldc, int col0, const float* bias, int act, float scale, cudaStream_t s,
-                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr, int n_store = -1) {
+                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr, int n_store = -1, int n_slices = 1) {
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M;
   p.N = N;
-  p.n_store = n_store >= 0 ? n_store : N;
+  p.n_slices = n_slices;
+  p.n_store = n_store >= 0 ? n_store : N * n_slices;
   if (w.n_part > N || N % w.n_part != 0) { m0_set_error("tensor-core GEMM: launch width %d does not match the weight map box %d", N, w.n_part); return M0_ERR_ARG; }
   p.n_part = w.n_part;
   p.taps = taps;
@@ -404,7 +410,7 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   const int cs = w.cluster;
   const int groups = (tiles + cs - 1) / cs;
   int clusters = st->sm_count / cs;
-  if (clusters > groups) clusters = groups;
+  if (clusters > groups * n_slices) clusters = groups * n_slices;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(clusters * cs));
@@ -429,6 +435,18 @@ int conv3x3(TcState* st, const CUtensorMap& a_map, const CUtensorMap& a_map_pair
   if (w.pair) return launch_conv_pair(st, a_map_pair, w, B, cin, out_f32, out_half, w.n, act, s, gn_gamma, gn_beta, pool_part, fuse);
   if (fuse) { m0_set_error("fused SE / residual epilogue needs the CTA-pair convolution"); return M0_ERR_ARG; }
   return launch_gemm(st, a_map, w, B * 64, 1, 9, cin, 0, w.n, out_f32, out_half, w.n, 0, nullptr, act, 1.0f, s, gn_gamma, gn_beta, pool_part);
+}
+
+// out = A[B*64][cin] W^T for all n_slices * n_launch output channels in one launch (1x1 convolutions over the board tensor)
+int gemm_rows64(TcState* st, const CUtensorMap& a_mat, const TcWeight& w, int B, int cin, float* out_f32, __nv_bfloat16* out_half, int ldc,
+                cudaStream_t s) {
+  const int n_slices = w.n / w.n_launch;
+  // (the CTA-pair kernel's plain mode re-streams A for every (slice, half) and measures slower here: M0_TC_PAIR_GEMM=1 selects it)
+  static int pg = -1;
+  if (pg < 0) pg = env_int("M0_TC_PAIR_GEMM", 0);
+  if (pg && w.pair) return launch_conv_pair(st, a_mat, w, B, cin, out_f32, out_half, ldc, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, 0, n_slices);
+  return launch_gemm(st, a_mat, w, B * 64, 0, 1, cin, 0, w.n_launch, out_f32, out_half, ldc, 0, nullptr, ACT_NONE, 1.0f, s, nullptr, nullptr, nullptr, -1,
+                     n_slices);
 }
 
 int tc_reserve(m0_net* n, TcState* st, int B) {
@@ -645,7 +663,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
     float* cur = n->x;
     if (c.piece_square_tables) {
-      PROF("gemm_pst", launch_gemm(st, st->a1_mat, st->pst, M, 0, 1, C, 0, C, n->t1, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+      PROF("gemm_pst", gemm_rows64(st, st->a1_mat, st->pst, B, C, n->t1, nullptr, C, s));
       PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
       cur = n->t2;
     }
@@ -705,16 +723,14 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     if (run_att) {
       const float* rb = c.attention_relbias ? b.att_rel_bias : nullptr;
       if (tc_att) {
-        for (int r0 = 0; r0 < 3 * C; r0 += C)
-          PROF("gemm_qkv", launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, nullptr, st->qkv_h, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+        PROF("gemm_qkv", gemm_rows64(st, st->a1_mat, tb.qkv, B, C, nullptr, st->qkv_h, 3 * C, s));
         PROF("attention_tc", nn_attention_tc(st->qkv_h, rb, st->a2, B, C, c.attention_heads, c.attention_unmasked_mix, s));
       } else {
-        for (int r0 = 0; r0 < 3 * C; r0 += C)
-          PROF("gemm_qkv", launch_gemm(st, st->a1_mat, tb.qkv, M, 0, 1, C, r0, C, n->qkv, nullptr, 3 * C, r0, none, ACT_NONE, 1.0f, s));
+        PROF("gemm_qkv", gemm_rows64(st, st->a1_mat, tb.qkv, B, C, n->qkv, nullptr, 3 * C, s));
         PROF("attention_f32", nn_attention_f32(n->qkv, rb, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
         PROF("f32_to_bf16", nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
       }
-      PROF("gemm_proj", launch_gemm(st, st->a2_mat, tb.proj, M, 0, 1, C, 0, C, n->t2, nullptr, C, 0, none, ACT_NONE, 1.0f, s));
+      PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, n->t2, nullptr, C, s));
       PROF("layernorm_residual_f32", nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
       if (!last) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
     }
@@ -727,18 +743,16 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   PROF("gemm_pol_conv", launch_gemm(st, st->a1_mat, st->pol_conv, M, 0, 1, C, 0, 64, n->t1, nullptr, 64, 0, none, ACT_NONE, 1.0f, s));
   PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
   PROF("gemm_pol_fc1", launch_gemm(st, st->ph_mat, st->pol_fc1, B, 0, 1, 4096, 0, r, nullptr, st->pf_h, rp, 0, w.pol_fc1_b, ACT_RELU, 1.0f, s));
-  for (int r0 = 0; r0 < c.policy_size; r0 += 320) {
-    const int nn = c.policy_size - r0 < 320 ? c.policy_size - r0 : 320;
-    PROF("gemm_pol_fc2", launch_gemm(st, st->pf_mat, st->pol_fc2, B, 0, 1, rp, r0, 320, logits, nullptr, c.policy_size, r0, w.pol_fc2_b, ACT_NONE, w.policy_logit_scale, s,
-                    nullptr, nullptr, nullptr, nn));
-  }
+  // one launch over all 320-column slices of the (zero-padded) policy_fc2 weight; the padding columns are not stored
+  PROF("gemm_pol_fc2", launch_gemm(st, st->pf_mat, st->pol_fc2, B, 0, 1, rp, 0, 320, logits, nullptr, c.policy_size, 0, w.pol_fc2_b, ACT_NONE,
+                                   w.policy_logit_scale, s, nullptr, nullptr, nullptr, c.policy_size, (c.policy_size + 319) / 320));
   // value: conv1x1 C->128, GN, act, conv1x1 128->128, GN, act, fc1 (+ activation) on tensor cores
   PROF("gemm_val_conv1", launch_gemm(st, st->a1_mat, st->val_conv1, M, 0, 1, C, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
   PROF("groupnorm_mixed", nn_groupnorm_mixed(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
   PROF("gemm_val_conv2", launch_gemm(st, st->vh_conv_mat, st->val_conv2, M, 0, 1, 128, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
   PROF("groupnorm_mixed", nn_groupnorm_mixed(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
-  for (int r0 = 0; r0 < 2 * C; r0 += C)
-    PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, r0, C, n->vf1, nullptr, 2 * C, r0, w.val_fc1_b, vact, 1.0f, s));
+  PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, 0, C, n->vf1, nullptr, 2 * C, 0, w.val_fc1_b, vact, 1.0f, s, nullptr, nullptr,
+                                   nullptr, -1, 2));
   PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
   PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf2, w.val_gate_w, w.val_gate_b, n->vf2, n->vg, B, C, C, C, C, 0, ACT_SIGMOID, 1.0f, s));
   PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vg, w.val_fc3_w, w.val_fc3_b, nullptr, values, B, 1, C, C, 1, 0, ACT_TANH, 1.0f, s));
@@ -769,11 +783,18 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
   w.cluster = pick_cluster(w.n_part);
   TRY(make_map_2d(&w.map, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)(w.n_part / w.cluster)));
   CUtensorMap a;
+  w.n_launch = n;
   if (taps == 9 && pair_ok(n)) {
     w.pair = true;
     TRY(make_map_2d(&w.map_pair, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)(n / 4)));
     TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin, 10));
     return launch_conv_pair(&st, a, w, boards, cin, d_out_f32, nullptr, n, ACT_NONE, (cudaStream_t)stream);
+  }
+  if (taps == 1 && pair_ok(n)) {   // plain GEMM over whole boards on the CTA-pair kernel (qkv / proj / piece-square projections)
+    w.pair = true;
+    TRY(make_map_2d(&w.map_pair, d_w_bf16, (uint64_t)n, (uint64_t)cin, (uint32_t)(n / 4)));
+    TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));
+    return launch_conv_pair(&st, a, w, boards, cin, d_out_f32, nullptr, n, ACT_NONE, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 1);
   }
   if (taps == 9) TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin));
   else TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));

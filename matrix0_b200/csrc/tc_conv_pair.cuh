@@ -28,6 +28,8 @@ struct ConvPairParams {
   int boards;       // valid boards; rows b*64.. of the output are stored only for b < boards
   int N;            // output channels: N % 32 == 0, 64 <= N <= 512
   int kb_per_tap;   // Cin / 64
+  int conv;         // 1: 3x3 convolution (A = x-padded NHWC boxes); 0: plain GEMM out = A[boards*64][64*kb_per_tap] W^T (A box {64, 128})
+  int n_slices;     // >= 1: consecutive groups of N output channels handled by this launch (W rows / output columns advance by N)
   int stages;
   int fp16;         // operands are IEEE fp16 instead of bf16
   float* out_f32;   // [boards*64][ldc] or null
@@ -129,7 +131,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nh = p.N >> 1, nq = p.N >> 2;
   const int wq_bytes = nq * 128;
-  const int stage_bytes = CP_A_SLOT + 3 * wq_bytes;
+  const int a_bytes = p.conv ? CP_A_SLOT : A_TILE_BYTES, n_w = p.conv ? 3 : 1;
+  const int stage_bytes = a_bytes + n_w * wq_bytes;
+  const int ns2 = 2 * (p.n_slices > 1 ? p.n_slices : 1);   // work items per group of 4 boards: (slice, channel half)
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
   float* s_gamma = epi_stage + 8 * 512;   // [512]
   float* s_beta = s_gamma + 512;          // [512]
@@ -146,7 +150,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int num_tiles = (p.boards + 3) >> 2;
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
-  const int steps = p.kb_per_tap * 3;
+  const int steps = p.conv ? p.kb_per_tap * 3 : p.kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -181,18 +185,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int board0 = t * 4 + rank * 2;   // boards past the end are zero-filled by TMA
-        for (int h = 0; h < 2; ++h) {
-          const int w_row = h * nh + rank * nq;
-          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
-            for (int dyi = 0; dyi < 3; ++dyi) {
+        for (int u2 = 0; u2 < ns2; ++u2) {
+          const int w_row = (u2 >> 1) * p.N + (u2 & 1) * nh + rank * nq;
+          if (p.conv) {
+            for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+              for (int dyi = 0; dyi < 3; ++dyi) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+                const uint32_t bar = lead_full + (uint32_t)stage * 8u;
+                uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                tma_load_4d_pair(a_dst, &tma_a, bar, kc * BK, -1, dyi - 1, board0);
+#pragma unroll
+                for (int dxi = 0; dxi < 3; ++dxi)
+                  tma_load_2d_pair(a_dst + CP_A_SLOT + dxi * wq_bytes, &tma_w, bar, ((dyi * 3 + dxi) * p.kb_per_tap + kc) * BK, w_row);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              }
+            }
+          } else {
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
               const uint32_t bar = lead_full + (uint32_t)stage * 8u;
               uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-              tma_load_4d_pair(a_dst, &tma_a, bar, kc * BK, -1, dyi - 1, board0);
-#pragma unroll
-              for (int dxi = 0; dxi < 3; ++dxi)
-                tma_load_2d_pair(a_dst + CP_A_SLOT + dxi * wq_bytes, &tma_w, bar, ((dyi * 3 + dxi) * p.kb_per_tap + kc) * BK, w_row);
+              tma_load_2d_pair(a_dst, &tma_a, bar, kb * BK, board0 * 64);
+              tma_load_2d_pair(a_dst + A_TILE_BYTES, &tma_w, bar, kb * BK, w_row);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -207,7 +223,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0, unit = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        for (int h = 0; h < 2; ++h, ++unit) {
+        for (int u2 = 0; u2 < ns2; ++u2, ++unit) {
           const uint32_t buf = unit & 1u;
           mbar_wait(&tmem_empty_bar[buf], ((unit >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
           tc_fence_after();
@@ -217,12 +233,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tc_fence_after();
             const uint32_t a_addr = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
             if (elect_one()) {
+              if (p.conv) {
 #pragma unroll
-              for (int dxi = 0; dxi < 3; ++dxi) {
-                const uint64_t adesc = make_smem_desc_sbo(a_addr + dxi * 128, 1280, p.base_offset);
-                const uint64_t bdesc = make_smem_desc_sbo(a_addr + CP_A_SLOT + dxi * wq_bytes, 1024, 0);
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                  const uint64_t adesc = make_smem_desc_sbo(a_addr + dxi * 128, 1280, p.base_offset);
+                  const uint64_t bdesc = make_smem_desc_sbo(a_addr + CP_A_SLOT + dxi * wq_bytes, 1024, 0);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) umma_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, (step > 0 || dxi > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < BK / 16; ++k) umma_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, (step > 0 || dxi > 0 || k > 0) ? 1u : 0u);
+                }
+              } else {
+                const uint64_t adesc = make_smem_desc_sbo(a_addr, 1024, 0);
+                const uint64_t bdesc = make_smem_desc_sbo(a_addr + A_TILE_BYTES, 1024, 0);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, (step > 0 || k > 0) ? 1u : 0u);
               }
               umma_commit_pair(&empty_bar[stage], 3);   // frees the stage in both CTAs
             }
@@ -257,7 +280,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     uint32_t unit = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      for (int h = 0; h < 2; ++h, ++unit) {
+      for (int u2 = 0; u2 < ns2; ++u2, ++unit) {
+        const int h = u2 & 1, cbase = (u2 >> 1) * p.N + h * nh;   // first output column of this work item
         const uint32_t buf = unit & 1u;
         const int row0 = t * 256 + rank * 128 + quarter * 32;
         const int m_lane = row0 + lane;
@@ -394,7 +418,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int k = 0; k < NCH; ++k) {
           const int ci = cset + 2 * k;
           if (ci >= nchunks) break;
-          const int col = h * nh + ci * 16;
+          const int col = cbase + ci * 16;
           if (fused_gn) {
             const float2 sa = *reinterpret_cast<const float2*>(stats + ((quarter & 2) * 16 + ci) * 2);
             const float2 sb = *reinterpret_cast<const float2*>(stats + ((quarter | 1) * 16 + ci) * 2);

@@ -161,7 +161,7 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int f
 struct GemmParams {
   int M;            // valid rows of D (rows >= M are computed on zero / stale A rows and not stored)
   int N;            // output columns handled by this launch (<= 320, multiple of 16)
-  int n_store;      // columns actually stored (<= N; the rest are zero-padded weight rows)
+  int n_store;      // columns actually stored, counted over all n_slices (<= N * n_slices; the rest are zero-padded weight rows)
   int n_part;       // columns per tcgen05.mma (N if N <= 256, else N / 2); multiple of 16
   int taps;         // 9 (3x3 convolution) or 1 (plain GEMM / 1x1 convolution)
   int kb_per_tap;   // k-blocks per tap = Cin / 64 (plain GEMM: K / 64)
@@ -186,6 +186,8 @@ struct GemmParams {
   const float* gn_beta;
   float* pool_part;
   int exp_mode;      // timing experiments only (results invalid): 1 = load W once per tile, 2 = load A once per tile
+  int n_slices;      // >= 1: the launch covers n_slices consecutive groups of N output columns (w_row0 / col0 advance by N per slice);
+                     // a CTA walks the slices of one M tile back to back, so the A tile is re-read from L2, not from HBM
 };
 
 // two floats -> one 32-bit word of bf16 or fp16 (low half = first value)
@@ -238,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int kblocks = p.taps * p.kb_per_tap;
   const int n_parts = p.N / p.n_part;
   const int slice_rows = p.n_part / cs;                       // W rows of each part fetched by this CTA for the whole cluster
+  const int ns = p.n_slices > 1 ? p.n_slices : 1;
   const uint16_t mask = (uint16_t)((1u << cs) - 1u);
 
   if (warp == 0 && lane == 0) {
@@ -266,7 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int g = cluster_id; g < num_groups; g += num_clusters) {
+      for (int gi = cluster_id; gi < num_groups * ns; gi += num_clusters) {
+        const int g = gi / ns, w_row0 = p.w_row0 + (gi - g * ns) * p.N;
         const int m0 = (g * cs + rank) * BM;   // may lie past M for the padding tiles of the last group: TMA zero-fills
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -284,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           for (int part = 0; part < n_parts && !skip_w; ++part) {
             uint8_t* dst = w_dst + ((size_t)part * p.n_part + (size_t)rank * slice_rows) * BK * 2;
-            const int row = p.w_row0 + part * p.n_part + rank * slice_rows;
+            const int row = w_row0 + part * p.n_part + rank * slice_rows;
             if (cs > 1) tma_load_2d_mcast(dst, &tma_w, &full_bar[stage], kb * BK, row, mask);
             else tma_load_2d(dst, &tma_w, &full_bar[stage], kb * BK, row);
           }
@@ -301,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     const uint32_t smem_base = smem_u32(smem);
-    for (int g = cluster_id; g < num_groups; g += num_clusters) {
+    for (int gi = cluster_id; gi < num_groups * ns; gi += num_clusters) {
       mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the accumulator
       tc_fence_after();
       for (int kb = 0; kb < kblocks; ++kb) {
@@ -347,7 +351,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     uint32_t acc_phase = 0;
-    for (int g = cluster_id; g < num_groups; g += num_clusters) {
+    for (int gi = cluster_id; gi < num_groups * ns; gi += num_clusters) {
+      const int g = gi / ns, slice = gi - g * ns;
+      const int w_row0 = p.w_row0 + slice * p.N, col0 = p.col0 + slice * p.N;
+      const int n_store = (p.n_store - slice * p.N) < p.N ? (p.n_store - slice * p.N) : p.N;   // p.n_store counts over all slices
       mbar_wait(tmem_full_bar, acc_phase);
       tc_fence_after();
       const int tile_row0 = (g * cs + rank) * BM + quarter * 32;
@@ -402,13 +409,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         } else if (!plain) {
-          const float* bias = p.bias ? p.bias + p.w_row0 + c0 : nullptr;
+          const float* bias = p.bias ? p.bias + w_row0 + c0 : nullptr;
           const int act = p.act;
           const float scale = p.scale;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]);
-            if (bias && c0 + j < p.n_store) x += bias[j];
+            if (bias && c0 + j < n_store) x += bias[j];
             r[j] = __float_as_uint(tc_act(x, act) * scale);
           }
         }
@@ -417,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
         __syncwarp();
-        const int ncols = (p.n_store - c0) < 32 ? (p.n_store - c0) : 32;
+        const int ncols = (n_store - c0) < 32 ? (n_store - c0) : 32;
         if (p.pool_part && tile_row0 < p.M && lane < ncols) {
           // column sums of this half board (lane = column): conflict-free reads of the swizzled buffer
           float cs_sum = 0.f;
@@ -434,7 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int m = tile_row0 + rr;
             if (m < p.M && 4 * q < ncols) {
               uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((q ^ (rr & 7)) << 2));
-              *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + p.col0 + c0 + 4 * q) = v;
+              *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + col0 + c0 + 4 * q) = v;
             }
           }
         }
@@ -451,7 +458,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               uint4 pk;
               pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
               pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
-              *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldc + p.col0 + c0 + 8 * q2) = pk;
+              *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)m * p.ldc + col0 + c0 + 8 * q2) = pk;
             }
           }
         }

@@ -17,7 +17,9 @@ def run_tc(act, w, taps):
     return out
 
 
-@pytest.mark.parametrize("boards,cin,n", [(2, 64, 64), (2, 320, 320), (6, 128, 160), (298, 320, 320), (2, 320, 64), (4, 64, 256)])
+# n % 32 == 0 runs on the CTA-pair kernel (tc_conv_pair.cuh), other widths on the single-CTA kernel (tc_gemm.cuh)
+@pytest.mark.parametrize("boards,cin,n", [(2, 64, 64), (2, 320, 320), (6, 128, 160), (298, 320, 320), (2, 320, 64), (4, 64, 256),
+                                           (4, 128, 48), (2, 320, 80), (298, 320, 176), (64, 3840, 80)])
 def test_plain_gemm(boards, cin, n):
     g = torch.Generator(device="cuda").manual_seed(boards * 1000 + cin + n)
     act = torch.randn((boards, 64, cin), device="cuda", generator=g).to(torch.bfloat16)
