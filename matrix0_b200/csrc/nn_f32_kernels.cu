@@ -285,6 +285,126 @@ __global__ void layernorm_residual_f32_kernel(const float* __restrict__ proj, co
   for (int c = lane; c < C; c += 32) o[c] = (p[c] + xr[c] - mean) * rstd * gamma[c] + beta[c];
 }
 
+// Tensor-core path: x_new = LN(proj + x) (resnet.py:182-188) and, fused, a_out = half(act(GroupNorm_16ch(x_new))) = the bn1 +
+// activation of the next residual block (resnet.py:46-47).  One block (8 warps) per board; warp w owns tokens 8w..8w+7, lane l
+// owns channels 2l + 64j (j < C/64): proj and x are read once, the sums live in registers for both normalisations.
+template <int NJ>
+__global__ void __launch_bounds__(256, 2)
+ln_res_gn_kernel(const float* __restrict__ proj, float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                 const float* __restrict__ gn_g, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ a_out, int act, int fp16) {
+  constexpr int C = 64 * NJ;
+  __shared__ float s_part[8][NJ][4][2];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = ((size_t)b * 64 + warp * 8) * C + 2 * lane;
+  float v[8][2 * NJ];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float2 p2 = __ldg(reinterpret_cast<const float2*>(proj + base + (size_t)t * C + 64 * j));
+      const float2 x2 = *reinterpret_cast<const float2*>(x + base + (size_t)t * C + 64 * j);
+      v[t][2 * j] = p2.x + x2.x;
+      v[t][2 * j + 1] = p2.y + x2.y;
+    }
+  float lg[2 * NJ], lb[2 * NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const float2 g2 = *reinterpret_cast<const float2*>(ln_g + 2 * lane + 64 * j), b2 = *reinterpret_cast<const float2*>(ln_b + 2 * lane + 64 * j);
+    lg[2 * j] = g2.x; lg[2 * j + 1] = g2.y; lb[2 * j] = b2.x; lb[2 * j + 1] = b2.y;
+  }
+  // LayerNorm over the C channels of each token (two-pass, from registers)
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * NJ; ++k) s += v[t][k];
+    mean[t] = s;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) mean[t] += __shfl_xor_sync(0xFFFFFFFFu, mean[t], off);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    mean[t] *= (1.0f / C);
+    float d2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * NJ; ++k) {
+      const float d = v[t][k] - mean[t];
+      d2 = fmaf(d, d, d2);
+    }
+    rstd[t] = d2;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) rstd[t] += __shfl_xor_sync(0xFFFFFFFFu, rstd[t], off);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    rstd[t] = rsqrtf(rstd[t] * (1.0f / C) + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 2 * NJ; ++k) v[t][k] = (v[t][k] - mean[t]) * rstd[t] * lg[k] + lb[k];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) *reinterpret_cast<float2*>(x + base + (size_t)t * C + 64 * j) = make_float2(v[t][2 * j], v[t][2 * j + 1]);
+  }
+  if (!a_out) return;
+  // GroupNorm over (board, 16 channels): channel 2l + 64j belongs to group 4j + l / 8 -> 8 lanes x 8 tokens x 8 warps
+  const int sub = lane >> 3;
+  float gm[NJ], gr[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += v[t][2 * j] + v[t][2 * j + 1];
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, 1); s += __shfl_xor_sync(0xFFFFFFFFu, s, 2); s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+    if ((lane & 7) == 0) s_part[warp][j][sub][0] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_part[w][j][sub][0];
+    gm[j] = tot * (1.0f / 1024.0f);
+    float d2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float a0 = v[t][2 * j] - gm[j], a1 = v[t][2 * j + 1] - gm[j];
+      d2 = fmaf(a0, a0, d2);
+      d2 = fmaf(a1, a1, d2);
+    }
+    d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 1); d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 2); d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 4);
+    if ((lane & 7) == 0) s_part[warp][j][sub][1] = d2;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_part[w][j][sub][1];
+    gr[j] = rsqrtf(tot * (1.0f / 1024.0f) + 1e-5f);
+  }
+  if (gn_g) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float2 g2 = *reinterpret_cast<const float2*>(gn_g + 2 * lane + 64 * j), b2 = *reinterpret_cast<const float2*>(gn_b + 2 * lane + 64 * j);
+      const float g0 = g2.x * gr[j], g1 = g2.y * gr[j];
+      const float b0 = b2.x - gm[j] * g0, b1 = b2.y - gm[j] * g1;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float y0 = fmaf(v[t][2 * j], g0, b0), y1 = fmaf(v[t][2 * j + 1], g1, b1);
+        if (act == ACT_SILU) { y0 = __fdividef(y0, 1.0f + __expf(-y0)); y1 = __fdividef(y1, 1.0f + __expf(-y1)); }
+        else if (act == ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+        uint32_t pk;
+        if (fp16) { __half2 h = __floats2half2_rn(y0, y1); pk = *reinterpret_cast<uint32_t*>(&h); }
+        else { __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1); pk = *reinterpret_cast<uint32_t*>(&h); }
+        *reinterpret_cast<uint32_t*>(a_out + base + (size_t)t * C + 64 * j) = pk;
+      }
+    }
+  }
+}
+
 // NHWC [B][64][C] -> NCHW [B][C][8][8] (SSL head outputs are returned in the reference's layout)
 __global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,6 +459,20 @@ int nn_layernorm_residual_f32(const float* proj, const float* x, const float* ga
                               cudaStream_t s) {
   layernorm_residual_f32_kernel<<<(tokens + 7) / 8, 256, 0, s>>>(proj, x, gamma, beta, out, tokens, C);
   return m0_check_launch("layernorm_residual_f32");
+}
+// x <- LN(proj + x) in place; a_out (optional) = half(act(GroupNorm(x))) with the next block's bn1 parameters
+int nn_ln_res_gn(const float* proj, float* x, const float* ln_g, const float* ln_b, const float* gn_g, const float* gn_b, __nv_bfloat16* a_out,
+                 int B, int C, int act, cudaStream_t s) {
+  const int fp16 = g_half_fp16;
+  switch (C) {
+    case 64: ln_res_gn_kernel<1><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
+    case 128: ln_res_gn_kernel<2><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
+    case 192: ln_res_gn_kernel<3><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
+    case 256: ln_res_gn_kernel<4><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
+    case 320: ln_res_gn_kernel<5><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
+    default: m0_set_error("ln_res_gn: unsupported channel count %d", C); return M0_ERR_ARG;
+  }
+  return m0_check_launch("ln_res_gn");
 }
 int nn_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, cudaStream_t s) {
   size_t total = (size_t)B * 64 * C;

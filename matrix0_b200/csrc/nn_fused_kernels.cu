@@ -145,6 +145,80 @@ se_apply_gn_kernel(const __nv_bfloat16* __restrict__ conv_out, const float* __re
   }
 }
 
+// out = act(GroupNorm_16ch(x)) + residual (residual optional; residual_bstride = 0 broadcasts one board, e.g. the positional
+// encoding), written as fp32 and / or 16-bit.  Same thread layout as se_apply_gn_kernel: one block per board, C threads, thread
+// (rg, q) owns 8 channels x 8 rows in registers, so x is read once with 16-byte loads (stem / piece-square / interaction / head
+// normalisations of the tensor-core forward, resnet.py:18-24).
+__global__ void __launch_bounds__(320, 2)
+gn_act_res_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
+                  long long residual_bstride, float* __restrict__ out, __nv_bfloat16* __restrict__ out_half, int C, int act, int fp16) {
+  __shared__ float s_part[8][40][2];
+  const int b = blockIdx.x;
+  const int nq = C >> 3;
+  const int q = threadIdx.x % nq, rg = threadIdx.x / nq;
+  const size_t off = (size_t)rg * 8 * C + 8 * q;
+  const size_t base = (size_t)b * 64 * C + off;
+  float v[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const float4 x0 = *reinterpret_cast<const float4*>(x + base + (size_t)r * C);
+    const float4 x1 = *reinterpret_cast<const float4*>(x + base + (size_t)r * C + 4);
+    v[r][0] = x0.x; v[r][1] = x0.y; v[r][2] = x0.z; v[r][3] = x0.w; v[r][4] = x1.x; v[r][5] = x1.y; v[r][6] = x1.z; v[r][7] = x1.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s += ((v[r][0] + v[r][1]) + (v[r][2] + v[r][3])) + ((v[r][4] + v[r][5]) + (v[r][6] + v[r][7]));
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+  s_part[rg][q][0] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) tot += s_part[g][q][0];
+  const float mean = tot * (1.0f / 1024.0f);
+  float d2 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = v[r][j] - mean;
+      d2 = fmaf(a, a, d2);
+    }
+  d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, 1);
+  s_part[rg][q][1] = d2;
+  __syncthreads();
+  float vs = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) vs += s_part[g][q][1];
+  const float rstd = rsqrtf(vs * (1.0f / 1024.0f) + 1e-5f);
+  float gsc[8], bsh[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + 8 * q), g1 = *reinterpret_cast<const float4*>(gamma + 8 * q + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + 8 * q), b1 = *reinterpret_cast<const float4*>(beta + 8 * q + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gsc[j] = gg[j] * rstd; bsh[j] = bb[j] - mean * gsc[j]; }
+  }
+  const float* rb = residual ? residual + (size_t)b * residual_bstride + off : nullptr;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = fk_act(fmaf(v[r][j], gsc[j], bsh[j]), act);
+    if (rb) {
+      const float4 r0 = *reinterpret_cast<const float4*>(rb + (size_t)r * C), r1 = *reinterpret_cast<const float4*>(rb + (size_t)r * C + 4);
+      y[0] += r0.x; y[1] += r0.y; y[2] += r0.z; y[3] += r0.w; y[4] += r1.x; y[5] += r1.y; y[6] += r1.z; y[7] += r1.w;
+    }
+    if (out) {
+      *reinterpret_cast<float4*>(out + base + (size_t)r * C) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(out + base + (size_t)r * C + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (out_half)
+      *reinterpret_cast<uint4*>(out_half + base + (size_t)r * C) =
+          make_uint4(fk_pack2(y[0], y[1], fp16), fk_pack2(y[2], y[3], fp16), fk_pack2(y[4], y[5], fp16), fk_pack2(y[6], y[7], fp16));
+  }
+}
+
 // NCHW float32 planes [B][P][8][8] -> NHWC half [B][64][64] with channels P..63 zero (stem input of the tensor-core path)
 __global__ void planes_to_nhwc_half_kernel(const float* __restrict__ planes, __nv_bfloat16* __restrict__ out, int B, int P, int fp16) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*64*64
@@ -187,8 +261,8 @@ se_gate_kernel(const float* __restrict__ pool, const float* __restrict__ w1t, co
 #pragma unroll
       for (int j = 0; j < 16; ++j) h[j] = 0.f;
       const int c0 = part * (C / parts), c1 = (part + 1 == parts) ? C : c0 + C / parts;
-#pragma unroll 4
-      for (int c = c0; c < c1; ++c) {
+#pragma unroll 16
+      for (int c = c0; c < c1; ++c) {   // 16 independent weight loads in flight: the loop is bound by L2 latency
         const float w = __ldg(w1t + c * hid + u);
         const float4* sp = reinterpret_cast<const float4*>(s_pool + c * 16);
         const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];
@@ -215,7 +289,7 @@ se_gate_kernel(const float* __restrict__ pool, const float* __restrict__ w1t, co
     const float bias = b2[c];
 #pragma unroll
     for (int j = 0; j < 16; ++j) z[j] = bias;
-#pragma unroll 4
+#pragma unroll 16
     for (int u = 0; u < hid; ++u) {
       const float w = __ldg(w2t + u * C + c);
       const float4* sh = reinterpret_cast<const float4*>(s_hid + u * 16);
@@ -245,6 +319,13 @@ int nn_se_apply_gn(const __nv_bfloat16* conv_out, const float* gate, float* x, c
   if (C % 16 != 0) { m0_set_error("se_apply_gn: channels must be a multiple of 16"); return M0_ERR_ARG; }
   se_apply_gn_kernel<<<B, C, 0, s>>>(conv_out, gate, x, gamma, beta, a_out, C, act, nn_half_format());
   return m0_check_launch("se_apply_gn");
+}
+int nn_gn_act_res(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride, float* out,
+                  __nv_bfloat16* out_half, int B, int C, int act, cudaStream_t s) {
+  if (C > 320 || C % 16 != 0) { m0_set_error("gn_act_res: unsupported channel count %d", C); return M0_ERR_ARG; }
+  if (act != ACT_NONE && act != ACT_RELU && act != ACT_SILU) { m0_set_error("gn_act_res: unsupported activation %d", act); return M0_ERR_ARG; }
+  gn_act_res_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, out_half, C, act, nn_half_format());
+  return m0_check_launch("gn_act_res");
 }
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s) {
   const size_t total = (size_t)B * 64 * 64;

@@ -18,6 +18,8 @@ namespace m0 {
 int nn_se_apply_gn(const __nv_bfloat16* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
                    int C, int act, cudaStream_t s);
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s);
+int nn_gn_act_res(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride, float* out,
+                  __nv_bfloat16* out_half, int B, int C, int act, cudaStream_t s);
 int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half, int B, int C, int heads, float mix, cudaStream_t s);
 int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float* w2t, const float* b2, float* gate, int B, int C, int hid, int act,
                cudaStream_t s);
@@ -660,15 +662,15 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   PROF("planes_to_nhwc_half", nn_planes_to_nhwc_half(planes, st->planes_h, B, c.planes, s));
   PROF("conv_other", conv3x3(st, st->planes_conv, st->planes_convp, st->stem, B, 64, n->t1, nullptr, ACT_NONE, s));
   if (c.chess_features) {
-    PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
+    PROF("gn_act_res", nn_gn_act_res(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
     float* cur = n->x;
     if (c.piece_square_tables) {
       PROF("gemm_pst", gemm_rows64(st, st->a1_mat, st->pst, B, C, n->t1, nullptr, C, s));
-      PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
+      PROF("gn_act_res", nn_gn_act_res(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
       cur = n->t2;
     }
     PROF("conv_other", conv3x3(st, st->a1_conv, st->a1_convp, st->inter, B, C, n->t1, nullptr, ACT_NONE, s));
-    PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
+    PROF("gn_act_res", nn_gn_act_res(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
   } else {
     PROF("groupnorm_f32", nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
   }
@@ -731,8 +733,14 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
         PROF("f32_to_bf16", nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
       }
       PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, n->t2, nullptr, C, s));
-      PROF("layernorm_residual_f32", nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
-      if (!last) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
+      // x = LN(proj + x) and, in the same pass, a1 = act(GN1_{i+1}(x)) for the next block
+      if (C % 64 == 0 && C <= 320) {
+        PROF("ln_res_gn", nn_ln_res_gn(n->t2, n->x, b.att_ln_w, b.att_ln_b, last ? nullptr : w.blocks[i + 1].gn1_w, last ? nullptr : w.blocks[i + 1].gn1_b,
+                                       last ? nullptr : st->a1, B, C, act, s));
+      } else {
+        PROF("layernorm_residual_f32", nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
+        if (!last) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
+      }
     }
   }
   if (!st->heads_tc) return net_forward_heads_f32(n, B, logits, values, s);
@@ -741,16 +749,16 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   PROF("f32_to_bf16", nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
   // policy: conv1x1 C->64, GN, act, fc1 + ReLU, fc2 * logit scale
   PROF("gemm_pol_conv", launch_gemm(st, st->a1_mat, st->pol_conv, M, 0, 1, C, 0, 64, n->t1, nullptr, 64, 0, none, ACT_NONE, 1.0f, s));
-  PROF("groupnorm_mixed", nn_groupnorm_mixed(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
+  PROF("gn_act_res", nn_gn_act_res(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
   PROF("gemm_pol_fc1", launch_gemm(st, st->ph_mat, st->pol_fc1, B, 0, 1, 4096, 0, r, nullptr, st->pf_h, rp, 0, w.pol_fc1_b, ACT_RELU, 1.0f, s));
   // one launch over all 320-column slices of the (zero-padded) policy_fc2 weight; the padding columns are not stored
   PROF("gemm_pol_fc2", launch_gemm(st, st->pf_mat, st->pol_fc2, B, 0, 1, rp, 0, 320, logits, nullptr, c.policy_size, 0, w.pol_fc2_b, ACT_NONE,
                                    w.policy_logit_scale, s, nullptr, nullptr, nullptr, c.policy_size, (c.policy_size + 319) / 320));
   // value: conv1x1 C->128, GN, act, conv1x1 128->128, GN, act, fc1 (+ activation) on tensor cores
   PROF("gemm_val_conv1", launch_gemm(st, st->a1_mat, st->val_conv1, M, 0, 1, C, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
-  PROF("groupnorm_mixed", nn_groupnorm_mixed(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
+  PROF("gn_act_res", nn_gn_act_res(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
   PROF("gemm_val_conv2", launch_gemm(st, st->vh_conv_mat, st->val_conv2, M, 0, 1, 128, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
-  PROF("groupnorm_mixed", nn_groupnorm_mixed(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
+  PROF("gn_act_res", nn_gn_act_res(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
   PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, 0, C, n->vf1, nullptr, 2 * C, 0, w.val_fc1_b, vact, 1.0f, s, nullptr, nullptr,
                                    nullptr, -1, 2));
   PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
