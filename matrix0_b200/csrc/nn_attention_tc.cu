@@ -6,12 +6,11 @@
 //
 // The kernel is instruction-bound (2 x 4096 probabilities per head), so the per-element work is kept minimal:
 //   * the 64x64 bias of the head is staged once per block, pre-multiplied by log2(e), and a block walks 32 boards;
-//   * the attack-pattern mask (resnet.py:105-129) of the 128 score elements a lane owns is 4 registers of bits,
-//     computed once per warp;
-//   * ONE exponential per element: softmax is shift invariant, so the masked probabilities reuse
-//     2^(s - max_all) scaled by 2^(max_all - max_allowed) per row (masked-out entries are exactly 0 in the
-//     reference too: exp(-1e4 - max) underflows).  Rows whose allowed maximum lies more than 80 octaves below the
-//     row maximum take a second exponential instead (warp-uniform branch);
+//   * the attack-pattern mask (resnet.py:105-129) is a 0/1 table staged next to the bias;
+//   * ONE exponential per element: softmax is shift invariant, so the masked probabilities are 2^(s - max_all)
+//     times the mask (masked-out entries are exactly 0 in the reference too: exp(-1e4 - max) underflows), and both
+//     normalisers come out of the tensor cores as P * ones.  Rows whose allowed squares hold < 2^-6 of the mass
+//     are rescaled by their own maximum before the 16-bit rounding (warp-uniform branch, rare);
 //   * V fragments come from 32-bit loads + movmatrix.trans instead of 16-bit gathers.
 // Blocks are ordered head-fastest so that the 20 heads of a board (one 1920-byte row of qkv per token) are read
 // by co-scheduled blocks while the lines are still in L2.
@@ -58,33 +57,28 @@ __device__ __forceinline__ bool attn_mask_tc(int i, int j) {  // resnet.py:105-1
   return dr == 0 || dc == 0 || adr == adc || (adr == 2 && adc == 1) || (adr == 1 && adc == 2) || (adr <= 1 && adc <= 1);
 }
 
-static constexpr int BIAS_LD = 72;          // padded row stride of the staged bias (floats)
+static constexpr int BIAS_LD = 72;          // padded row stride of the staged tables (floats)
 static constexpr int ATT_BOARDS_PER_WARP = 4;
 static constexpr float LOG2E = 1.4426950408889634f;
 
 template <bool FP16>
 __global__ void __launch_bounds__(256, 2)
 attention_tc_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ rel_bias, uint16_t* __restrict__ out, int B, int C, float mix) {
-  __shared__ __align__(16) float s_bias[64 * BIAS_LD];
+  __shared__ __align__(16) float s_bias[64 * BIAS_LD];   // rel_bias of the head * log2(e)
+  __shared__ __align__(16) float s_mask[64 * BIAS_LD];   // 1 where the attack-pattern mask lets row attend to column, else 0
   const int h = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) s_bias[(i >> 6) * BIAS_LD + (i & 63)] = rel_bias ? rel_bias[(size_t)h * 4096 + i] * LOG2E : 0.0f;
-  const int g = lane >> 2, t = lane & 3;
-  // allowed[mt] bit (nt*4 + e): element (row = 16mt + g + 8*(e>>1), col = 8nt + 2t + (e&1)) may attend
-  uint32_t allowed[4];
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
-    uint32_t w = 0;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (attn_mask_tc(16 * mt + g + ((e & 2) ? 8 : 0), 8 * nt + 2 * t + (e & 1))) w |= 1u << (nt * 4 + e);
-    allowed[mt] = w;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    s_bias[(i >> 6) * BIAS_LD + (i & 63)] = rel_bias ? rel_bias[(size_t)h * 4096 + i] * LOG2E : 0.0f;
+    s_mask[(i >> 6) * BIAS_LD + (i & 63)] = attn_mask_tc(i >> 6, i & 63) ? 1.0f : 0.0f;
   }
   __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
   const int ld = 3 * C;
   const float blend = 1.0f - mix;
   const float kscale = 0.25f * LOG2E, kclamp = 50.0f * LOG2E;
+  // B fragment of an all-ones 16 x 8 tile: P * ones = the row sums of the (rounded) probabilities the PV product uses
+  const uint32_t one2 = pack2<FP16>(1.0f, 1.0f);
+  const uint32_t ones[2] = {one2, one2};
   const int b_first = (blockIdx.y * 8 + warp) * ATT_BOARDS_PER_WARP;
 #pragma unroll 1
   for (int bi = 0; bi < ATT_BOARDS_PER_WARP; ++bi) {
@@ -112,65 +106,55 @@ attention_tc_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ 
         vf[kk][nd][0] = movmatrix_trans(lo);
         vf[kk][nd][1] = movmatrix_trans(hi);
       }
+    // Q fragments of all four 16-row tiles up front: the loads overlap the K / V loads instead of stalling every tile
+    uint32_t qall[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const uint16_t* qr = q_base + (size_t)(16 * mt + g) * ld + 2 * t;
+      qall[mt][0] = __ldg(reinterpret_cast<const uint32_t*>(qr));
+      qall[mt][1] = __ldg(reinterpret_cast<const uint32_t*>(qr + (size_t)8 * ld));
+      qall[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qr + 8));
+      qall[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qr + (size_t)8 * ld + 8));
+    }
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
       const int r0 = 16 * mt + g, r1 = r0 + 8;
       uint32_t qa[4];
-      qa[0] = __ldg(reinterpret_cast<const uint32_t*>(q_base + (size_t)r0 * ld + 2 * t));
-      qa[1] = __ldg(reinterpret_cast<const uint32_t*>(q_base + (size_t)r1 * ld + 2 * t));
-      qa[2] = __ldg(reinterpret_cast<const uint32_t*>(q_base + (size_t)r0 * ld + 2 * t + 8));
-      qa[3] = __ldg(reinterpret_cast<const uint32_t*>(q_base + (size_t)r1 * ld + 2 * t + 8));
-      const uint32_t am = mt == 0 ? allowed[0] : mt == 1 ? allowed[1] : mt == 2 ? allowed[2] : allowed[3];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) qa[e] = mt == 0 ? qall[0][e] : mt == 1 ? qall[1][e] : mt == 2 ? qall[2][e] : qall[3][e];
       float su[8][4];
-      float mu0 = -INFINITY, mu1 = -INFINITY, mm0 = -INFINITY, mm1 = -INFINITY;
+      float mu0 = -INFINITY, mu1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         mma16816<FP16>(acc, qa, kf[nt]);
         const float2 b0 = *reinterpret_cast<const float2*>(s_bias + r0 * BIAS_LD + 8 * nt + 2 * t);
         const float2 b1 = *reinterpret_cast<const float2*>(s_bias + r1 * BIAS_LD + 8 * nt + 2 * t);
-        const float bb[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = fmaf(acc[e], kscale, bb[e]);
-          v = fminf(fmaxf(v, -kclamp), kclamp);
-          su[nt][e] = v;
-          const float vm = (am >> (nt * 4 + e)) & 1u ? v : -INFINITY;
-          if (e & 2) { mu1 = fmaxf(mu1, v); mm1 = fmaxf(mm1, vm); }
-          else { mu0 = fmaxf(mu0, v); mm0 = fmaxf(mm0, vm); }
-        }
+        su[nt][0] = fminf(fmaxf(fmaf(acc[0], kscale, b0.x), -kclamp), kclamp);
+        su[nt][1] = fminf(fmaxf(fmaf(acc[1], kscale, b0.y), -kclamp), kclamp);
+        su[nt][2] = fminf(fmaxf(fmaf(acc[2], kscale, b1.x), -kclamp), kclamp);
+        su[nt][3] = fminf(fmaxf(fmaf(acc[3], kscale, b1.y), -kclamp), kclamp);
+        mu0 = fmaxf(mu0, fmaxf(su[nt][0], su[nt][1]));
+        mu1 = fmaxf(mu1, fmaxf(su[nt][2], su[nt][3]));
       }
 #pragma unroll
       for (int off = 1; off <= 2; off <<= 1) {
-        mu0 = fmaxf(mu0, __shfl_xor_sync(0xFFFFFFFFu, mu0, off)); mu1 = fmaxf(mu1, __shfl_xor_sync(0xFFFFFFFFu, mu1, off));
-        mm0 = fmaxf(mm0, __shfl_xor_sync(0xFFFFFFFFu, mm0, off)); mm1 = fmaxf(mm1, __shfl_xor_sync(0xFFFFFFFFu, mm1, off));
+        mu0 = fmaxf(mu0, __shfl_xor_sync(0xFFFFFFFFu, mu0, off));
+        mu1 = fmaxf(mu1, __shfl_xor_sync(0xFFFFFFFFu, mu1, off));
       }
-      // every row may attend to itself, so mm is finite
-      const float gap0 = mu0 - mm0, gap1 = mu1 - mm1;
-      const bool far = __any_sync(0xFFFFFFFFu, fmaxf(gap0, gap1) > 80.0f);
-      const float c0 = fast_ex2(fminf(gap0, 80.0f)), c1 = fast_ex2(fminf(gap1, 80.0f));
-      float zu0 = 0.f, zu1 = 0.f, zm0 = 0.f, zm1 = 0.f;
+      // softmax is shift invariant: both distributions use 2^(s - row max); the masked one multiplies by the 0/1 mask
+      // (the reference's masked entries are exactly 0 as well: exp(-1e4 - max) underflows)
       float sm[8][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float s = su[nt][e];
-          const float pu = fast_ex2(s - ((e & 2) ? mu1 : mu0));
-          float pm;
-          if (far) pm = fast_ex2(s - ((e & 2) ? mm1 : mm0));
-          else pm = pu * ((e & 2) ? c1 : c0);
-          pm = (am >> (nt * 4 + e)) & 1u ? pm : 0.0f;
-          su[nt][e] = pu;
-          sm[nt][e] = pm;
-          if (e & 2) { zu1 += pu; zm1 += pm; } else { zu0 += pu; zm0 += pm; }
-        }
-#pragma unroll
-      for (int off = 1; off <= 2; off <<= 1) {
-        zu0 += __shfl_xor_sync(0xFFFFFFFFu, zu0, off); zu1 += __shfl_xor_sync(0xFFFFFFFFu, zu1, off);
-        zm0 += __shfl_xor_sync(0xFFFFFFFFu, zm0, off); zm1 += __shfl_xor_sync(0xFFFFFFFFu, zm1, off);
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 m0 = *reinterpret_cast<const float2*>(s_mask + r0 * BIAS_LD + 8 * nt + 2 * t);
+        const float2 m1 = *reinterpret_cast<const float2*>(s_mask + r1 * BIAS_LD + 8 * nt + 2 * t);
+        su[nt][0] = fast_ex2(su[nt][0] - mu0); su[nt][1] = fast_ex2(su[nt][1] - mu0);
+        su[nt][2] = fast_ex2(su[nt][2] - mu1); su[nt][3] = fast_ex2(su[nt][3] - mu1);
+        sm[nt][0] = su[nt][0] * m0.x; sm[nt][1] = su[nt][1] * m0.y;
+        sm[nt][2] = su[nt][2] * m1.x; sm[nt][3] = su[nt][3] * m1.y;
       }
-      float ou[2][4], om[2][4];
+      float ou[2][4], om[2][4], zu[4] = {0.f, 0.f, 0.f, 0.f}, zm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int nd = 0; nd < 2; ++nd)
 #pragma unroll
@@ -191,8 +175,44 @@ attention_tc_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ 
           mma16816<FP16>(ou[nd], pu, vf[kk][nd]);
           mma16816<FP16>(om[nd], pm, vf[kk][nd]);
         }
+        mma16816<FP16>(zu, pu, ones);
+        mma16816<FP16>(zm, pm, ones);
       }
-      const float iu0 = __fdividef(1.0f, zu0), iu1 = __fdividef(1.0f, zu1), im0 = __fdividef(1.0f, zm0), im1 = __fdividef(1.0f, zm1);
+      // zu, zm: elements 0 / 2 hold the sums of rows r0 / r1.  A row whose allowed squares carry less than 2^-6 of the unmasked
+      // mass would lose precision in the 16-bit probabilities: rescale its masked probabilities by their maximum and redo the product
+      if (__any_sync(0xFFFFFFFFu, fminf(zm[0], zm[2]) < 0.015625f)) {
+        float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          x0 = fmaxf(x0, fmaxf(sm[nt][0], sm[nt][1]));
+          x1 = fmaxf(x1, fmaxf(sm[nt][2], sm[nt][3]));
+        }
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+          x0 = fmaxf(x0, __shfl_xor_sync(0xFFFFFFFFu, x0, off));
+          x1 = fmaxf(x1, __shfl_xor_sync(0xFFFFFFFFu, x1, off));
+        }
+        const float c0 = x0 > 0.f ? 1.0f / x0 : 0.f, c1 = x1 > 0.f ? 1.0f / x1 : 0.f;
+#pragma unroll
+        for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) om[nd][e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) zm[e] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t pm[4];
+          pm[0] = pack2<FP16>(sm[2 * kk][0] * c0, sm[2 * kk][1] * c0);
+          pm[1] = pack2<FP16>(sm[2 * kk][2] * c1, sm[2 * kk][3] * c1);
+          pm[2] = pack2<FP16>(sm[2 * kk + 1][0] * c0, sm[2 * kk + 1][1] * c0);
+          pm[3] = pack2<FP16>(sm[2 * kk + 1][2] * c1, sm[2 * kk + 1][3] * c1);
+#pragma unroll
+          for (int nd = 0; nd < 2; ++nd) mma16816<FP16>(om[nd], pm, vf[kk][nd]);
+          mma16816<FP16>(zm, pm, ones);
+        }
+      }
+      const float iu0 = __fdividef(1.0f, zu[0]), iu1 = __fdividef(1.0f, zu[2]);
+      const float im0 = zm[0] > 0.f ? __fdividef(1.0f, zm[0]) : 0.f, im1 = zm[2] > 0.f ? __fdividef(1.0f, zm[2]) : 0.f;
 #pragma unroll
       for (int nd = 0; nd < 2; ++nd) {
         float o[4];
