@@ -92,6 +92,8 @@ int m0_games_reset(m0_engine* e, const int* d_games, int n, void* stream);      
  * history before each root: positions uint64[n][hist_stride][9], moves uint16[n][hist_stride], lengths int32[n]. */
 int m0_games_set_positions(m0_engine* e, const int* d_games, int n, const uint64_t* d_root_pos, const uint64_t* d_hist_pos,
                            const uint16_t* d_hist_moves, const int32_t* d_hist_lens, int hist_stride, void* stream);
+/* root position of every game, packed records uint64[G][9] (the state selfplay_worker records before a search, internal.py:447) */
+int m0_games_get_positions(m0_engine* e, uint64_t* d_out_pos, void* stream);
 /* MCTS.run prologue (mcts.py:336-371): d_info int32[G] bit0 = terminal root (d_value float64[G] = _terminal_value),
  * bit1 = root needs an evaluation (its planes are written to d_planes float32[G][19][8][8]). */
 int m0_search_begin(m0_engine* e, float* d_planes, int32_t* d_info, double* d_value, void* stream);

@@ -41,6 +41,7 @@ SIGNATURES = {
     "m0_engine_configure": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_games_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "m0_games_set_positions": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "m0_games_get_positions": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_search_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_search_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "m0_search_expand_backup": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -164,6 +164,14 @@ int m0_games_set_positions(m0_engine* e, const int* d_games, int n, const uint64
   return m0_check_launch("m0_games_set_positions");
 }
 
+// Current root position of every game (packed records uint64[G][9]): what selfplay_worker encodes as the training state
+// before each search (internal.py:447) -- read back by the self-play recorder.
+int m0_games_get_positions(m0_engine* e, uint64_t* d_out_pos, void* stream) {
+  if (!e || !d_out_pos) { m0_set_error("m0_games_get_positions: invalid argument"); return M0_ERR_ARG; }
+  return m0_check_cuda(cudaMemcpyAsync(d_out_pos, e->v.root_pos, (size_t)e->v.G * 9 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream),
+                       "m0_games_get_positions");
+}
+
 static inline int tree_blocks(const m0_engine* e) { return (e->v.G + TREE_WARPS - 1) / TREE_WARPS; }
 
 // MCTS.run prologue (mcts.py:336-371): d_info int32[G] (bit0 terminal root, bit1 needs evaluation),
