@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import time
 from typing import Any, Dict, List, Optional
 
@@ -184,3 +185,57 @@ class SelfPlayEngine:
 
     def counters(self) -> Dict[str, int]:
         return self.engine.counters()
+
+
+def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[str], games: int, q=None, shared_memory_resource=None,
+                    device: Optional[int] = None, concurrent_games: Optional[int] = None, precision: str = "fp16", data_manager=None) -> int:
+    """Drop-in for ``azchess.selfplay.internal.selfplay_worker`` (internal.py:94): plays ``games`` self-play games and emits the same
+    artefacts -- one NPZ shard per game (internal.py:626-651) and the orchestrator's queue messages (``heartbeat`` :546-556,
+    ``game`` :666-679).  One call drives a whole GPU: ``concurrent_games`` games (default min(games, 4096)) advance in lock step on
+    ``device`` instead of one game per process; the evaluator is the native network (``shared_memory_resource`` -- the handle of the
+    reference's inference server -- is accepted and ignored, nothing leaves the device).
+
+    ``data_manager``: any object with ``add_selfplay_data(game_data, worker_id, game_id) -> path`` (the reference's DataManager);
+    default writes ``{cfg.data_dir or 'data'}/selfplay/selfplay_w{proc}_g{game}_{ms}.npz`` with ``records.write_game_npz``.
+    Returns the number of games written."""
+    import torch
+    from .model import PolicyValueNet
+    from .records import GameRecorder, write_game_npz
+    dev = int(device if device is not None else (proc_id % max(1, torch.cuda.device_count())))
+    seed = int(cfg_dict.get("seed", 1234)) + int(proc_id)     # internal.py:111-113 seeds by worker
+    model = PolicyValueNet.from_config(cfg_dict.get("model", {}), device=f"cuda:{dev}", precision=precision, seed=seed)
+    if ckpt_path:
+        state = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+        sd = state.get("model_ema", state.get("model", state)) if isinstance(state, dict) else state   # internal.py:172-174
+        model.load_state_dict(sd, strict=False)
+    G = int(concurrent_games or min(int(games), 4096))
+    sp = SelfPlayEngine(model, cfg_dict, games=G, device=dev, deterministic=False, seed=seed, precision=precision)
+    rec = GameRecorder(sp)
+    out_dir = os.path.join(str(cfg_dict.get("data_dir", "data")), "selfplay")
+    written, last_hb, t_start = 0, time.perf_counter(), time.perf_counter()
+    sp.start()
+    while written < games:
+        sp.begin_move()
+        for _ in range(sp.batches_per_move()):
+            sp.search_step()
+        rec.after_search()
+        sp.end_move()
+        for gd in rec.after_move():
+            if written >= games:
+                break
+            T = int(gd["meta_moves"][0])
+            path = (data_manager.add_selfplay_data(gd, worker_id=proc_id, game_id=written) if data_manager is not None
+                    else write_game_npz(out_dir, gd, proc_id, written))
+            secs = time.perf_counter() - t_start
+            if q is not None:
+                z = float(gd["meta_result"][0])
+                q.put({"type": "game", "proc": proc_id, "file": path, "moves": T, "result": z, "secs": secs,
+                       "resigned": bool(gd["meta_resigned"][0]), "resigner": None, "draw": bool(z == 0.0),
+                       "avg_policy_entropy": float(gd["meta_avg_policy_entropy"][0]), "avg_ms_per_move": secs * 1000.0 / max(1, T),
+                       "avg_sims": float(gd["meta_avg_sims"][0])})
+            written += 1
+        if q is not None and time.perf_counter() - last_hb >= 2.0:
+            q.put({"type": "heartbeat", "proc": proc_id, "game": written, "moves": sp.moves, "avg_sims": float(sp.mcfg.num_simulations),
+                   "resigned": False, "avg_policy_entropy": 0.0})
+            last_hb = time.perf_counter()
+    return written

@@ -192,3 +192,33 @@ def _boards_from_planes(s):
         out.append(b)
         prev = b
     return out
+
+
+def test_selfplay_worker_dropin_writes_shards_and_messages(golden_dir, tmp_path):
+    """selfplay_worker(proc_id, cfg, ckpt, games, q) -- the reference's worker entry (internal.py:94): NPZ shards in data_dir/selfplay
+    and `game` messages with the orchestrator's keys (internal.py:666-679)."""
+    import queue
+    from matrix0_b200.selfplay import selfplay_worker
+    g, ncfg, sd = load_case(golden_dir, "small")
+    ckpt = tmp_path / "ckpt.pt"
+    torch.save({"model": sd}, ckpt)
+    model_cfg = {k: getattr(ncfg, k) for k in ncfg.__dataclass_fields__}
+    cfg = {"model": model_cfg, "data_dir": str(tmp_path / "data"), "seed": 3,
+           "mcts": dict(MCTS_KW, num_simulations=32, inference_batch_size=16),
+           "selfplay": {"num_simulations": 32, "opening_random_plies": 4, "max_game_len": 8, "temperature_start": 1.0, "temperature_end": 0.3,
+                        "temperature_moves": 40, "resign_threshold": -0.85, "min_resign_plies": 50}}
+    q = queue.Queue()
+    n = selfplay_worker(0, cfg, str(ckpt), games=10, q=q, concurrent_games=8, precision="fp32")
+    assert n == 10
+    files = sorted((tmp_path / "data" / "selfplay").glob("selfplay_w0_g*.npz"))
+    assert len(files) == 10
+    msgs = []
+    while not q.empty():
+        msgs.append(q.get())
+    game_msgs = [m for m in msgs if m["type"] == "game"]
+    assert len(game_msgs) == 10
+    assert set(game_msgs[0]) >= {"type", "proc", "file", "moves", "result", "secs", "resigned", "resigner", "draw", "avg_policy_entropy",
+                                 "avg_ms_per_move", "avg_sims"}
+    with np.load(files[0]) as f:
+        T = int(f["meta_moves"][0])
+        assert f["s"].shape == (T, 19, 8, 8) and f["pi"].shape == (T, 4672) and f["z"].shape == (T,)
