@@ -120,6 +120,9 @@ typedef struct m0_selfplay_config { /* selfplay: section of the reference config
   double temperature_start, temperature_end, resign_threshold, resign_min_entropy, resign_value_margin;
   int temperature_moves, max_game_len, min_resign_plies, resign_window, resign_consecutive_bad, opening_random_plies;
   unsigned long long seed;
+  int argmax_after_plies; /* >= 0: arena move rule (arena.py:75-91): sample at temperature_start while plies < this, then argmax;
+                             < 0: the self-play temperature schedule (internal.py:386-394) */
+  int reserved;
 } m0_selfplay_config;
 typedef struct m0_finished_game {
   int game, plies; /* slot, len(states) */

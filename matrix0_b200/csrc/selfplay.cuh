@@ -12,6 +12,8 @@ struct SelfPlayParams {
   double resign_threshold, resign_min_entropy, resign_value_margin;  // :352-360
   int temperature_moves, max_game_len, min_resign_plies, resign_window, resign_consecutive_bad, opening_random_plies;
   unsigned long long seed;
+  int argmax_after_plies;  // >= 0: arena rule (arena.py:75-91): temperature_start while plies < this, then argmax; < 0: self-play schedule
+  int reserved;
 };
 
 struct FinishedGame {

@@ -13,6 +13,7 @@ struct m0_selfplay_config {
   double temperature_start, temperature_end, resign_threshold, resign_min_entropy, resign_value_margin;
   int temperature_moves, max_game_len, min_resign_plies, resign_window, resign_consecutive_bad, opening_random_plies;
   unsigned long long seed;
+  int argmax_after_plies, reserved;
 };
 
 struct m0_finished_game {
@@ -74,6 +75,7 @@ int m0_selfplay_configure(m0_engine* e, const m0_selfplay_config* c, void* strea
   p.resign_consecutive_bad = c->resign_consecutive_bad;
   p.opening_random_plies = c->opening_random_plies;
   p.seed = c->seed;
+  p.argmax_after_plies = c->argmax_after_plies;
   M0_CUDA_TRY(cudaMemcpyAsync(e->d_sp_params, &p, sizeof(p), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   M0_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return M0_OK;

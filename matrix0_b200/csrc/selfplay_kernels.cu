@@ -218,6 +218,7 @@ selfplay_advance_kernel(EngineView E, SelfPlayState S, unsigned long long step, 
     double t = (double)(mn < P.temperature_moves ? mn : P.temperature_moves) / (double)P.temperature_moves;
     temperature = P.temperature_start + (P.temperature_end - P.temperature_start) * t;
   }
+  if (P.argmax_after_plies >= 0) temperature = S.ply[g] < P.argmax_after_plies ? P.temperature_start : 0.0;   // arena.py:75-91
   // visit counts -> move (internal.py:690-735)
   long long total = 0;
   int best_n = -1, best_j = 0;

@@ -38,7 +38,7 @@ class SelfPlayConfigStruct(ctypes.Structure):
                                                "resign_value_margin")] \
         + [(n, ctypes.c_int) for n in ("temperature_moves", "max_game_len", "min_resign_plies", "resign_window",
                                        "resign_consecutive_bad", "opening_random_plies")] \
-        + [("seed", ctypes.c_uint64)]
+        + [("seed", ctypes.c_uint64), ("argmax_after_plies", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class FinishedGameStruct(ctypes.Structure):
@@ -103,6 +103,7 @@ class SelfPlayEngine:
             s.resign_consecutive_bad = int(self.sp.get("resign_consecutive_bad", 5))
             s.opening_random_plies = int(self.sp.get("opening_random_plies", cfg_dict.get("openings", {}).get("random_plies", 0)))
             s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            s.argmax_after_plies = int(self.sp.get("argmax_after_plies", -1))
             lib = _native.lib()
             _native.check(lib.m0_selfplay_configure(self.engine._h, ctypes.byref(s), _native.current_stream()), "m0_selfplay_configure")
         self._lib = lib

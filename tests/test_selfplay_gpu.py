@@ -222,3 +222,33 @@ def test_selfplay_worker_dropin_writes_shards_and_messages(golden_dir, tmp_path)
     with np.load(files[0]) as f:
         T = int(f["meta_moves"][0])
         assert f["s"].shape == (T, 19, 8, 8) and f["pi"].shape == (T, 4672) and f["z"].shape == (T,)
+
+
+def test_arena_two_evaluators_route_rows_and_score(golden_dir):
+    """ArenaEngine (arena.py:59-126 semantics): with identical networks on both sides the match equals the single-evaluator game
+    loop move for move; leaves are routed to the mover's network (all roots are White to move at ply 0: half the games use A)."""
+    from matrix0_b200.arena import ArenaEngine
+    from matrix0_b200.selfplay import SelfPlayEngine
+    net_a, net_b = small_net(golden_dir), small_net(golden_dir)
+    G, sims, n = 16, 32, 16
+    cfg = {"mcts": dict(MCTS_KW, num_simulations=sims, inference_batch_size=16, dirichlet_frac=0.0, playout_random_frac=0.0),
+           "selfplay": {"selection_jitter": 0.0}}
+    arena = ArenaEngine(net_a, net_b, cfg, num_sims=sims, temperature=0.0, temp_plies=0, max_moves=12, concurrent_games=G, seed=4,
+                        precision="fp32", deterministic=True)
+    res = arena.play(n)
+    assert len(res["games"]) == n and all(r is not None for r in res["games"])
+    assert res["wins"] + res["draws"] + res["losses"] == n
+    assert abs(res["score_a"] - sum(r["score"] for r in res["games"])) < 1e-9
+    assert [r["a_is_white"] for r in res["games"][:4]] == [True, False, True, False]
+    assert res["rows_a"] > 0 and res["rows_b"] > 0
+    # deterministic argmax games with one network on both sides: every game is the same game, and equals the plain game loop
+    sp_cfg = {"mcts": dict(cfg["mcts"], selection_jitter=0.0),
+              "selfplay": {"num_simulations": sims, "selection_jitter": 0.0, "opening_random_plies": 0, "max_game_len": 12, "temperature_start": 0.0,
+                           "temperature_end": 0.0, "temperature_moves": 0, "argmax_after_plies": 0, "resign_threshold": -2.0}}
+    sp = SelfPlayEngine(net_a, sp_cfg, games=G, deterministic=True, seed=4, precision="fp32")
+    sp.start()
+    fin = []
+    while len(fin) < G:
+        sp.play_move()
+        fin += sp.finished_games()
+    assert sorted((f["moves"], f["reason"]) for f in fin[:G]) == sorted((r["moves"], r["reason"]) for r in res["games"])
