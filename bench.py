@@ -260,6 +260,9 @@ def main():
     ap.add_argument("--e2e-positions", type=int, default=1 << 16)
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--leaf-batch", type=int, default=96,
+                    help="mcts.inference_batch_size: 96 = the reference's accounting (one evaluated leaf per game stands for up to 96 "
+                         "simulations, SURVEY Q1); 1 = distinct-leaf mode, every simulation evaluates its own leaf (SURVEY 8d row 4, second mode)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--precision", default=os.environ.get("M0_BENCH_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     args = ap.parse_args()

@@ -16,7 +16,7 @@ import time
 FLOP_PER_POSITION = 6.068e9  # SURVEY 6 [measured with FlopCounterMode]: conv 6020 + addmm 16 + bmm 31 MFLOP
 
 
-def reference_cfg(sims: int):
+def reference_cfg(sims: int, leaf_batch: int = 96):
     """config.yaml of the reference (mcts: / selfplay: / model: sections) with the BASELINE overrides:
     ResNet-24 = 320 channels / 24 blocks / 20 heads, num_simulations = sims."""
     model = dict(planes=19, channels=320, blocks=24, attention=True, attention_heads=20, policy_size=4672, norm="group", activation="silu",
@@ -29,7 +29,7 @@ def reference_cfg(sims: int):
                 dirichlet_frac=0.25, dirichlet_plies=30, selection_jitter=0.05, fpu=0.6, fpu_reduction=0.1, draw_penalty=-0.05,
                 tt_capacity=1500000, tt_cleanup_frequency=5000, encoder_cache=True, legal_softmax=True, max_children=0, min_child_prior=0.0,
                 no_instant_backtrack=True, parent_q_init=True, tt_cleanup_interval_s=5, value_from_white=False, virtual_loss=1.0,
-                enable_memory_cleanup=True, inference_batch_size=96, parallel_simulations=True, tree_parallelism=True,
+                enable_memory_cleanup=True, inference_batch_size=int(leaf_batch), parallel_simulations=True, tree_parallelism=True,
                 memory_cleanup_threshold_mb=512, max_tree_nodes=100000, playout_random_frac=0.05, enable_entropy_noise=True)
     return {"model": model, "selfplay": selfplay, "mcts": mcts}
 
@@ -54,11 +54,13 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     lib = _native.lib()
     precision = os.environ.get("M0_BENCH_PRECISION", args.precision if hasattr(args, "precision") else "fp16")
     G = args.games
-    cfg = reference_cfg(args.sims)
+    leaf_batch = int(getattr(args, "leaf_batch", 96))
+    cfg = reference_cfg(args.sims, leaf_batch)
     net = PolicyValueNet.from_config(cfg["model"], device=f"cuda:{local}", precision=precision, seed=0)
     from matrix0_b200 import distributed as D
     D.broadcast_parameters(net._params, src=0)  # identical weights everywhere: one NCCL broadcast per tensor
-    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=D.rank_seed(1234, rank), precision=precision, max_nodes=4096)
+    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=D.rank_seed(1234, rank), precision=precision,
+                        max_nodes=4096 if leaf_batch >= 16 else 40960)   # distinct-leaf mode expands ~sims nodes of ~35 children per move
     stream = torch.cuda.current_stream()
     sp.start()
     per_move = 1 + sp.batches_per_move()
@@ -197,8 +199,9 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
         "config": {"workload": f"batched self-play: {G} concurrent games/GPU x {args.sims} sims/move, ResNet-24 320ch/24 blocks/20 heads {precision}, random init",
-                   "games_per_gpu": G, "sims_per_move": args.sims, "inference_batch_size": 96, "steps_per_move": per_move,
-                   "mode": "reference-exact accounting (one evaluated leaf per game and mini-batch, SURVEY Q1), fresh tree per move",
+                   "games_per_gpu": G, "sims_per_move": args.sims, "inference_batch_size": leaf_batch, "steps_per_move": per_move,
+                   "mode": ("reference-exact accounting (one evaluated leaf per game and mini-batch, SURVEY Q1), fresh tree per move" if leaf_batch > 1
+                            else "distinct leaves: every simulation selects, evaluates and backs up its own leaf (inference_batch_size = 1), fresh tree per move"),
                    "openings": "start position + 12 random plies (device RNG)", "l2": "per-step activations (>1 GB) exceed the 126 MB L2"},
         "positions_per_s": pos_all / secs, "unique_nn_evals_per_s": allsum(nn_rows) / secs, "pending_leaf_evals_per_s": evals_all / secs,
         "clocks": clocks,
