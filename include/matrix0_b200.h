@@ -65,6 +65,13 @@ int m0_encode_planes(const uint64_t* d_pos, int n, float* d_planes, void* stream
 int m0_legal_mask(const uint64_t* d_pos, int n, uint8_t* d_mask, void* stream);
 int m0_legal_moves(const uint64_t* d_pos, int n, uint16_t* d_moves, uint16_t* d_idx, int32_t* d_counts, void* stream);
 
+/* SSL target maps of azchess/ssl_algorithms.py create_enhanced_ssl_targets (:502-535), one position per row as selfplay_worker
+ * calls it (internal.py:460-466); float32, plane coordinates (row = 7 - rank); any output may be NULL:
+ *   d_piece[n][13][8][8] (_create_piece_targets :537-557)   d_threat[n][8][8] (detect_threats_batch :51-143)
+ *   d_pin[n][8][8] (detect_pins_batch :256-346)   d_fork[n][8][8] (detect_forks_batch :348-421)
+ *   d_control[n][8][8] in {-1, 0, 1} (calculate_square_control_batch :423-500) */
+int m0_ssl_targets(const uint64_t* d_pos, int n, float* d_piece, float* d_threat, float* d_pin, float* d_fork, float* d_control, void* stream);
+
 /* ---- search engine: azchess/mcts.py ------------------------------------------------------------
  * One engine per GPU holds up to max_games concurrent games as GPU-resident structure-of-arrays
  * trees (Node, mcts.py:120-133), a per-game transposition table (MCTS.tt, :302) and the move-stack

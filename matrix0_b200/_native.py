@@ -34,6 +34,7 @@ SIGNATURES = {
     "m0_encode_positions": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_encode_planes": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "m0_legal_mask": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "m0_ssl_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_legal_moves": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_engine_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "m0_engine_destroy": (c_int, [c_void_p]),

@@ -58,6 +58,27 @@ def encode_positions_device(pos, planes: bool = True, mask: bool = True, moves: 
     return t_planes, t_mask, t_moves, t_idx, t_cnt
 
 
+def ssl_targets_device(pos):
+    """SSL target maps (azchess/ssl_algorithms.py create_enhanced_ssl_targets) of packed positions already in HBM:
+    dict of float32 device tensors {"piece": [n,13,8,8], "threat" / "pin" / "fork" / "control": [n,8,8]}."""
+    import torch
+    lib = _native.lib()
+    n = pos.shape[0]
+    out = {"piece": torch.empty((n, 13, 8, 8), dtype=torch.float32, device=pos.device)}
+    for k in ("threat", "pin", "fork", "control"):
+        out[k] = torch.empty((n, 8, 8), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        _native.check(lib.m0_ssl_targets(pos.data_ptr(), n, out["piece"].data_ptr(), out["threat"].data_ptr(), out["pin"].data_ptr(),
+                                         out["fork"].data_ptr(), out["control"].data_ptr(), _native.current_stream()), "m0_ssl_targets")
+    return out
+
+
+def create_enhanced_ssl_targets(boards: Sequence, device=None) -> dict:
+    """Batch form of ``ChessSSLAlgorithms.create_enhanced_ssl_targets`` (ssl_algorithms.py:502) taking boards instead of planes."""
+    pos = upload_positions(boards, device)
+    return {k: v.cpu().numpy() for k, v in ssl_targets_device(pos).items()}
+
+
 def encode_boards(boards: Sequence, device=None) -> Tuple[np.ndarray, np.ndarray]:
     """Batch form of ``encode_board`` + ``get_legal_actions``: (float32[n,19,8,8], bool[n,4672])."""
     if len(boards) == 0:

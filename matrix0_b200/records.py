@@ -11,7 +11,7 @@
 The games run on the GPU (selfplay.SelfPlayEngine); per ply only the packed root positions (72 B) and the root children's
 (policy index, visit count) pairs leave the device.  When a game ends, its positions go back through the encode kernel in one
 batch (planes + legal masks) and ``pi`` is rebuilt as ``n / total`` (float64 divide, float32 store -- mcts.py:846).
-SSL targets (``ssl_*`` keys) are not produced here: they are the next row of SURVEY 8f.
+``ssl_{task}`` arrays (internal.py:460-466, 644-648) come from the SSL target kernel (``m0_ssl_targets``) for the tasks in ``ssl_tasks``.
 """
 from __future__ import annotations
 
@@ -36,7 +36,7 @@ class GameRecorder:
                 np.savez_compressed(path, **game)
     """
 
-    def __init__(self, sp, keep_plies: int = 1024):
+    def __init__(self, sp, keep_plies: int = 1024, ssl_tasks=()):
         import torch
         self.sp = sp
         self.G = sp.G
@@ -50,6 +50,7 @@ class GameRecorder:
         self._start = np.zeros((self.G,), dtype=np.int64)   # absolute ply index at which the current game of a slot started
         self._sims = np.zeros((self.G,), dtype=np.float64)
         self.keep_plies = int(keep_plies)
+        self.ssl_tasks = tuple(t for t in ssl_tasks if t in ("piece", "threat", "pin", "fork", "control"))   # model.ssl_tasks (internal.py:251-256)
 
     def after_search(self) -> None:
         """Call after the last search step of a ply and before SelfPlayEngine.end_move()."""
@@ -111,7 +112,13 @@ class GameRecorder:
             turns[t] = 1.0 if (int(pos[t, 8]) & 1) else -1.0          # packed state word: bit 0 = side to move (White = 1)
             sims.append(float(tot))
         z = float(fin["result"])
+        ssl = {}
+        if self.ssl_tasks:
+            from .encoding import ssl_targets_device
+            maps = ssl_targets_device(dpos)
+            ssl = {f"ssl_{t}": maps[t].cpu().numpy() for t in self.ssl_tasks}
         return {
+            **ssl,
             "s": planes.cpu().numpy(), "pi": pi, "z": (z * turns).astype(np.float32), "legal_mask": mask.cpu().numpy(),
             "meta_moves": np.array([T], dtype=np.int32), "meta_result": np.array([z], dtype=np.float32),
             "meta_resigned": np.array([1 if fin["resigned"] else 0], dtype=np.int8), "meta_draw": np.array([1 if z == 0.0 else 0], dtype=np.int8),

@@ -211,7 +211,9 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
         model.load_state_dict(sd, strict=False)
     G = int(concurrent_games or min(int(games), 4096))
     sp = SelfPlayEngine(model, cfg_dict, games=G, device=dev, deterministic=False, seed=seed, precision=precision)
-    rec = GameRecorder(sp)
+    mcfg = cfg_dict.get("model", {}) or {}
+    ssl_tasks = tuple(mcfg.get("ssl_tasks", ())) if mcfg.get("self_supervised", False) else ()      # internal.py:251-256
+    rec = GameRecorder(sp, ssl_tasks=ssl_tasks)
     out_dir = os.path.join(str(cfg_dict.get("data_dir", "data")), "selfplay")
     written, last_hb, t_start = 0, time.perf_counter(), time.perf_counter()
     sp.start()

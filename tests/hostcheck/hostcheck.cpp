@@ -3,6 +3,7 @@
 // spent.  Built by tests/test_hostcheck.py into tests/hostcheck/_hostcheck.so; never imported by
 // matrix0_b200 (the product has no CPU path and raises when the CUDA library is missing).
 #include "../../matrix0_b200/csrc/chess_core.cuh"
+#include "../../matrix0_b200/csrc/ssl_core.cuh"
 #include <string.h>
 using namespace m0;
 
@@ -53,5 +54,17 @@ void hc_planes(const uint64_t* pos9, float* out) {
   for (int pl = 0; pl < 19; ++pl)
     for (int r = 0; r < 8; ++r)
       for (int c = 0; c < 8; ++c) out[(pl * 8 + r) * 8 + c] = plane_value(p, pl, r, c);
+}
+// 17 maps x 64 floats in plane coordinates: piece[13], threat, pin, fork, control (ssl_core.cuh)
+void hc_ssl(const uint64_t* pos9, float* out) {
+  SslMasks m;
+  ssl_masks(load(pos9), m);
+  for (int i = 0; i < 64; ++i) {
+    for (int k = 0; k < 13; ++k) out[k * 64 + i] = (m.piece[k] >> i) & 1 ? 1.0f : 0.0f;
+    out[13 * 64 + i] = (m.threat >> i) & 1 ? 1.0f : 0.0f;
+    out[14 * 64 + i] = 0.0f;
+    out[15 * 64 + i] = (m.fork >> i) & 1 ? 1.0f : 0.0f;
+    out[16 * 64 + i] = (m.ctrl_pos >> i) & 1 ? 1.0f : ((m.ctrl_neg >> i) & 1 ? -1.0f : 0.0f);
+  }
 }
 }

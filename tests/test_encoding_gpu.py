@@ -120,3 +120,18 @@ def test_full_size_properties(enc):
     # idempotence: a second launch gives the same bytes
     planes2, mask2, _, _, _ = enc.encode_positions_device(pos, True, True, False)
     assert torch.equal(planes, planes2) and torch.equal(mask, mask2)
+
+
+def test_ssl_targets_match_reference_goldens(golden_dir):
+    """m0_ssl_targets (azchess/ssl_algorithms.py create_enhanced_ssl_targets as a bitboard kernel) vs the maps generated from the
+    unmodified reference module, bit-exact; ragged batch sizes."""
+    import os
+    import chess
+    from matrix0_b200.encoding import create_enhanced_ssl_targets
+    g = np.load(os.path.join(golden_dir, "ssl_golden.npz"))
+    boards = [chess.Board(str(f)) for f in g["fens"]]
+    for n in (len(boards), 1, 129, 0):
+        t = create_enhanced_ssl_targets(boards[:n])
+        for k in ("piece", "threat", "pin", "fork", "control"):
+            assert t[k].dtype == np.float32
+            assert np.array_equal(t[k], g[k][:n]), (k, n)

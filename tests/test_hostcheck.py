@@ -23,7 +23,8 @@ def hc():
     so = os.path.join(HC_DIR, "_hostcheck.so")
     src = os.path.join(HC_DIR, "hostcheck.cpp")
     core = os.path.join(ROOT, "matrix0_b200", "csrc", "chess_core.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+    ssl = os.path.join(ROOT, "matrix0_b200", "csrc", "ssl_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(ssl)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     return ctypes.CDLL(so)
 
@@ -74,3 +75,19 @@ def test_core_matches_oracle(hc):
             tk, kk = b2._transposition_key(), (int(k[0]), int(k[1]))
             assert keys.setdefault(tk, kk) == kk
     assert len(set(keys.values())) == len(keys)  # distinct transposition keys -> distinct hashes
+
+
+def test_ssl_core_matches_reference_goldens(hc, golden_dir):
+    """matrix0_b200/csrc/ssl_core.cuh (bitboard form of azchess/ssl_algorithms.py) on the host vs the golden maps generated from the
+    unmodified reference module."""
+    g = np.load(os.path.join(golden_dir, "ssl_golden.npz"))
+    for i, fen in enumerate(g["fens"]):
+        b = chess.Board(str(fen))
+        pos = pack(hc, b)
+        out = np.zeros((17, 8, 8), dtype=np.float32)
+        hc.hc_ssl(pos.ctypes.data_as(U64P), out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        assert np.array_equal(out[:13], g["piece"][i]), fen
+        assert np.array_equal(out[13], g["threat"][i]), fen
+        assert np.array_equal(out[14], g["pin"][i]), fen
+        assert np.array_equal(out[15], g["fork"][i]), fen
+        assert np.array_equal(out[16], g["control"][i]), fen

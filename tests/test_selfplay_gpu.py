@@ -99,6 +99,7 @@ def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path):
     normalised visit counts on legal indices only, z = result x side to move, consecutive states one legal move apart."""
     from matrix0_b200.records import GameRecorder, write_game_npz
     from matrix0_b200.selfplay import SelfPlayEngine
+    from oracle import ssl_ref
     from oracle.encoding_ref import encode_board, get_legal_actions
     net = small_net(golden_dir)
     G, sims = 48, 48
@@ -106,7 +107,7 @@ def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path):
            "selfplay": {"num_simulations": sims, "opening_random_plies": 6, "max_game_len": 10, "temperature_start": 1.2, "temperature_end": 0.3,
                         "temperature_moves": 40, "resign_threshold": -0.85, "min_resign_plies": 50}}
     sp = SelfPlayEngine(net, cfg, games=G, deterministic=False, seed=9, precision="fp32", max_nodes=2048)
-    rec = GameRecorder(sp)
+    rec = GameRecorder(sp, ssl_tasks=("piece", "threat", "pin", "fork", "control"))
     sp.start()
     games = []
     for _ in range(12):
@@ -136,6 +137,9 @@ def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path):
             assert abs(float(gd["pi"][t].sum()) - 1.0) < 1e-5
             assert not np.any(gd["pi"][t][~gd["legal_mask"][t].astype(bool)] > 0)
             assert gd["z"][t] == np.float32(z * (1.0 if b.turn else -1.0))
+            want = ssl_ref.ssl_targets(gd["s"][t])               # ssl_{task} arrays, internal.py:460-466 / 644-648
+            for task, arr in want.items():
+                assert np.array_equal(gd[f"ssl_{task}"][t], arr), (task, t, b.fen())
             if t + 1 < T:   # the next recorded state is one legal move away
                 nxt = boards[t + 1]
                 assert any(_same_placement(_pushed(b, m), nxt) for m in b.legal_moves), (t, b.fen(), nxt.fen())
