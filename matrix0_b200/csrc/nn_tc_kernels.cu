@@ -292,17 +292,16 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   p.gn_beta = gn_beta;
   p.pool_part = pool_part;
   if (fuse) { p.resid_x = fuse->resid_x; p.gate = fuse->gate; p.prims = fuse->prims; }
-  static int em = -1, bo = -1, cap = -1;
-  if (em < 0) { em = env_int("M0_TC_EXP", 0); bo = env_int("M0_CP_BASEOFF", 0); cap = env_int("M0_TC_STAGES", 0); }
-  p.exp_mode = em;
-  p.base_offset = bo;
-  const int stage_bytes = conv ? tc::CP_A_SLOT + 3 * (w.n_launch / 4) * 128 : tc::A_TILE_BYTES + (w.n_launch / 4) * 128;
-  int stages = (st->max_smem - 2048 - tc::CP_EPI_BYTES) / stage_bytes;
+  static int cap = -1;
+  if (cap < 0) cap = env_int("M0_TC_STAGES", 0);   // pipeline-depth experiments
+  const int stage_bytes = conv ? tc::CP_A_SLOT + 3 * (w.n_launch / 4) * 128 : (w.n_launch / 4) * 128;
+  const int a_res = conv ? 0 : 2 * (cin / 64) * tc::A_TILE_BYTES;   // plain mode keeps two resident A tiles (K <= 320)
+  int stages = (st->max_smem - 2048 - tc::CP_EPI_BYTES - a_res) / stage_bytes;
   if (stages > 8) stages = 8;
   if (cap > 0 && stages > cap) stages = cap;
   if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n_launch); return M0_ERR_ARG; }
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + tc::CP_EPI_BYTES + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + a_res + tc::CP_EPI_BYTES + 1024 + 256;
   // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
   const int nch = (w.n_launch + 63) / 64;
   const bool fz = fuse && (fuse->resid_x || fuse->prims);
@@ -384,11 +383,6 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   p.gn_gamma = gn_gamma;
   p.gn_beta = gn_beta;
   p.pool_part = pool_part;
-  {
-    static int em = -1;
-    if (em < 0) { const char* e = getenv("M0_TC_EXP"); em = e ? atoi(e) : 0; }
-    p.exp_mode = em;
-  }
   if ((gn_gamma || pool_part) && (w_row0 != 0 || N % 32 != 0)) { m0_set_error("fused epilogue needs the full channel range"); return M0_ERR_ARG; }
   p.cluster = w.cluster;
   p.fp16 = nn_half_format();
@@ -443,10 +437,11 @@ int conv3x3(TcState* st, const CUtensorMap& a_map, const CUtensorMap& a_map_pair
 int gemm_rows64(TcState* st, const CUtensorMap& a_mat, const TcWeight& w, int B, int cin, float* out_f32, __nv_bfloat16* out_half, int ldc,
                 cudaStream_t s) {
   const int n_slices = w.n / w.n_launch;
-  // (the CTA-pair kernel's plain mode re-streams A for every (slice, half) and measures slower here: M0_TC_PAIR_GEMM=1 selects it)
+  // M0_TC_PAIR_GEMM=1: CTA-pair kernel with the A tile resident across the (slice, half) work items of a group of boards; measured
+  // slower than the single-CTA kernel for K = 320 (both are bound by their epilogues there), so it is opt-in
   static int pg = -1;
   if (pg < 0) pg = env_int("M0_TC_PAIR_GEMM", 0);
-  if (pg && w.pair) return launch_conv_pair(st, a_mat, w, B, cin, out_f32, out_half, ldc, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, 0, n_slices);
+  if (pg && w.pair && cin <= 320) return launch_conv_pair(st, a_mat, w, B, cin, out_f32, out_half, ldc, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, 0, n_slices);
   return launch_gemm(st, a_mat, w, B * 64, 0, 1, cin, 0, w.n_launch, out_f32, out_half, ldc, 0, nullptr, ACT_NONE, 1.0f, s, nullptr, nullptr, nullptr, -1,
                      n_slices);
 }
@@ -798,7 +793,7 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
     TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin, 10));
     return launch_conv_pair(&st, a, w, boards, cin, d_out_f32, nullptr, n, ACT_NONE, (cudaStream_t)stream);
   }
-  if (taps == 1 && pair_ok(n)) {   // plain GEMM over whole boards on the CTA-pair kernel (qkv / proj / piece-square projections)
+  if (taps == 1 && pair_ok(n) && cin <= 320) {   // plain GEMM over whole boards on the CTA-pair kernel (qkv / proj / piece-square projections)
     w.pair = true;
     TRY(make_map_2d(&w.map_pair, d_w_bf16, (uint64_t)n, (uint64_t)cin, (uint32_t)(n / 4)));
     TRY(make_map_2d(&a, d_act_bf16, (uint64_t)boards * 64, (uint64_t)cin, 128));

@@ -53,8 +53,6 @@ struct ConvPairParams {
   float* resid_x;
   const float* gate;
   __nv_bfloat16* prims;
-  int exp_mode;     // timing experiments only: 4 = drop the accumulator instead of storing it
-  int base_offset;  // set the descriptor base-offset field of the row-shifted A views
 };
 
 static constexpr int CP_THREADS = 384;   // warpgroup 0: TMA producer, MMA issuer, two idle warps; warpgroups 1-2: epilogue
@@ -116,13 +114,12 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr));
 }
 // K-major 128-byte-swizzled operand whose 8-row groups are sbo_bytes apart (1024 for a dense tile)
-// base_offset [49,52) = (start address >> 7) & 7: the phase of the 8-row swizzle pattern when the start is not 1024-byte aligned
-__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t use_base_offset) {
-  const uint64_t base_off = use_base_offset ? (uint64_t)((smem_addr >> 7) & 7u) : 0ull;
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (base_off << 49) | (2ull << 61);
+// The swizzle phase follows the absolute shared-memory address bits [7,10) (measured: a start that is a multiple of 128 B but not
+// of 1024 B reads the rows TMA wrote there correctly with base_offset = 0), which is what lets one x-padded box serve three taps.
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// NCH = 16-column chunks per epilogue warp held in registers: ceil(N / 64)
 // FUSE compiles the SE / residual / half-board-sum epilogues in (kept out of the plain kernels: code size costs instruction fetch)
 template <int NCH, bool FUSE>
 __global__ void __launch_bounds__(CP_THREADS, 1)
@@ -131,8 +128,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nh = p.N >> 1, nq = p.N >> 2;
   const int wq_bytes = nq * 128;
-  const int a_bytes = p.conv ? CP_A_SLOT : A_TILE_BYTES, n_w = p.conv ? 3 : 1;
-  const int stage_bytes = a_bytes + n_w * wq_bytes;
+  // 3x3 mode: ring stage = x-padded A box + the three W tiles of its dx taps.
+  // plain mode (K <= 320): the whole A tile of a group of boards (kb_per_tap x 16 KB) is RESIDENT and double buffered across groups
+  // -- every (slice, half) work item of the group reuses it -- and the ring carries only the W tiles.
+  const int a_res_bytes = p.conv ? 0 : p.kb_per_tap * A_TILE_BYTES;
+  const int stage_bytes = p.conv ? CP_A_SLOT + 3 * wq_bytes : wq_bytes;
+  uint8_t* a_res = smem;                        // [2][kb_per_tap][16 KB]   (plain mode)
+  smem += 2 * (size_t)a_res_bytes;              // ring base
   const int ns2 = 2 * (p.n_slices > 1 ? p.n_slices : 1);   // work items per group of 4 boards: (slice, channel half)
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
   float* s_gamma = epi_stage + 8 * 512;   // [512]
@@ -143,7 +145,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], only the leader's are used
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* a_full_bar = tmem_empty_bar + 2;        // [2] resident A tile landed (leader's are used)
+  uint64_t* a_empty_bar = a_full_bar + 2;           // [2] every MMA reading the resident A tile has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -162,6 +166,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 16);   // one arrival per epilogue warp of both CTAs
+      mbar_init(&a_full_bar[b], 1);
+      mbar_init(&a_empty_bar[b], 1);
     }
     fence_barrier_init();
   }
@@ -183,8 +189,21 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const uint32_t lead_afull = mapa_u32(smem_u32(a_full_bar), 0);
+      // plain mode: the resident A tile of a group, all k-blocks, into buffer it & 1 (signals the leader's a_full barrier)
+      auto load_a_tile = [&](int t, int it) {
+        const int ab = it & 1;
+        mbar_wait(&a_empty_bar[ab], (uint32_t)((it >> 1) & 1) ^ 1u);
+        if (rank == 0) mbar_expect_tx(&a_full_bar[ab], (uint32_t)(2 * a_res_bytes));
+        for (int kb = 0; kb < p.kb_per_tap; ++kb)
+          tma_load_2d_pair(a_res + (size_t)ab * a_res_bytes + (size_t)kb * A_TILE_BYTES, &tma_a, lead_afull + (uint32_t)ab * 8u, kb * BK,
+                           (t * 4 + rank * 2) * 64);
+      };
+      int it = 0;
+      if (!p.conv && cluster_id < num_tiles) load_a_tile(cluster_id, 0);
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int board0 = t * 4 + rank * 2;   // boards past the end are zero-filled by TMA
+        if (!p.conv && t + num_clusters < num_tiles) load_a_tile(t + num_clusters, it + 1);   // one group ahead
         for (int u2 = 0; u2 < ns2; ++u2) {
           const int w_row = (u2 >> 1) * p.N + (u2 & 1) * nh + rank * nq;
           if (p.conv) {
@@ -205,10 +224,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int kb = 0; kb < p.kb_per_tap; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
-              const uint32_t bar = lead_full + (uint32_t)stage * 8u;
-              uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-              tma_load_2d_pair(a_dst, &tma_a, bar, kb * BK, board0 * 64);
-              tma_load_2d_pair(a_dst + A_TILE_BYTES, &tma_w, bar, kb * BK, w_row);
+              tma_load_2d_pair(smem + (size_t)stage * stage_bytes, &tma_w, lead_full + (uint32_t)stage * 8u, kb * BK, w_row);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -222,7 +238,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0, unit = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const uint32_t a_tile = smem_u32(a_res) + (uint32_t)(it & 1) * (uint32_t)a_res_bytes;
+        if (!p.conv) {
+          mbar_wait(&a_full_bar[it & 1], (uint32_t)(it >> 1) & 1u);   // the group's resident A tile has landed in both CTAs
+          tc_fence_after();
+        }
         for (int u2 = 0; u2 < ns2; ++u2, ++unit) {
           const uint32_t buf = unit & 1u;
           mbar_wait(&tmem_empty_bar[buf], ((unit >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
@@ -236,14 +258,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               if (p.conv) {
 #pragma unroll
                 for (int dxi = 0; dxi < 3; ++dxi) {
-                  const uint64_t adesc = make_smem_desc_sbo(a_addr + dxi * 128, 1280, p.base_offset);
-                  const uint64_t bdesc = make_smem_desc_sbo(a_addr + CP_A_SLOT + dxi * wq_bytes, 1024, 0);
+                  const uint64_t adesc = make_smem_desc_sbo(a_addr + dxi * 128, 1280);
+                  const uint64_t bdesc = make_smem_desc_sbo(a_addr + CP_A_SLOT + dxi * wq_bytes, 1024);
 #pragma unroll
                   for (int k = 0; k < BK / 16; ++k) umma_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, (step > 0 || dxi > 0 || k > 0) ? 1u : 0u);
                 }
               } else {
-                const uint64_t adesc = make_smem_desc_sbo(a_addr, 1024, 0);
-                const uint64_t bdesc = make_smem_desc_sbo(a_addr + A_TILE_BYTES, 1024, 0);
+                const uint64_t adesc = make_smem_desc_sbo(a_tile + (uint32_t)step * A_TILE_BYTES, 1024);
+                const uint64_t bdesc = make_smem_desc_sbo(a_addr, 1024);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) umma_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, (step > 0 || k > 0) ? 1u : 0u);
               }
@@ -252,7 +274,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if (elect_one()) umma_commit_pair(&tmem_full_bar[buf], 3);
+          if (elect_one()) {
+            umma_commit_pair(&tmem_full_bar[buf], 3);
+            if (!p.conv && u2 == ns2 - 1) umma_commit_pair(&a_empty_bar[it & 1], 3);   // the resident A buffer may be refilled
+          }
           __syncwarp();
         }
       }
@@ -285,10 +310,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const uint32_t buf = unit & 1u;
         const int row0 = t * 256 + rank * 128 + quarter * 32;
         const int m_lane = row0 + lane;
-        const bool live = !(p.exp_mode & 4);
         // residual stream of this warp's rows and the SE gates of its board: requested before the accumulator is ready
         float xr[NCH][16];
-        if (resid && live) {
+        if (resid) {
           const float* xrow = p.resid_x + (size_t)m_lane * p.ldc + h * nh;
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
@@ -296,7 +320,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ci < nchunks && m_lane < M && !(p.exp_mode & 32)) v = *reinterpret_cast<const float4*>(xrow + ci * 16 + 4 * q);
+              if (ci < nchunks && m_lane < M) v = *reinterpret_cast<const float4*>(xrow + ci * 16 + 4 * q);
               xr[k][4 * q] = v.x; xr[k][4 * q + 1] = v.y; xr[k][4 * q + 2] = v.z; xr[k][4 * q + 3] = v.w;
             }
           }
@@ -307,7 +331,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               *reinterpret_cast<float4*>(wgate + k * 16 + 4 * q) = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bq * p.N + h * nh + ci * 16 + 4 * q));
           }
         }
-        if (resid && live) {
+        if (resid) {
           // pull the residual rows of the NEXT work item into L2 while this one is processed (its loads above then hit L2)
           const int nt = h ? t + num_clusters : t, nh2 = h ? 0 : 1;
           const int nm = nt * 256 + rank * 128 + quarter * 32 + lane;
@@ -325,13 +349,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t r[NCH][16];
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
-          if (live && cset + 2 * k < nchunks) tmem_ld_32x16(tmem_row + (uint32_t)((cset + 2 * k) * 16), r[k]);
+          if (cset + 2 * k < nchunks) tmem_ld_32x16(tmem_row + (uint32_t)((cset + 2 * k) * 16), r[k]);
         tmem_ld_wait();
         // the accumulator is free again: the MMAs of the work item after next may overwrite it while this one is stored
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_empty + buf * 8u);
-        if (!live) continue;
         if (resid) {
           // x_new = x + gate * conv  (SE excitation + residual add, resnet.py:68-80), written back in place
 #pragma unroll
@@ -363,7 +386,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               for (int i = 0; i < 4; ++i) {
                 const int rr = (lane >> 2) + 8 * i;
                 const int m = row0 + rr;
-                if (m < M && !(p.exp_mode & 64)) {
+                if (m < M) {
                   uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((q ^ ((rr >> 1) & 3)) << 2));
                   *reinterpret_cast<uint4*>(p.resid_x + (size_t)m * p.ldc + col + 4 * q) = v;
                 }

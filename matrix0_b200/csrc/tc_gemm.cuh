@@ -185,7 +185,6 @@ struct GemmParams {
   const float* gn_gamma;
   const float* gn_beta;
   float* pool_part;
-  int exp_mode;      // timing experiments only (results invalid): 1 = load W once per tile, 2 = load A once per tile
   int n_slices;      // >= 1: the launch covers n_slices consecutive groups of N output columns (w_row0 / col0 advance by N per slice);
                      // a CTA walks the slices of one M tile back to back, so the A tile is re-read from L2, not from HBM
 };
@@ -276,17 +275,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
           uint8_t* w_dst = a_dst + A_TILE_BYTES;
-          const bool skip_a = ((p.exp_mode & 2) && kb > 0), skip_w = ((p.exp_mode & 1) && kb > 0);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)((skip_a ? 0 : A_TILE_BYTES) + (skip_w ? 0 : w_tile_bytes)));
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
-          if (skip_a) {
-          } else if (p.conv) {
+          if (p.conv) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
             tma_load_4d(a_dst, &tma_a, &full_bar[stage], kc * BK, dx, dy, m0 >> 6);
           } else {
             tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m0);
           }
-          for (int part = 0; part < n_parts && !skip_w; ++part) {
+          for (int part = 0; part < n_parts; ++part) {
             uint8_t* dst = w_dst + ((size_t)part * p.n_part + (size_t)rank * slice_rows) * BK * 2;
             const int row = w_row0 + part * p.n_part + rank * slice_rows;
             if (cs > 1) tma_load_2d_mcast(dst, &tma_w, &full_bar[stage], kb * BK, row, mask);
@@ -386,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (quarter < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
         else asm volatile("bar.sync 3, 128;" ::: "memory");
       }
-      for (int c0 = cset * 32; c0 < p.N && !(p.exp_mode & 4); c0 += 64) {
+      for (int c0 = cset * 32; c0 < p.N; c0 += 64) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
         tmem_ld_wait();
