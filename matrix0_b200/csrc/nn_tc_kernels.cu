@@ -128,6 +128,20 @@ int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C, 
   return M0_OK;
 }
 
+// row-major output tensor [rows][cols] (16-bit or fp32) written by the pair kernel's bulk stores: box {16 columns, 32 rows}, no swizzle
+int make_map_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, bool fp32) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { m0_set_error("cuTensorMapEncodeTiled is not available from the driver"); return M0_ERR_CUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (fp32 ? 4 : 2)};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { m0_set_error("cuTensorMapEncodeTiled(out %llu x %llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (int)r); return M0_ERR_CUDA; }
+  return M0_OK;
+}
+
 struct TcWeight {
   __nv_bfloat16* w = nullptr;  // [n][k] bf16
   CUtensorMap map;             // box {64, n_part / cluster}
@@ -183,6 +197,10 @@ struct TcState {
   __nv_bfloat16 *a1 = nullptr, *a2 = nullptr;
   CUtensorMap a1_conv, a2_conv, a1_mat, a2_mat;
   CUtensorMap a1_convp, a2_convp, planes_convp;   // x-padded boxes of the CTA-pair kernel
+  CUtensorMap qkv_out, t2f_out;                   // qkv (half, 3C columns) and n->t2 as fp32 (attention projection)
+  CUtensorMap a1_out, a2_out, t1_out, t2h_out;    // output maps of the pair kernel's bulk stores (a1, a2 half; n->t1 fp32; n->t2 as half)
+  const void *t1_ptr = nullptr, *t2_ptr = nullptr;
+  int out_rows = 0;
   std::vector<void*> allocs;
 };
 
@@ -274,7 +292,7 @@ struct ConvFusion {   // optional fused epilogue inputs / outputs of the CTA-pai
 
 int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int boards, int cin, float* out_f32, __nv_bfloat16* out_half,
                      int ldc, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr,
-                     const ConvFusion* fuse = nullptr, int conv = 1, int n_slices = 1) {
+                     const ConvFusion* fuse = nullptr, int conv = 1, int n_slices = 1, const CUtensorMap* out_map = nullptr) {
   tc::ConvPairParams p;
   memset(&p, 0, sizeof(p));
   p.boards = boards;
@@ -329,7 +347,8 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a_map, w.map_pair, p));
+  p.out_tma = (out_map && !fz) ? 1 : 0;   // the epilogue fills shared-memory tiles and TMA writes them out
+  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a_map, w.map_pair, p.out_tma ? *out_map : a_map, p));
   return m0_check_launch("conv_pair_kernel");
 }
 
@@ -427,21 +446,22 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
 // 3x3 convolution of B boards with all C_out channels in one launch: CTA-pair kernel when the weight supports it
 int conv3x3(TcState* st, const CUtensorMap& a_map, const CUtensorMap& a_map_pair, const TcWeight& w, int B, int cin, float* out_f32,
             __nv_bfloat16* out_half, int act, cudaStream_t s, const float* gn_gamma = nullptr, const float* gn_beta = nullptr,
-            float* pool_part = nullptr, const ConvFusion* fuse = nullptr) {
-  if (w.pair) return launch_conv_pair(st, a_map_pair, w, B, cin, out_f32, out_half, w.n, act, s, gn_gamma, gn_beta, pool_part, fuse);
+            float* pool_part = nullptr, const ConvFusion* fuse = nullptr, const CUtensorMap* out_map = nullptr) {
+  if (w.pair) return launch_conv_pair(st, a_map_pair, w, B, cin, out_f32, out_half, w.n, act, s, gn_gamma, gn_beta, pool_part, fuse, 1, 1, out_map);
   if (fuse) { m0_set_error("fused SE / residual epilogue needs the CTA-pair convolution"); return M0_ERR_ARG; }
   return launch_gemm(st, a_map, w, B * 64, 1, 9, cin, 0, w.n, out_f32, out_half, w.n, 0, nullptr, act, 1.0f, s, gn_gamma, gn_beta, pool_part);
 }
 
 // out = A[B*64][cin] W^T for all n_slices * n_launch output channels in one launch (1x1 convolutions over the board tensor)
 int gemm_rows64(TcState* st, const CUtensorMap& a_mat, const TcWeight& w, int B, int cin, float* out_f32, __nv_bfloat16* out_half, int ldc,
-                cudaStream_t s) {
+                cudaStream_t s, const CUtensorMap* out_map = nullptr) {
   const int n_slices = w.n / w.n_launch;
   // M0_TC_PAIR_GEMM=1: CTA-pair kernel with the A tile resident across the (slice, half) work items of a group of boards; measured
   // slower than the single-CTA kernel for K = 320 (both are bound by their epilogues there), so it is opt-in
   static int pg = -1;
   if (pg < 0) pg = env_int("M0_TC_PAIR_GEMM", 0);
-  if (pg && w.pair && cin <= 320) return launch_conv_pair(st, a_mat, w, B, cin, out_f32, out_half, ldc, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, 0, n_slices);
+  if (pg && w.pair && cin <= 320)
+    return launch_conv_pair(st, a_mat, w, B, cin, out_f32, out_half, ldc, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, 0, n_slices, out_map);
   return launch_gemm(st, a_mat, w, B * 64, 0, 1, cin, 0, w.n_launch, out_f32, out_half, ldc, 0, nullptr, ACT_NONE, 1.0f, s, nullptr, nullptr, nullptr, -1,
                      n_slices);
 }
@@ -505,6 +525,7 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   TRY(make_map_nhwc(&st->a2_conv, st->a2, need, C));
   TRY(make_map_nhwc(&st->a1_convp, st->a1, need, C, 10));
   TRY(make_map_nhwc(&st->a2_convp, st->a2, need, C, 10));
+  st->t1_ptr = st->t2_ptr = nullptr;   // the output maps are rebuilt on the next forward
   TRY(make_map_2d(&st->a1_mat, st->a1, (uint64_t)need * 64, C, 128));
   TRY(make_map_2d(&st->a2_mat, st->a2, (uint64_t)need * 64, C, 128));
   st->cap = need;
@@ -653,18 +674,30 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   const m0_net_weights& w = n->w;
   const int C = c.channels, M = B * 64, act = c.activation;
   const float* none = nullptr;
+  if (st->t1_ptr != n->t1 || st->t2_ptr != n->t2 || st->out_rows != M) {
+    // output maps of the bulk stores: their row extent is exactly this batch (rows of padding boards are clipped by TMA)
+    TRY(make_map_out(&st->a1_out, st->a1, (uint64_t)M, C, false));
+    TRY(make_map_out(&st->a2_out, st->a2, (uint64_t)M, C, false));
+    TRY(make_map_out(&st->t1_out, n->t1, (uint64_t)M, C, true));
+    TRY(make_map_out(&st->t2h_out, n->t2, (uint64_t)M, C, false));
+    TRY(make_map_out(&st->t2f_out, n->t2, (uint64_t)M, C, true));
+    TRY(make_map_out(&st->qkv_out, st->qkv_h, (uint64_t)M, 3 * (uint64_t)C, false));
+    st->t1_ptr = n->t1;
+    st->t2_ptr = n->t2;
+    st->out_rows = M;
+  }
   // stem: planes -> NHWC half (64 channels, zero padded) -> tensor-core conv3x3 -> GN + act (+ position encoding)
   PROF("planes_to_nhwc_half", nn_planes_to_nhwc_half(planes, st->planes_h, B, c.planes, s));
-  PROF("conv_other", conv3x3(st, st->planes_conv, st->planes_convp, st->stem, B, 64, n->t1, nullptr, ACT_NONE, s));
+  PROF("conv_other", conv3x3(st, st->planes_conv, st->planes_convp, st->stem, B, 64, n->t1, nullptr, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, &st->t1_out));
   if (c.chess_features) {
     PROF("gn_act_res", nn_gn_act_res(n->t1, w.stem_gn_w, w.stem_gn_b, w.pos_enc, 0, n->x, st->a1, B, C, act, s));
     float* cur = n->x;
     if (c.piece_square_tables) {
-      PROF("gemm_pst", gemm_rows64(st, st->a1_mat, st->pst, B, C, n->t1, nullptr, C, s));
+      PROF("gemm_pst", gemm_rows64(st, st->a1_mat, st->pst, B, C, n->t1, nullptr, C, s, &st->t1_out));
       PROF("gn_act_res", nn_gn_act_res(n->t1, w.pst_gn_w, w.pst_gn_b, n->x, (long long)64 * C, n->t2, st->a1, B, C, act, s));
       cur = n->t2;
     }
-    PROF("conv_other", conv3x3(st, st->a1_conv, st->a1_convp, st->inter, B, C, n->t1, nullptr, ACT_NONE, s));
+    PROF("conv_other", conv3x3(st, st->a1_conv, st->a1_convp, st->inter, B, C, n->t1, nullptr, ACT_NONE, s, nullptr, nullptr, nullptr, nullptr, &st->t1_out));
     PROF("gn_act_res", nn_gn_act_res(n->t1, w.inter_gn_w, w.inter_gn_b, cur, (long long)64 * C, n->x, nullptr, B, C, act, s));
   } else {
     PROF("groupnorm_f32", nn_groupnorm_f32(n->t1, w.stem_gn_w, w.stem_gn_b, nullptr, 0, n->x, B, C, act, s));
@@ -703,11 +736,12 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
                                       fuse_next ? w.blocks[i + 1].gn1_b : nullptr, nullptr, &f2));
     } else {
       // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
-      PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr));
+      PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr, nullptr, &st->a2_out));
       // conv2 with the SE squeeze (half-board column sums) fused into the epilogue
       // (conv2's output is kept in the 16-bit operand format, as under the reference's autocast; the fp32 buffer t2 is reused for it)
       __nv_bfloat16* t2h = reinterpret_cast<__nv_bfloat16*>(n->t2);
-      PROF("conv2+pool", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, t2h, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr));
+      PROF("conv2+pool", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, t2h, ACT_NONE, s, nullptr, nullptr, c.se ? st->pool : nullptr, nullptr,
+                                 &st->t2h_out));
       const float* gate = nullptr;
       if (c.se) {
         PROF("se_gate", nn_se_gate(st->pool, st->se_w1t[i], b.se_b1, st->se_w2t[i], b.se_b2, st->se_gate, B, C, c.se_hidden, act, s));
@@ -720,14 +754,14 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     if (run_att) {
       const float* rb = c.attention_relbias ? b.att_rel_bias : nullptr;
       if (tc_att) {
-        PROF("gemm_qkv", gemm_rows64(st, st->a1_mat, tb.qkv, B, C, nullptr, st->qkv_h, 3 * C, s));
+        PROF("gemm_qkv", gemm_rows64(st, st->a1_mat, tb.qkv, B, C, nullptr, st->qkv_h, 3 * C, s, &st->qkv_out));
         PROF("attention_tc", nn_attention_tc(st->qkv_h, rb, st->a2, B, C, c.attention_heads, c.attention_unmasked_mix, s));
       } else {
         PROF("gemm_qkv", gemm_rows64(st, st->a1_mat, tb.qkv, B, C, n->qkv, nullptr, 3 * C, s));
         PROF("attention_f32", nn_attention_f32(n->qkv, rb, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
         PROF("f32_to_bf16", nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
       }
-      PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, n->t2, nullptr, C, s));
+      PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, n->t2, nullptr, C, s, &st->t2f_out));
       // x = LN(proj + x) and, in the same pass, a1 = act(GN1_{i+1}(x)) for the next block
       if (C % 64 == 0 && C <= 320) {
         PROF("ln_res_gn", nn_ln_res_gn(n->t2, n->x, b.att_ln_w, b.att_ln_b, last ? nullptr : w.blocks[i + 1].gn1_w, last ? nullptr : w.blocks[i + 1].gn1_b,
@@ -791,7 +825,9 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
     w.pair = true;
     TRY(make_map_2d(&w.map_pair, d_w_bf16, (uint64_t)n, (uint64_t)taps * cin, (uint32_t)(n / 4)));
     TRY(make_map_nhwc(&a, d_act_bf16, (uint64_t)boards, (uint64_t)cin, 10));
-    return launch_conv_pair(&st, a, w, boards, cin, d_out_f32, nullptr, n, ACT_NONE, (cudaStream_t)stream);
+    CUtensorMap om;
+    TRY(make_map_out(&om, d_out_f32, (uint64_t)boards * 64, (uint64_t)n, true));
+    return launch_conv_pair(&st, a, w, boards, cin, d_out_f32, nullptr, n, ACT_NONE, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 1, 1, &om);
   }
   if (taps == 1 && pair_ok(n) && cin <= 320) {   // plain GEMM over whole boards on the CTA-pair kernel (qkv / proj / piece-square projections)
     w.pair = true;

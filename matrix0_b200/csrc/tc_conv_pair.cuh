@@ -35,6 +35,8 @@ struct ConvPairParams {
   float* out_f32;   // [boards*64][ldc] or null
   __nv_bfloat16* out_half;   // same shape, 16-bit storage in the operand format, or null
   int ldc;
+  int out_tma;      // 1: the output goes out through tma_out (box {16 columns, 32 rows} of the out_f32 / out_half tensor, row-major) -- the
+                    // epilogue warps only fill a shared-memory tile; 0: direct stores from the smem transposer
   // fused epilogues (tc_gemm.cuh GemmParams): GroupNorm(16-channel groups over a board) + activation -> out_half,
   // or the SE squeeze partial sums pool_part[(board*2 + half board)][n]
   int act;
@@ -114,6 +116,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr));
 }
 // K-major 128-byte-swizzled operand whose 8-row groups are sbo_bytes apart (1024 for a dense tile)
+// bulk tensor store of a row-major shared-memory tile (box of the map) to global memory; rows / columns past the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 // The swizzle phase follows the absolute shared-memory address bits [7,10) (measured: a start that is a multiple of 128 B but not
 // of 1024 B reads the rows TMA wrote there correctly with base_offset = 0), which is what lets one x-padded box serve three taps.
 __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -123,7 +134,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
 // FUSE compiles the SE / residual / half-board-sum epilogues in (kept out of the plain kernels: code size costs instruction fetch)
 template <int NCH, bool FUSE>
 __global__ void __launch_bounds__(CP_THREADS, 1)
-conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const ConvPairParams p) {
+conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_out,
+                 const ConvPairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nh = p.N >> 1, nq = p.N >> 2;
@@ -303,7 +315,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int c = epi_tid; c < p.N; c += 256) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    uint32_t unit = 0;
+    uint32_t unit = 0, nstore = 0;   // nstore: bulk stores issued by this warp (selects the output tile buffer)
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       for (int u2 = 0; u2 < ns2; ++u2, ++unit) {
         const int h = u2 & 1, cbase = (u2 >> 1) * p.N + h * nh;   // first output column of this work item
@@ -468,6 +480,57 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(y[j]);
           }
+          if (!FUSE && p.out_tma) {
+            // ---- output through TMA: this lane's row of the chunk goes into a row-major tile, one bulk store per chunk ----
+            if (p.pool_part && row0 < M) {
+              // column sums over the 32 rows (lanes) of this half board: reduce-scatter over lane bits 4..1, then bit 0
+              float a8[8], a4[4], a2[2];
+              const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float send = __uint_as_float(b4 ? r[k][j] : r[k][8 + j]), keep = __uint_as_float(b4 ? r[k][8 + j] : r[k][j]);
+                a8[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) a4[j] = (b3 ? a8[4 + j] : a8[j]) + __shfl_xor_sync(0xFFFFFFFFu, b3 ? a8[j] : a8[4 + j], 8);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) a2[j] = (b2 ? a4[2 + j] : a4[j]) + __shfl_xor_sync(0xFFFFFFFFu, b2 ? a4[j] : a4[2 + j], 4);
+              float a1 = (b1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? a2[0] : a2[1], 2);
+              a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, 1);
+              if (!(lane & 1)) p.pool_part[(size_t)(row0 >> 5) * p.N + col + (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0)] = a1;
+            }
+            if (p.out_half) {
+              uint8_t* tile = reinterpret_cast<uint8_t*>(stg) + (nstore & 1) * 1024;   // two 32 x 32 B tiles alternate
+              if (lane == 0) tma_store_wait_read<1>();                                 // the store that last read this tile is done
+              __syncwarp();
+              uint4 lo, hi;
+              lo.x = pack_half2(__uint_as_float(r[k][0]), __uint_as_float(r[k][1]), p.fp16);
+              lo.y = pack_half2(__uint_as_float(r[k][2]), __uint_as_float(r[k][3]), p.fp16);
+              lo.z = pack_half2(__uint_as_float(r[k][4]), __uint_as_float(r[k][5]), p.fp16);
+              lo.w = pack_half2(__uint_as_float(r[k][6]), __uint_as_float(r[k][7]), p.fp16);
+              hi.x = pack_half2(__uint_as_float(r[k][8]), __uint_as_float(r[k][9]), p.fp16);
+              hi.y = pack_half2(__uint_as_float(r[k][10]), __uint_as_float(r[k][11]), p.fp16);
+              hi.z = pack_half2(__uint_as_float(r[k][12]), __uint_as_float(r[k][13]), p.fp16);
+              hi.w = pack_half2(__uint_as_float(r[k][14]), __uint_as_float(r[k][15]), p.fp16);
+              *reinterpret_cast<uint4*>(tile + lane * 32) = lo;
+              *reinterpret_cast<uint4*>(tile + lane * 32 + 16) = hi;
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&tma_out, tile, col, row0); tma_store_commit(); }
+              ++nstore;
+            } else {
+              uint8_t* tile = reinterpret_cast<uint8_t*>(stg);                          // one 32 x 64 B tile
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(tile + lane * 64 + q * 16) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&tma_out, tile, col, row0); tma_store_commit(); }
+            }
+            continue;
+          }
           // lane = row; 16-byte chunk q of row i sits at chunk position q ^ ((i >> 1) & 3) (conflict-free both ways)
           const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -546,6 +609,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();   // the tile buffers must outlive the bulk stores that read them
   }
   tc_fence_before();
   __syncthreads();
