@@ -129,7 +129,7 @@ int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t boards, uint64_t C, 
 }
 
 // row-major output tensor [rows][cols] (16-bit or fp32) written by the pair kernel's bulk stores: box {16 columns, 32 rows}, no swizzle
-int make_map_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, bool fp32) {
+int make_map_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, bool fp32, bool swizzle64 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { m0_set_error("cuTensorMapEncodeTiled is not available from the driver"); return M0_ERR_CUDA; }
   cuuint64_t dims[2] = {cols, rows};
@@ -137,7 +137,8 @@ int make_map_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
   cuuint32_t box[2] = {16, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { m0_set_error("cuTensorMapEncodeTiled(out %llu x %llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (int)r); return M0_ERR_CUDA; }
   return M0_OK;
 }
@@ -197,6 +198,8 @@ struct TcState {
   __nv_bfloat16 *a1 = nullptr, *a2 = nullptr;
   CUtensorMap a1_conv, a2_conv, a1_mat, a2_mat;
   CUtensorMap a1_convp, a2_convp, planes_convp;   // x-padded boxes of the CTA-pair kernel
+  CUtensorMap x_io;                               // residual stream n->x (fp32, 64-byte swizzled tiles) for the fused conv2 epilogue
+  const void* x_ptr = nullptr;
   CUtensorMap qkv_out, t2f_out;                   // qkv (half, 3C columns) and n->t2 as fp32 (attention projection)
   CUtensorMap a1_out, a2_out, t1_out, t2h_out;    // output maps of the pair kernel's bulk stores (a1, a2 half; n->t1 fp32; n->t2 as half)
   const void *t1_ptr = nullptr, *t2_ptr = nullptr;
@@ -288,6 +291,7 @@ struct ConvFusion {   // optional fused epilogue inputs / outputs of the CTA-pai
   float* resid_x = nullptr;
   const float* gate = nullptr;
   __nv_bfloat16* prims = nullptr;
+  const CUtensorMap* x_map = nullptr;   // resid_x as a [rows][C] fp32 tensor, box {16, 32}, 64-byte swizzle (tiles in and out by TMA)
 };
 
 int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int boards, int cin, float* out_f32, __nv_bfloat16* out_half,
@@ -314,15 +318,16 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   if (cap < 0) cap = env_int("M0_TC_STAGES", 0);   // pipeline-depth experiments
   const int stage_bytes = conv ? tc::CP_A_SLOT + 3 * (w.n_launch / 4) * 128 : (w.n_launch / 4) * 128;
   const int a_res = conv ? 0 : 2 * (cin / 64) * tc::A_TILE_BYTES;   // plain mode keeps two resident A tiles (K <= 320)
-  int stages = (st->max_smem - 2048 - tc::CP_EPI_BYTES - a_res) / stage_bytes;
+  const bool fz = fuse && (fuse->resid_x || fuse->prims);
+  const int epi_bytes = fz ? tc::CP_EPI_BYTES_FUSE : tc::CP_EPI_BYTES;
+  int stages = (st->max_smem - 2048 - epi_bytes - a_res) / stage_bytes;
   if (stages > 8) stages = 8;
   if (cap > 0 && stages > cap) stages = cap;
   if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n_launch); return M0_ERR_ARG; }
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + a_res + tc::CP_EPI_BYTES + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + a_res + epi_bytes + 1024 + 512;
   // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
   const int nch = (w.n_launch + 63) / 64;
-  const bool fz = fuse && (fuse->resid_x || fuse->prims);
   auto kernel = fz ? (nch <= 2 ? tc::conv_pair_kernel<2, true> : nch <= 5 ? tc::conv_pair_kernel<5, true> : tc::conv_pair_kernel<8, true>)
                    : (nch <= 2 ? tc::conv_pair_kernel<2, false> : nch <= 5 ? tc::conv_pair_kernel<5, false> : tc::conv_pair_kernel<8, false>);
   const int kidx = (nch <= 2 ? 0 : nch <= 5 ? 1 : 2) + (fz ? 3 : 0);
@@ -347,8 +352,9 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  p.out_tma = (out_map && !fz) ? 1 : 0;   // the epilogue fills shared-memory tiles and TMA writes them out
-  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a_map, w.map_pair, p.out_tma ? *out_map : a_map, p));
+  if (fuse && fuse->resid_x && (!fuse->x_map || (out_half && !out_map))) { m0_set_error("pair kernel: the residual epilogue needs the x and output tensor maps"); return M0_ERR_ARG; }
+  p.out_tma = (out_map && !(fuse && fuse->prims)) ? 1 : 0;   // the epilogue fills shared-memory tiles and TMA writes them out
+  M0_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a_map, w.map_pair, out_map ? *out_map : a_map, (fuse && fuse->x_map) ? *fuse->x_map : a_map, p));
   return m0_check_launch("conv_pair_kernel");
 }
 
@@ -607,7 +613,7 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
     }
     // fused SE + residual epilogue of conv2 (M0_TC_FUSE_SE=0 keeps the separate SE / residual kernels)
     st->hid_pad = (c.se_hidden + 63) / 64 * 64;
-    st->se_fused = env_int("M0_TC_FUSE_SE", 0) != 0 && pair_ok(C) && (!c.se || (c.se_hidden % 16 == 0 && c.se_hidden <= 256));
+    st->se_fused = env_int("M0_TC_FUSE_SE", 1) != 0 && pair_ok(C) && (!c.se || (c.se_hidden % 16 == 0 && c.se_hidden <= 256));
     st->blocks.resize(c.blocks);
     for (int i = 0; i < c.blocks && rc == M0_OK; ++i) {
       const m0_block_weights& b = n->w.blocks[i];
@@ -674,7 +680,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   const m0_net_weights& w = n->w;
   const int C = c.channels, M = B * 64, act = c.activation;
   const float* none = nullptr;
-  if (st->t1_ptr != n->t1 || st->t2_ptr != n->t2 || st->out_rows != M) {
+  if (st->t1_ptr != n->t1 || st->t2_ptr != n->t2 || st->x_ptr != n->x || st->out_rows != M) {
     // output maps of the bulk stores: their row extent is exactly this batch (rows of padding boards are clipped by TMA)
     TRY(make_map_out(&st->a1_out, st->a1, (uint64_t)M, C, false));
     TRY(make_map_out(&st->a2_out, st->a2, (uint64_t)M, C, false));
@@ -682,6 +688,8 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
     TRY(make_map_out(&st->t2h_out, n->t2, (uint64_t)M, C, false));
     TRY(make_map_out(&st->t2f_out, n->t2, (uint64_t)M, C, true));
     TRY(make_map_out(&st->qkv_out, st->qkv_h, (uint64_t)M, 3 * (uint64_t)C, false));
+    TRY(make_map_out(&st->x_io, n->x, (uint64_t)M, C, true, true));
+    st->x_ptr = n->x;
     st->t1_ptr = n->t1;
     st->t2_ptr = n->t2;
     st->out_rows = M;
@@ -732,8 +740,9 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
       ConvFusion f2;
       f2.resid_x = n->x;
       f2.gate = c.se ? st->se_gate : nullptr;
+      f2.x_map = &st->x_io;
       PROF("conv2+se+res+gn", conv3x3(st, st->a2_conv, st->a2_convp, tb.conv2, B, C, nullptr, next_a, act, s, fuse_next ? w.blocks[i + 1].gn1_w : nullptr,
-                                      fuse_next ? w.blocks[i + 1].gn1_b : nullptr, nullptr, &f2));
+                                      fuse_next ? w.blocks[i + 1].gn1_b : nullptr, nullptr, &f2, next_a ? &st->a1_out : nullptr));
     } else {
       // conv1 with GN2 + activation fused into the epilogue: a2 = act(GN2(conv1(a1)))
       PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr, nullptr, &st->a2_out));

@@ -62,6 +62,7 @@ static constexpr int CP_EPI_WARP0 = 4;
 static constexpr int CP_REGS_CTRL = 40, CP_REGS_EPI = 232;   // setmaxnreg split of the 64K register file (128*40 + 256*232)
 static constexpr int CP_A_SLOT = 160 * 128;   // 2 boards x 8 y x 10 x rows of 64 channels
 static constexpr int CP_EPI_BYTES = 8 * 32 * 16 * 4 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4 + 8 * 128 * 4;   // transposers + gamma/beta + GN partial sums + SE gates
+static constexpr int CP_EPI_BYTES_FUSE = CP_EPI_BYTES + 8 * 6144;   // FUSE kernels: 8 KB of tiles per epilogue warp instead of 2 KB
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -135,7 +136,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
 template <int NCH, bool FUSE>
 __global__ void __launch_bounds__(CP_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_out,
-                 const ConvPairParams p) {
+                 const __grid_constant__ CUtensorMap tma_x, const ConvPairParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nh = p.N >> 1, nq = p.N >> 2;
@@ -149,7 +150,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   smem += 2 * (size_t)a_res_bytes;              // ring base
   const int ns2 = 2 * (p.n_slices > 1 ? p.n_slices : 1);   // work items per group of 4 boards: (slice, channel half)
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  float* s_gamma = epi_stage + 8 * 512;   // [512]
+  float* s_gamma = epi_stage + 8 * (FUSE ? 2048 : 512);   // [512]
   float* s_beta = s_gamma + 512;          // [512]
   float* s_stats = s_beta + 512;          // [2 accumulators][4 quarters][16 groups][sum, sumsq]
   float* s_gate = s_stats + 256;          // [8 epilogue warps][NCH * 16]
@@ -159,7 +160,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], only the leader's are used
   uint64_t* a_full_bar = tmem_empty_bar + 2;        // [2] resident A tile landed (leader's are used)
   uint64_t* a_empty_bar = a_full_bar + 2;           // [2] every MMA reading the resident A tile has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 2);
+  uint64_t* x_bar = a_empty_bar + 2;                // [8 epilogue warps][2] residual tiles landed (FUSE)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -181,6 +183,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(&a_full_bar[b], 1);
       mbar_init(&a_empty_bar[b], 1);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&x_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -301,7 +304,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     //       -> GroupNorm / activation in registers -> smem transpose -> coalesced stores, 16 columns at a time =====
     const int quarter = warp & 3;
     const int cset = (warp - CP_EPI_WARP0) >> 2;        // the two warps of a lane quarter take alternate 16-column chunks
-    float* stg = epi_stage + (warp - CP_EPI_WARP0) * 512;
+    // per-warp staging: 2 KB (transposer / two 1 KB output tiles), or 8 KB in the FUSE kernels (two 2 KB residual tiles in, two out)
+    uint8_t* wtile = reinterpret_cast<uint8_t*>(epi_stage) + (size_t)(warp - CP_EPI_WARP0) * (FUSE ? 8192 : 2048);
+    float* stg = reinterpret_cast<float*>(wtile);
+    uint8_t* xin = wtile;                          // FUSE: residual tiles by TMA
+    uint8_t* xout = FUSE ? wtile + 4096 : wtile;   // output tiles of the bulk stores
+    uint64_t* xbar = x_bar + (warp - CP_EPI_WARP0) * 2;
+    uint32_t xuse[2] = {0, 0};                     // completed uses of each residual tile buffer (mbarrier phase)
     float* wgate = s_gate + (warp - CP_EPI_WARP0) * (NCH * 16);   // this warp's SE gates of the current work item
     const bool fused_gn = p.gn_gamma != nullptr;
     const bool resid = FUSE && p.resid_x != nullptr;
@@ -322,36 +331,22 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const uint32_t buf = unit & 1u;
         const int row0 = t * 256 + rank * 128 + quarter * 32;
         const int m_lane = row0 + lane;
-        // residual stream of this warp's rows and the SE gates of its board: requested before the accumulator is ready
-        float xr[NCH][16];
+        // residual tiles of this warp's first two chunks (TMA -> shared memory) and the SE gates of its board: requested before
+        // the accumulator is ready
         if (resid) {
-          const float* xrow = p.resid_x + (size_t)m_lane * p.ldc + h * nh;
+          if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < NCH; ++k) {
-            const int ci = cset + 2 * k;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ci < nchunks && m_lane < M) v = *reinterpret_cast<const float4*>(xrow + ci * 16 + 4 * q);
-              xr[k][4 * q] = v.x; xr[k][4 * q + 1] = v.y; xr[k][4 * q + 2] = v.z; xr[k][4 * q + 3] = v.w;
-            }
+            for (int k = 0; k < 2; ++k)
+              if (k < NCH && cset + 2 * k < nchunks) {
+                mbar_expect_tx(&xbar[k], 2048);
+                tma_load_2d(xin + k * 2048, &tma_x, &xbar[k], cbase + (cset + 2 * k) * 16, row0);
+              }
           }
           if (p.gate) {
             const int bq = row0 >> 6;
             const int k = lane >> 2, q = lane & 3, ci = cset + 2 * k;
             if (k < NCH && ci < nchunks && row0 < M)
               *reinterpret_cast<float4*>(wgate + k * 16 + 4 * q) = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bq * p.N + h * nh + ci * 16 + 4 * q));
-          }
-        }
-        if (resid) {
-          // pull the residual rows of the NEXT work item into L2 while this one is processed (its loads above then hit L2)
-          const int nt = h ? t + num_clusters : t, nh2 = h ? 0 : 1;
-          const int nm = nt * 256 + rank * 128 + quarter * 32 + lane;
-          if (nt < num_tiles && nm < M) {
-            const float* nx = p.resid_x + (size_t)nm * p.ldc + nh2 * nh;
-#pragma unroll
-            for (int k = 0; k < NCH; ++k)
-              if (cset + 2 * k < nchunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (cset + 2 * k) * 16));
           }
         }
         mbar_wait(&tmem_full_bar[buf], (unit >> 1) & 1u);
@@ -368,60 +363,64 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_empty + buf * 8u);
         if (resid) {
-          // x_new = x + gate * conv  (SE excitation + residual add, resnet.py:68-80), written back in place
+          // x_new = x + gate * conv  (SE excitation + residual add, resnet.py:68-80): the x tile arrives by TMA (64-byte swizzle: 16-byte
+          // chunk c of row i sits at c ^ ((i >> 1) & 3)), x_new leaves the same way; nothing here touches global memory directly
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
             const int ci = cset + 2 * k;
             if (ci >= nchunks) break;
-            const int col = h * nh + ci * 16;
-            if (p.gate) {
+            const int col = cbase + ci * 16;
+            const int xb = k & 1;
+            mbar_wait(&xbar[xb], (xuse[xb]++) & 1u);
+            const uint8_t* xt = xin + xb * 2048 + lane * 64;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 g4 = *reinterpret_cast<const float4*>(wgate + k * 16 + 4 * q);
-                r[k][4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 0]), g4.x, xr[k][4 * q + 0]));
-                r[k][4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 1]), g4.y, xr[k][4 * q + 1]));
-                r[k][4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 2]), g4.z, xr[k][4 * q + 2]));
-                r[k][4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 3]), g4.w, xr[k][4 * q + 3]));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(__uint_as_float(r[k][j]) + xr[k][j]);
+            for (int q = 0; q < 4; ++q) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xt + ((q ^ sw) << 4));
+              float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (p.gate) g4 = *reinterpret_cast<const float4*>(wgate + k * 16 + 4 * q);
+              r[k][4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 0]), g4.x, x4.x));
+              r[k][4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 1]), g4.y, x4.y));
+              r[k][4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 2]), g4.z, x4.z));
+              r[k][4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 3]), g4.w, x4.w));
             }
-            const int sw = (lane >> 1) & 3;
+            __syncwarp();                      // every lane has read the tile: it can take the chunk after next
+            if (lane == 0 && k + 2 < NCH && ci + 4 < nchunks) {
+              mbar_expect_tx(&xbar[xb], 2048);
+              tma_load_2d(xin + xb * 2048, &tma_x, &xbar[xb], col + 64, row0);
+            }
+            {   // x_new tile -> bulk store
+              uint8_t* tile = xout + (nstore & 1) * 2048;
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(stg + lane * 16 + ((q ^ sw) << 2)) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
-            __syncwarp();
-            {
-              const int q = lane & 3;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = (lane >> 2) + 8 * i;
-                const int m = row0 + rr;
-                if (m < M) {
-                  uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((q ^ ((rr >> 1) & 3)) << 2));
-                  *reinterpret_cast<uint4*>(p.resid_x + (size_t)m * p.ldc + col + 4 * q) = v;
-                }
-              }
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ sw) << 4)) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&tma_x, tile, col, row0); tma_store_commit(); }
+              ++nstore;
             }
             if (!fused_gn && p.out_half) {   // the attention qkv GEMM takes the raw residual stream in half precision
-              const int hq = lane & 1;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const int rr = (lane >> 1) + 16 * i;
-                const int m = row0 + rr;
-                if (m < M) {
-                  const int sw2 = (rr >> 1) & 3;
-                  float4 lo = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq) ^ sw2) << 2));
-                  float4 hi = *reinterpret_cast<const float4*>(stg + rr * 16 + (((2 * hq + 1) ^ sw2) << 2));
-                  uint4 pk;
-                  pk.x = pack_half2(lo.x, lo.y, p.fp16); pk.y = pack_half2(lo.z, lo.w, p.fp16);
-                  pk.z = pack_half2(hi.x, hi.y, p.fp16); pk.w = pack_half2(hi.z, hi.w, p.fp16);
-                  *reinterpret_cast<uint4*>(p.out_half + (size_t)m * p.ldc + col + 8 * hq) = pk;
-                }
-              }
+              uint8_t* tile = xout + (nstore & 1) * 2048;
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+              uint4 lo, hi;
+              lo.x = pack_half2(__uint_as_float(r[k][0]), __uint_as_float(r[k][1]), p.fp16);
+              lo.y = pack_half2(__uint_as_float(r[k][2]), __uint_as_float(r[k][3]), p.fp16);
+              lo.z = pack_half2(__uint_as_float(r[k][4]), __uint_as_float(r[k][5]), p.fp16);
+              lo.w = pack_half2(__uint_as_float(r[k][6]), __uint_as_float(r[k][7]), p.fp16);
+              hi.x = pack_half2(__uint_as_float(r[k][8]), __uint_as_float(r[k][9]), p.fp16);
+              hi.y = pack_half2(__uint_as_float(r[k][10]), __uint_as_float(r[k][11]), p.fp16);
+              hi.z = pack_half2(__uint_as_float(r[k][12]), __uint_as_float(r[k][13]), p.fp16);
+              hi.w = pack_half2(__uint_as_float(r[k][14]), __uint_as_float(r[k][15]), p.fp16);
+              *reinterpret_cast<uint4*>(tile + lane * 32) = lo;
+              *reinterpret_cast<uint4*>(tile + lane * 32 + 16) = hi;
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&tma_out, tile, col, row0); tma_store_commit(); }
+              ++nstore;
             }
-            __syncwarp();
           }
           if (!fused_gn) continue;
         }
@@ -480,7 +479,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(y[j]);
           }
-          if (!FUSE && p.out_tma) {
+          if (p.out_tma && !want_prims) {
             // ---- output through TMA: this lane's row of the chunk goes into a row-major tile, one bulk store per chunk ----
             if (p.pool_part && row0 < M) {
               // column sums over the 32 rows (lanes) of this half board: reduce-scatter over lane bits 4..1, then bit 0
@@ -500,7 +499,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               if (!(lane & 1)) p.pool_part[(size_t)(row0 >> 5) * p.N + col + (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0)] = a1;
             }
             if (p.out_half) {
-              uint8_t* tile = reinterpret_cast<uint8_t*>(stg) + (nstore & 1) * 1024;   // two 32 x 32 B tiles alternate
+              uint8_t* tile = xout + (nstore & 1) * (FUSE ? 2048 : 1024);   // two tiles alternate
               if (lane == 0) tma_store_wait_read<1>();                                 // the store that last read this tile is done
               __syncwarp();
               uint4 lo, hi;
@@ -519,7 +518,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               if (lane == 0) { tma_store_2d(&tma_out, tile, col, row0); tma_store_commit(); }
               ++nstore;
             } else {
-              uint8_t* tile = reinterpret_cast<uint8_t*>(stg);                          // one 32 x 64 B tile
+              uint8_t* tile = xout;                                                     // one 32 x 64 B tile
               if (lane == 0) tma_store_wait_read<0>();
               __syncwarp();
 #pragma unroll

@@ -406,15 +406,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         } else if (!plain) {
-          const float* bias = p.bias ? p.bias + w_row0 + c0 : nullptr;
+          // bias (one lane per column, broadcast by shuffle), activation chosen once per chunk, scale
+          float bl = 0.0f;
+          if (p.bias && c0 + lane < n_store) bl = __ldg(p.bias + w_row0 + c0 + lane);
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + __shfl_sync(0xFFFFFFFFu, bl, j);
           const int act = p.act;
+          if (act == ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.0f, 1.0f + __expf(-x[j]));
+          } else if (act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __fdividef(x[j], 1.0f + __expf(-x[j]));
+          } else if (act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+          } else if (act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = tc_act(x[j], act);
+          }
           const float scale = p.scale;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (bias && c0 + j < n_store) x += bias[j];
-            r[j] = __float_as_uint(tc_act(x, act) * scale);
-          }
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(x[j] * scale);
         }
         // lane = row of the 32x32 block; 16-byte chunk q of row i is stored at chunk position q ^ (i & 7)
 #pragma unroll
