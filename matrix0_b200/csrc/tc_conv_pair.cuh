@@ -18,6 +18,15 @@
 // 0..127 of its own tensor memory).  Warp 0 = TMA producer (both CTAs; every load signals the LEADER's full
 // barrier), warp 1 = MMA issuer (leader CTA only) and TMEM allocator, warps 4..11 = epilogue (setmaxnreg gives
 // the two epilogue warpgroups 232 registers per thread so a warp's whole share of the accumulator stays in registers).
+//
+// Epilogues (an epilogue warp owns 32 rows = half a board and every other 16-column chunk of the work item; one chunk = one
+// GroupNorm group):
+//   plain          out_f32 / out_half (+ SE squeeze sums by warp reduce-scatter); the tile leaves through a TMA bulk store
+//   GroupNorm      act(GN(acc)) -> out_half (conv1 of a residual block); statistics exchanged between the four warps of a board
+//   FUSE kernels   conv2 of a residual block: x_new = x + gate * acc with the x tiles arriving AND leaving by TMA (64-byte swizzled,
+//                  double buffered per warp), then the next block's GroupNorm + activation -> out_half; conv1 additionally writes
+//                  the half-board sums from which the SE gate of conv2 is computed ahead of conv2 (ConvPairParams::prims)
+// A plain GEMM mode (conv = 0, K <= 320) keeps the A tile of a group of boards resident across its (slice, half) work items.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -384,15 +393,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               r[k][4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 2]), g4.z, x4.z));
               r[k][4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 3]), g4.w, x4.w));
             }
-            __syncwarp();                      // every lane has read the tile: it can take the chunk after next
+            if (lane == 0) tma_store_wait_read<1>();   // the output tile used two stores ago has been read
+            __syncwarp();                      // every lane has read the x tile (it can take the chunk after next); the output tile is free
             if (lane == 0 && k + 2 < NCH && ci + 4 < nchunks) {
               mbar_expect_tx(&xbar[xb], 2048);
               tma_load_2d(xin + xb * 2048, &tma_x, &xbar[xb], col + 64, row0);
             }
             {   // x_new tile -> bulk store
               uint8_t* tile = xout + (nstore & 1) * 2048;
-              if (lane == 0) tma_store_wait_read<1>();
-              __syncwarp();
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ sw) << 4)) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
