@@ -269,6 +269,9 @@ def reference_arm(args):
     return {"impl": "reference", "metric": "MCTS sims/sec, batched self-play, ResNet-24 (BASELINE configs[3])", "value": base["value"],
             "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"self-play, ResNet-24 fp32 on host cores, {args.sims} sims/move, single game (the reference's CPU path)"},
+            "config": {"workload": f"batched self-play: {args.games} concurrent games/GPU x {args.sims} sims/move, ResNet-24 320ch/24 blocks/20 heads, random init",
+                       "games_per_gpu": args.games, "sims_per_move": args.sims, "inference_batch_size": int(getattr(args, "leaf_batch", 96)),
+                       "sample": "the reference's CPU path (RefMCTS + fp32 torch forward on all host cores) on ONE game of that workload, "
+                                 "bounded to a few moves; games are independent, so sims/s per game is the reference's rate for any number of games"},
             "positions_per_s": base["positions_per_s"], "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
