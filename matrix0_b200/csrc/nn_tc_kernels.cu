@@ -318,8 +318,8 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   if (cap < 0) cap = env_int("M0_TC_STAGES", 0);   // pipeline-depth experiments
   const int stage_bytes = conv ? tc::CP_A_SLOT + 3 * (w.n_launch / 4) * 128 : (w.n_launch / 4) * 128;
   const int a_res = conv ? 0 : 2 * (cin / 64) * tc::A_TILE_BYTES;   // plain mode keeps two resident A tiles (K <= 320)
-  const bool fz = fuse && (fuse->resid_x || fuse->prims);
-  const int epi_bytes = fz ? tc::CP_EPI_BYTES_FUSE : tc::CP_EPI_BYTES;
+  const int fz = !fuse ? 0 : fuse->resid_x ? 2 : fuse->prims ? 1 : 0;   // tc_conv_pair.cuh FUSE variants
+  const int epi_bytes = fz == 2 ? tc::CP_EPI_BYTES_FUSE : tc::CP_EPI_BYTES;
   int stages = (st->max_smem - 2048 - epi_bytes - a_res) / stage_bytes;
   if (stages > 8) stages = 8;
   if (cap > 0 && stages > cap) stages = cap;
@@ -328,10 +328,11 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   const size_t smem = (size_t)stages * stage_bytes + a_res + epi_bytes + 1024 + 512;
   // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
   const int nch = (w.n_launch + 63) / 64;
-  auto kernel = fz ? (nch <= 2 ? tc::conv_pair_kernel<2, true> : nch <= 5 ? tc::conv_pair_kernel<5, true> : tc::conv_pair_kernel<8, true>)
-                   : (nch <= 2 ? tc::conv_pair_kernel<2, false> : nch <= 5 ? tc::conv_pair_kernel<5, false> : tc::conv_pair_kernel<8, false>);
-  const int kidx = (nch <= 2 ? 0 : nch <= 5 ? 1 : 2) + (fz ? 3 : 0);
-  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  auto kernel = fz == 2 ? (nch <= 2 ? tc::conv_pair_kernel<2, 2> : nch <= 5 ? tc::conv_pair_kernel<5, 2> : tc::conv_pair_kernel<8, 2>)
+                : fz == 1 ? (nch <= 2 ? tc::conv_pair_kernel<2, 1> : nch <= 5 ? tc::conv_pair_kernel<5, 1> : tc::conv_pair_kernel<8, 1>)
+                          : (nch <= 2 ? tc::conv_pair_kernel<2, 0> : nch <= 5 ? tc::conv_pair_kernel<5, 0> : tc::conv_pair_kernel<8, 0>);
+  const int kidx = (nch <= 2 ? 0 : nch <= 5 ? 1 : 2) + 3 * fz;
+  static size_t configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (smem > configured[kidx]) {
     M0_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[kidx] = smem;

@@ -141,8 +141,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// FUSE compiles the SE / residual / half-board-sum epilogues in (kept out of the plain kernels: code size costs instruction fetch)
-template <int NCH, bool FUSE>
+// FUSE compiles the extra epilogues in (kept out of the plain kernels: code size costs instruction fetch):
+//   0 = plain / GroupNorm, 1 = + half-board sums (conv1 of a fused block), 2 = SE gate + residual + next GroupNorm (conv2; 8 KB of
+//   tiles per epilogue warp, which leaves room for 3 pipeline stages instead of 4)
+template <int NCH, int FUSE>
 __global__ void __launch_bounds__(CP_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_out,
                  const __grid_constant__ CUtensorMap tma_x, const ConvPairParams p) {
@@ -159,7 +161,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   smem += 2 * (size_t)a_res_bytes;              // ring base
   const int ns2 = 2 * (p.n_slices > 1 ? p.n_slices : 1);   // work items per group of 4 boards: (slice, channel half)
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  float* s_gamma = epi_stage + 8 * (FUSE ? 2048 : 512);   // [512]
+  float* s_gamma = epi_stage + 8 * (FUSE == 2 ? 2048 : 512);   // [512]
   float* s_beta = s_gamma + 512;          // [512]
   float* s_stats = s_beta + 512;          // [2 accumulators][4 quarters][16 groups][sum, sumsq]
   float* s_gate = s_stats + 256;          // [8 epilogue warps][NCH * 16]
@@ -314,16 +316,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int quarter = warp & 3;
     const int cset = (warp - CP_EPI_WARP0) >> 2;        // the two warps of a lane quarter take alternate 16-column chunks
     // per-warp staging: 2 KB (transposer / two 1 KB output tiles), or 8 KB in the FUSE kernels (two 2 KB residual tiles in, two out)
-    uint8_t* wtile = reinterpret_cast<uint8_t*>(epi_stage) + (size_t)(warp - CP_EPI_WARP0) * (FUSE ? 8192 : 2048);
+    uint8_t* wtile = reinterpret_cast<uint8_t*>(epi_stage) + (size_t)(warp - CP_EPI_WARP0) * (FUSE == 2 ? 8192 : 2048);
     float* stg = reinterpret_cast<float*>(wtile);
     uint8_t* xin = wtile;                          // FUSE: residual tiles by TMA
-    uint8_t* xout = FUSE ? wtile + 4096 : wtile;   // output tiles of the bulk stores
+    uint8_t* xout = FUSE == 2 ? wtile + 4096 : wtile;   // output tiles of the bulk stores
     uint64_t* xbar = x_bar + (warp - CP_EPI_WARP0) * 2;
     uint32_t xuse[2] = {0, 0};                     // completed uses of each residual tile buffer (mbarrier phase)
     float* wgate = s_gate + (warp - CP_EPI_WARP0) * (NCH * 16);   // this warp's SE gates of the current work item
     const bool fused_gn = p.gn_gamma != nullptr;
-    const bool resid = FUSE && p.resid_x != nullptr;
-    const bool want_prims = FUSE && p.prims != nullptr;
+    const bool resid = FUSE == 2 && p.resid_x != nullptr;
+    const bool want_prims = FUSE == 1 && p.prims != nullptr;
     const int epi_tid = ((warp - CP_EPI_WARP0) << 5) | lane;
     const uint32_t lead_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
     const int nchunks = nh >> 4;
@@ -507,7 +509,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               if (!(lane & 1)) p.pool_part[(size_t)(row0 >> 5) * p.N + col + (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0)] = a1;
             }
             if (p.out_half) {
-              uint8_t* tile = xout + (nstore & 1) * (FUSE ? 2048 : 1024);   // two tiles alternate
+              uint8_t* tile = xout + (nstore & 1) * (FUSE == 2 ? 2048 : 1024);   // two tiles alternate
               if (lane == 0) tma_store_wait_read<1>();                                 // the store that last read this tile is done
               __syncwarp();
               uint4 lo, hi;
