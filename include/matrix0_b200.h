@@ -188,7 +188,8 @@ typedef struct m0_net m0_net;
 int m0_net_create(int device, const m0_net_config* cfg, const m0_net_weights* weights, m0_net** out);
 int m0_net_destroy(m0_net* net);
 /* PolicyValueNet.forward (resnet.py:755-760): d_planes float32[B][planes][8][8] -> d_logits float32[B][4672], d_values
- * float32[B].  precision 0 = fp32 SIMT kernels, 1 = bf16 tcgen05 tensor-core pipeline. */
+ * float32[B].  precision 0 = fp32 SIMT kernels (parity <= 1e-4), 1 = bf16 and 2 = fp16 operands on the tcgen05 tensor-core pipeline
+ * (fp32 accumulation; fp16 is the reference's autocast dtype and the default of the Python layer). */
 int m0_net_forward(m0_net* net, const float* d_planes, int B, float* d_logits, float* d_values, int precision, void* stream);
 /* The dominant kernel on its own (tests, roofline micro-benchmark): tcgen05/TMA implicit GEMM over bf16 operands.
  * taps = 9: 3x3 "same" convolution of NHWC activations d_act_bf16[boards][8][8][cin] with d_w_bf16[n][9*cin]

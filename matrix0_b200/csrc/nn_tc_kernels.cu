@@ -1,6 +1,10 @@
-// BF16 tensor-core path of PolicyValueNet.forward: every 3x3 / 1x1 convolution of the trunk runs as the
-// tcgen05 + TMEM + TMA implicit GEMM of tc_gemm.cuh (bf16 operands, fp32 accumulation in tensor memory);
-// normalisation statistics, SE, softmax and the heads stay in fp32.
+// Tensor-core path of PolicyValueNet.forward (precision fp16 = default, or bf16): the 3x3 convolutions of the trunk run on the CTA-pair
+// tcgen05 kernel of tc_conv_pair.cuh, the 1x1 convolutions / linear layers on the single-CTA tcgen05 GEMM of tc_gemm.cuh (16-bit operands,
+// fp32 accumulation in tensor memory); normalisation statistics, the SE gate, softmax and the last value layers stay in fp32.
+// This file owns the per-network device state (16-bit weights, TMA tensor maps, activation buffers) and issues the launches.
+// Environment switches (measurement / A-B comparison): M0_TC_PAIR=0 single-CTA kernel for the 3x3 convolutions, M0_TC_FUSE_SE=0 separate SE /
+// residual kernels instead of the fused conv2 epilogue, M0_TC_PAIR_GEMM=1 pair kernel for the K = 320 GEMMs, M0_TC_CLUSTER / M0_TC_STAGES cluster
+// size / pipeline-depth caps, M0_TC_PROFILE=1 per-launch-site event timing printed at exit.
 #include "net_host.cuh"
 #include "tc_gemm.cuh"
 #include "tc_conv_pair.cuh"
