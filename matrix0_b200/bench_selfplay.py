@@ -86,6 +86,7 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     torch.cuda.synchronize()
     c0 = sp.counters()
     l0 = int(lib.m0_launch_count())
+    r0 = sp.graph_replays
     sampler = ClockSampler(local)
     barrier(world)
     sampler.start()
@@ -99,7 +100,8 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     clocks = sampler.stop()
     total_ms = max_over_ranks(t0.elapsed_time(t1), world)
     c1 = sp.counters()
-    launches = int(lib.m0_launch_count()) - l0
+    # kernels launched one by one + the kernels inside every CUDA-graph replay of the evaluator
+    launches = int(lib.m0_launch_count()) - l0 + (sp.graph_replays - r0) * sp.graph_kernels
     d = {k: c1[k] - c0[k] for k in c1}
     nn_rows = args.steps * G
 

@@ -355,10 +355,36 @@ class PolicyValueNet:
         prec = {"fp32": 0, "bf16": 1, "fp16": 2}[precision or self.precision]
         if B == 0:
             return logits, values
+        if B > getattr(self, "_max_batch", 0):     # the library grows its workspaces: captured graphs of smaller batches are stale
+            self._max_batch = B
+            self._ws_epoch = getattr(self, "_ws_epoch", 0) + 1
         with torch.cuda.device(planes.device):
             _native.check(_native.lib().m0_net_forward(self._handle, planes.data_ptr(), B, logits.data_ptr(), values.data_ptr(), prec,
                                                        _native.current_stream()), "m0_net_forward")
         return logits, values
+
+    def capture_forward(self, planes, precision: Optional[str] = None):
+        """CUDA graph of one forward over a FIXED planes buffer (the ~100 kernel launches of the tensor-core pipeline replay as one
+        graph launch: no per-launch host work and no launch gaps).  Returns ``(graph, logits, values)``; ``graph.replay()`` refreshes
+        the two static output tensors from the current contents of ``planes``.  The capture is stale once ``ws_epoch`` changes
+        (a larger batch made the library reallocate its workspaces)."""
+        import torch
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()
+        with torch.cuda.device(planes.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):              # warm-up outside the capture: workspaces, tensor maps, kernel attributes
+                for _ in range(2):
+                    self.forward_planes(planes, precision)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                logits, values = self.forward_planes(planes, precision)
+        return graph, logits, values
+
+    @property
+    def ws_epoch(self) -> int:
+        return getattr(self, "_ws_epoch", 0)
 
     def forward(self, x, return_ssl: bool = False, visual_input=None):
         """``resnet.py:755-760``: (logits [B,4672], value [B]) or (+ dict of SSL maps [B,k,8,8])."""

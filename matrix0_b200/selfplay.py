@@ -75,7 +75,7 @@ def resolve_mcts_config(cfg_dict: Dict[str, Any]) -> MCTSConfig:
 
 class SelfPlayEngine:
     def __init__(self, model, cfg_dict: Dict[str, Any], games: int = 4096, device: Optional[int] = None, deterministic: bool = False,
-                 seed: int = 1234, precision: Optional[str] = None, max_nodes: int = 4096):
+                 seed: int = 1234, precision: Optional[str] = None, max_nodes: int = 4096, cuda_graph: bool = True):
         import torch
         self.model = model
         self.cfg_dict = cfg_dict
@@ -112,6 +112,10 @@ class SelfPlayEngine:
         self.moves_played = torch.zeros((self.G,), dtype=torch.int16, device=self.device)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed))
+        self.cuda_graph = bool(cuda_graph) and hasattr(model, "capture_forward")   # replay the evaluator's launches as one CUDA graph
+        self._graph = None
+        self.graph_kernels = 0      # kernels inside the captured forward
+        self.graph_replays = 0
         self.nn_evals = 0
         self.nn_rows = 0
         self.moves = 0
@@ -131,6 +135,19 @@ class SelfPlayEngine:
     def _forward(self, planes):
         self.nn_evals += 1
         self.nn_rows += planes.shape[0]
+        if self.cuda_graph and (self.precision or getattr(self.model, "precision", "fp32")) != "fp32":
+            key = (planes.data_ptr(), planes.shape[0], self.model.ws_epoch)
+            if self._graph is None or self._graph[0] != key:
+                lib = _native.lib()
+                g, lg, v = self.model.capture_forward(planes, self.precision)
+                n0 = int(lib.m0_launch_count())
+                self.model.forward_planes(planes, self.precision)          # one eager pass to count the kernels the graph replays
+                self.graph_kernels = int(lib.m0_launch_count()) - n0
+                self._graph = ((planes.data_ptr(), planes.shape[0], self.model.ws_epoch), g, lg, v)
+            _, g, lg, v = self._graph
+            g.replay()
+            self.graph_replays += 1
+            return lg, v
         return self.model.forward_planes(planes, self.precision) if self.precision else self.model.forward_planes(planes)
 
     def begin_move(self) -> None:
