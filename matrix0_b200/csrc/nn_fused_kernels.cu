@@ -327,6 +327,21 @@ int nn_gn_act_res(const float* x, const float* gamma, const float* beta, const f
   gn_act_res_kernel<<<B, C, 0, s>>>(x, gamma, beta, residual, residual_bstride, out, out_half, C, act, nn_half_format());
   return m0_check_launch("gn_act_res");
 }
+// hidden[b][u] = half(act(sum_ks part[ks][b][u] + b1[u])) for u < hid: reduction of the split-K partial sums of the first SE layer
+__global__ void se_hidden_kernel(const float* __restrict__ part, int splits, long long split_stride, const float* __restrict__ b1,
+                                 __nv_bfloat16* __restrict__ hidden, int B, int hid, int ld, int act, int fp16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * hid) return;
+  const int b = i / hid, u = i - b * hid;
+  float a = b1[u];
+  for (int ks = 0; ks < splits; ++ks) a += part[(size_t)ks * split_stride + (size_t)b * ld + u];
+  hidden[(size_t)b * ld + u] = fk_half(fk_act(a, act), fp16);
+}
+int nn_se_hidden(const float* part, int splits, long long split_stride, const float* b1, __nv_bfloat16* hidden, int B, int hid, int ld, int act,
+                 cudaStream_t s) {
+  se_hidden_kernel<<<(B * hid + 255) / 256, 256, 0, s>>>(part, splits, split_stride, b1, hidden, B, hid, ld, act, nn_half_format());
+  return m0_check_launch("se_hidden");
+}
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s) {
   const size_t total = (size_t)B * 64 * 64;
   planes_to_nhwc_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, out, B, P, nn_half_format());

@@ -22,6 +22,8 @@ namespace m0 {
 int nn_se_apply_gn(const __nv_bfloat16* conv_out, const float* gate, float* x, const float* gamma, const float* beta, __nv_bfloat16* a_out, int B,
                    int C, int act, cudaStream_t s);
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s);
+int nn_se_hidden(const float* part, int splits, long long split_stride, const float* b1, __nv_bfloat16* hidden, int B, int hid, int ld, int act,
+                 cudaStream_t s);
 int nn_gn_act_res(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride, float* out,
                   __nv_bfloat16* out_half, int B, int C, int act, cudaStream_t s);
 int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half, int B, int C, int heads, float mix, cudaStream_t s);
@@ -185,6 +187,9 @@ struct TcState {
   bool se_fused = false;
   int hid_pad = 0;
   __nv_bfloat16 *prims = nullptr, *se_hid_h = nullptr;
+  float* se_part = nullptr;     // split-K partial sums of the first SE layer [k_splits][rows][hid_pad]
+  int se_splits = 1;
+  size_t se_rows = 0;
   CUtensorMap prims_mat, se_hid_mat;
   // stem on tensor cores: planes as NHWC half with 64 channels, weights [C][9*64]
   __nv_bfloat16* planes_h = nullptr;
@@ -389,12 +394,19 @@ int pow2_cols(int n) {
 // one launch of the tensor-core GEMM: rows [0, M), output columns [w_row0, w_row0 + N) of the layer
 int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M, int conv, int taps, int cin, int w_row0, int N, float* out_f32,
                 __nv_bfloat16* out_bf16, int ldc, int col0, const float* bias, int act, float scale, cudaStream_t s,
-                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr, int n_store = -1, int n_slices = 1) {
+                const float* gn_gamma = nullptr, const float* gn_beta = nullptr, float* pool_part = nullptr, int n_store = -1, int n_slices = 1,
+                int k_splits = 1, long long split_stride = 0) {
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M;
   p.N = N;
   p.n_slices = n_slices;
+  p.k_splits = k_splits;
+  p.split_stride = split_stride;
+  if (k_splits > 1 && (out_bf16 || bias || act != ACT_NONE || gn_gamma || pool_part || (taps * (cin / 64)) % k_splits != 0 || !out_f32)) {
+    m0_set_error("tensor-core GEMM: split-K needs a plain fp32 output and a K range divisible into whole k-blocks");
+    return M0_ERR_ARG;
+  }
   p.n_store = n_store >= 0 ? n_store : N * n_slices;
   if (w.n_part > N || N % w.n_part != 0) { m0_set_error("tensor-core GEMM: launch width %d does not match the weight map box %d", N, w.n_part); return M0_ERR_ARG; }
   p.n_part = w.n_part;
@@ -436,7 +448,7 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   const int cs = w.cluster;
   const int groups = (tiles + cs - 1) / cs;
   int clusters = st->sm_count / cs;
-  if (clusters > groups * n_slices) clusters = groups * n_slices;
+  if (clusters > groups * n_slices * k_splits) clusters = groups * n_slices * k_splits;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(clusters * cs));
@@ -493,6 +505,8 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   if (st->vh_h) cudaFree(st->vh_h);
   if (st->prims) cudaFree(st->prims);
   if (st->se_hid_h) cudaFree(st->se_hid_h);
+  if (st->se_part) cudaFree(st->se_part);
+  st->se_part = nullptr;
   st->prims = st->se_hid_h = nullptr;
   st->qkv_h = st->ph_h = st->pf_h = st->vh_h = nullptr;
   st->a1 = st->a2 = nullptr;
@@ -522,6 +536,10 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
     M0_CUDA_TRY(cudaMalloc((void**)&st->se_hid_h, rows * st->hid_pad * 2));
     M0_CUDA_TRY(cudaMemset(st->prims, 0, rows * 12 * C * 2));
     M0_CUDA_TRY(cudaMemset(st->se_hid_h, 0, rows * st->hid_pad * 2));
+    const int kblocks = 12 * (int)C / 64;
+    st->se_splits = kblocks % 4 == 0 ? 4 : kblocks % 3 == 0 ? 3 : kblocks % 2 == 0 ? 2 : 1;
+    st->se_rows = rows;
+    M0_CUDA_TRY(cudaMalloc((void**)&st->se_part, (size_t)st->se_splits * rows * st->hid_pad * 4));
     TRY(make_map_2d(&st->prims_mat, st->prims, rows, 12 * C, 128));
     TRY(make_map_2d(&st->se_hid_mat, st->se_hid_h, rows, (uint64_t)st->hid_pad, 128));
   }
@@ -671,6 +689,7 @@ void tc_net_release(::m0_net* n) {
     if (st->vh_h) cudaFree(st->vh_h);
     if (st->prims) cudaFree(st->prims);
     if (st->se_hid_h) cudaFree(st->se_hid_h);
+    if (st->se_part) cudaFree(st->se_part);
     delete st;
   }
   delete all;
@@ -738,7 +757,10 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
       PROF("conv1+gn", conv3x3(st, st->a1_conv, st->a1_convp, tb.conv1, B, C, nullptr, st->a2, act, s, b.gn2_w, b.gn2_b, nullptr, &f1));
       if (c.se) {
         // SE excitation before conv2 runs: hidden = act(fold * sums + b1), gate = sigmoid(W2 hidden + b2)  (resnet.py:61-64)
-        PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, nullptr, st->se_hid_h, st->hid_pad, 0, b.se_b1, act, 1.0f, s));
+        // first layer split over K (60 k-blocks on only B/128 tiles otherwise), partial sums reduced with the bias + activation
+        PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, st->se_part, nullptr, st->hid_pad, 0, none, ACT_NONE, 1.0f, s,
+                                   nullptr, nullptr, nullptr, -1, 1, st->se_splits, (long long)st->se_rows * st->hid_pad));
+        PROF("se_hidden", nn_se_hidden(st->se_part, st->se_splits, (long long)st->se_rows * st->hid_pad, b.se_b1, st->se_hid_h, B, c.se_hidden, st->hid_pad, act, s));
         PROF("se_fc2", launch_gemm(st, st->se_hid_mat, tb.se_w2, B, 0, 1, st->hid_pad, 0, C, st->se_gate, nullptr, C, 0, b.se_b2, ACT_SIGMOID, 1.0f, s));
       }
       // conv2 with the whole block tail in its epilogue: x += gate * conv2 ; a1 = act(GN1_{i+1}(x)) (or half(x) before attention)

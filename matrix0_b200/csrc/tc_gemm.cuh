@@ -185,6 +185,9 @@ struct GemmParams {
   const float* gn_gamma;
   const float* gn_beta;
   float* pool_part;
+  int k_splits;      // >= 1: the K range is cut into k_splits equal parts (whole k-blocks); part ks writes its partial sums to
+                     // out_f32 + ks * split_stride (plain fp32 output only) -- more CTAs for tall-K, few-tile GEMMs
+  long long split_stride;
   int n_slices;      // >= 1: the launch covers n_slices consecutive groups of N output columns (w_row0 / col0 advance by N per slice);
                      // a CTA walks the slices of one M tile back to back, so the A tile is re-read from L2, not from HBM
 };
@@ -240,6 +243,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int n_parts = p.N / p.n_part;
   const int slice_rows = p.n_part / cs;                       // W rows of each part fetched by this CTA for the whole cluster
   const int ns = p.n_slices > 1 ? p.n_slices : 1;
+  const int nk = p.k_splits > 1 ? p.k_splits : 1;          // work item = (group of M tiles, column slice, K part)
+  const int kb_part = kblocks / nk;
   const uint16_t mask = (uint16_t)((1u << cs) - 1u);
 
   if (warp == 0 && lane == 0) {
@@ -268,10 +273,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int gi = cluster_id; gi < num_groups * ns; gi += num_clusters) {
-        const int g = gi / ns, w_row0 = p.w_row0 + (gi - g * ns) * p.N;
+      for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters) {
+        const int ks = gi % nk, gs = gi / nk;
+        const int g = gs / ns, w_row0 = p.w_row0 + (gs - g * ns) * p.N;
         const int m0 = (g * cs + rank) * BM;   // may lie past M for the padding tiles of the last group: TMA zero-fills
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = ks * kb_part; kb < (ks + 1) * kb_part; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
           uint8_t* w_dst = a_dst + A_TILE_BYTES;
@@ -302,10 +308,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     const uint32_t smem_base = smem_u32(smem);
-    for (int gi = cluster_id; gi < num_groups * ns; gi += num_clusters) {
+    for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters) {
       mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the accumulator
       tc_fence_after();
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = 0; kb < kb_part; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
@@ -348,8 +354,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     uint32_t acc_phase = 0;
-    for (int gi = cluster_id; gi < num_groups * ns; gi += num_clusters) {
-      const int g = gi / ns, slice = gi - g * ns;
+    for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters) {
+      const int ks = gi % nk, gs = gi / nk;
+      const int g = gs / ns, slice = gs - g * ns;
+      float* const out_f32 = p.out_f32 ? p.out_f32 + (size_t)ks * p.split_stride : nullptr;
       const int w_row0 = p.w_row0 + slice * p.N, col0 = p.col0 + slice * p.N;
       const int n_store = (p.n_store - slice * p.N) < p.N ? (p.n_store - slice * p.N) : p.N;   // p.n_store counts over all slices
       mbar_wait(tmem_full_bar, acc_phase);
@@ -443,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int i = 0; i < 32; ++i) cs_sum += stg[i * 32 + ((((lane >> 2) ^ (i & 7)) << 2) | (lane & 3))];
           p.pool_part[(size_t)(tile_row0 >> 5) * p.N + c0 + lane] = cs_sum;
         }
-        if (p.out_f32) {
+        if (out_f32) {
           // 8 lanes cover the 128 contiguous bytes of one row: each store instruction writes 4 full lines
           const int q = lane & 7;
 #pragma unroll
@@ -452,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int m = tile_row0 + rr;
             if (m < p.M && 4 * q < ncols) {
               uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((q ^ (rr & 7)) << 2));
-              *reinterpret_cast<uint4*>(p.out_f32 + (size_t)m * p.ldc + col0 + c0 + 4 * q) = v;
+              *reinterpret_cast<uint4*>(out_f32 + (size_t)m * p.ldc + col0 + c0 + 4 * q) = v;
             }
           }
         }

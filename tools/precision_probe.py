@@ -10,7 +10,8 @@ from test_oracle_nn import load_case
 from matrix0_b200.model import PolicyValueNet
 
 g, cfg, sd = load_case(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden"), "r24")
-boards = random_playout_boards(20, 120, seed=31)[::3][:512]
+N = int(os.environ.get("M0_PROBE_POSITIONS", "512"))
+boards = random_playout_boards(max(20, N // 20), 120, seed=31)[::3][:N]
 x = torch.from_numpy(np.stack([encode_board(b) for b in boards]))
 legal = torch.from_numpy(np.stack([get_legal_actions(b) for b in boards])).cuda()
 nets = {p: PolicyValueNet(cfg, device="cuda", precision=p) for p in ("fp32", "bf16", "fp16")}
