@@ -335,12 +335,13 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
   if (stages < 2) { m0_set_error("pair convolution: stage does not fit in shared memory (N=%d)", w.n_launch); return M0_ERR_ARG; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + a_res + epi_bytes + 1024 + 512;
-  // epilogue register tile: 16-column chunks per warp = ceil(N / 64)
-  const int nch = (w.n_launch + 63) / 64;
-  auto kernel = fz == 2 ? (nch <= 2 ? tc::conv_pair_kernel<2, 2> : nch <= 5 ? tc::conv_pair_kernel<5, 2> : tc::conv_pair_kernel<8, 2>)
-                : fz == 1 ? (nch <= 2 ? tc::conv_pair_kernel<2, 1> : nch <= 5 ? tc::conv_pair_kernel<5, 1> : tc::conv_pair_kernel<8, 1>)
-                          : (nch <= 2 ? tc::conv_pair_kernel<2, 0> : nch <= 5 ? tc::conv_pair_kernel<5, 0> : tc::conv_pair_kernel<8, 0>);
-  const int kidx = (nch <= 2 ? 0 : nch <= 5 ? 1 : 2) + 3 * fz;
+  // epilogue register tile: 16-column chunks per warp = ceil((N / 2 / 16) / CP_CSETS)
+  const int nch = (w.n_launch / 32 + tc::CP_CSETS - 1) / tc::CP_CSETS;
+  if (nch > 4) { m0_set_error("pair kernel: N = %d is too wide", w.n_launch); return M0_ERR_ARG; }
+  auto kernel = fz == 2 ? (nch <= 1 ? tc::conv_pair_kernel<1, 2> : nch <= 3 ? tc::conv_pair_kernel<3, 2> : tc::conv_pair_kernel<4, 2>)
+                : fz == 1 ? (nch <= 1 ? tc::conv_pair_kernel<1, 1> : nch <= 3 ? tc::conv_pair_kernel<3, 1> : tc::conv_pair_kernel<4, 1>)
+                          : (nch <= 1 ? tc::conv_pair_kernel<1, 0> : nch <= 3 ? tc::conv_pair_kernel<3, 0> : tc::conv_pair_kernel<4, 0>);
+  const int kidx = (nch <= 1 ? 0 : nch <= 3 ? 1 : 2) + 3 * fz;
   static size_t configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (smem > configured[kidx]) {
     M0_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

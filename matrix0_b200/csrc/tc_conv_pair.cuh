@@ -16,8 +16,9 @@
 //
 // Work item = (group of 4 boards, channel half).  CTA r of the pair owns boards 4t + 2r, 4t + 2r + 1 (TMEM lanes
 // 0..127 of its own tensor memory).  Warp 0 = TMA producer (both CTAs; every load signals the LEADER's full
-// barrier), warp 1 = MMA issuer (leader CTA only) and TMEM allocator, warps 4..11 = epilogue (setmaxnreg gives
-// the two epilogue warpgroups 232 registers per thread so a warp's whole share of the accumulator stays in registers).
+// barrier), warp 1 = MMA issuer (leader CTA only) and TMEM allocator, warps 4..19 = epilogue: four warps per TMEM lane quarter, each
+// holding its share of the accumulator (every fourth 16-column chunk) in registers -- the epilogue is latency bound, and four warps
+// per scheduler hide what two could not (setmaxnreg moves registers from the control warpgroup to the four epilogue warpgroups).
 //
 // Epilogues (an epilogue warp owns 32 rows = half a board and every other 16-column chunk of the work item; one chunk = one
 // GroupNorm group):
@@ -66,12 +67,18 @@ struct ConvPairParams {
   __nv_bfloat16* prims;
 };
 
-static constexpr int CP_THREADS = 384;   // warpgroup 0: TMA producer, MMA issuer, two idle warps; warpgroups 1-2: epilogue
-static constexpr int CP_EPI_WARP0 = 4;
-static constexpr int CP_REGS_CTRL = 40, CP_REGS_EPI = 232;   // setmaxnreg split of the 64K register file (128*40 + 256*232)
+static constexpr int CP_EPI_WARP0 = 4;    // warpgroup 0: TMA producer, MMA issuer, two idle warps
+static constexpr int CP_EPI_WARPS = 16;   // warpgroups 1-4: epilogue, four warps per TMEM lane quarter (the epilogue is latency bound:
+                                          // four warps per scheduler hide what two could not)
+static constexpr int CP_CSETS = CP_EPI_WARPS / 4;   // the warps of a lane quarter take every CP_CSETS-th 16-column chunk
+static constexpr int CP_THREADS = (CP_EPI_WARP0 + CP_EPI_WARPS) * 32;
+// setmaxnreg: the kernel launches with 65536 / 640 -> 96 registers per thread; the control warpgroup gives back 128 * (96 - 40) = 7168,
+// of which the four epilogue warpgroups take 512 * (104 - 96) = 4096.  An increase can only draw on what the CTA's own decrease released
+// (asking for more blocks forever).
+static constexpr int CP_REGS_CTRL = 40, CP_REGS_EPI = 104;
 static constexpr int CP_A_SLOT = 160 * 128;   // 2 boards x 8 y x 10 x rows of 64 channels
-static constexpr int CP_EPI_BYTES = 8 * 32 * 16 * 4 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4 + 8 * 128 * 4;   // transposers + gamma/beta + GN partial sums + SE gates
-static constexpr int CP_EPI_BYTES_FUSE = CP_EPI_BYTES + 8 * 6144;   // FUSE kernels: 8 KB of tiles per epilogue warp instead of 2 KB
+static constexpr int CP_EPI_BYTES = CP_EPI_WARPS * 2048 + 2 * 512 * 4 + 2 * 4 * 16 * 2 * 4 + CP_EPI_WARPS * 64 * 4;   // tiles + gamma/beta + GN sums + SE gates
+static constexpr int CP_EPI_BYTES_FUSE = CP_EPI_BYTES + CP_EPI_WARPS * 2048;   // FUSE = 2: 4 KB of tiles per epilogue warp instead of 2 KB
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -161,18 +168,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   smem += 2 * (size_t)a_res_bytes;              // ring base
   const int ns2 = 2 * (p.n_slices > 1 ? p.n_slices : 1);   // work items per group of 4 boards: (slice, channel half)
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  float* s_gamma = epi_stage + 8 * (FUSE == 2 ? 2048 : 512);   // [512]
+  float* s_gamma = epi_stage + CP_EPI_WARPS * (FUSE == 2 ? 1024 : 512);   // [512]
   float* s_beta = s_gamma + 512;          // [512]
   float* s_stats = s_beta + 512;          // [2 accumulators][4 quarters][16 groups][sum, sumsq]
-  float* s_gate = s_stats + 256;          // [8 epilogue warps][NCH * 16]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_gate + 8 * 128);
+  float* s_gate = s_stats + 256;          // [epilogue warps][NCH * 16 <= 64]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_gate + CP_EPI_WARPS * 64);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], only the leader's are used
   uint64_t* a_full_bar = tmem_empty_bar + 2;        // [2] resident A tile landed (leader's are used)
   uint64_t* a_empty_bar = a_full_bar + 2;           // [2] every MMA reading the resident A tile has completed
-  uint64_t* x_bar = a_empty_bar + 2;                // [8 epilogue warps][2] residual tiles landed (FUSE)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 16);
+  uint64_t* x_bar = a_empty_bar + 2;                // [epilogue warps][2] residual tiles landed (FUSE = 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2 * CP_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -190,11 +197,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 16);   // one arrival per epilogue warp of both CTAs
+      mbar_init(&tmem_empty_bar[b], 2 * CP_EPI_WARPS);   // one arrival per epilogue warp of both CTAs
       mbar_init(&a_full_bar[b], 1);
       mbar_init(&a_empty_bar[b], 1);
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&x_bar[i], 1);
+    for (int i = 0; i < 2 * CP_EPI_WARPS; ++i) mbar_init(&x_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -314,12 +321,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===== epilogue (both CTAs): TMEM -> registers (whole share of the warp, then the accumulator is released at once)
     //       -> GroupNorm / activation in registers -> smem transpose -> coalesced stores, 16 columns at a time =====
     const int quarter = warp & 3;
-    const int cset = (warp - CP_EPI_WARP0) >> 2;        // the two warps of a lane quarter take alternate 16-column chunks
-    // per-warp staging: 2 KB (transposer / two 1 KB output tiles), or 8 KB in the FUSE kernels (two 2 KB residual tiles in, two out)
-    uint8_t* wtile = reinterpret_cast<uint8_t*>(epi_stage) + (size_t)(warp - CP_EPI_WARP0) * (FUSE == 2 ? 8192 : 2048);
+    const int cset = (warp - CP_EPI_WARP0) >> 2;        // the CP_CSETS warps of a lane quarter interleave their 16-column chunks
+    // per-warp staging: 2 KB (transposer / two 1 KB output tiles / one fp32 tile), or 4 KB with FUSE = 2 (two 2 KB residual tiles, updated in
+    // place and stored from where they landed)
+    uint8_t* wtile = reinterpret_cast<uint8_t*>(epi_stage) + (size_t)(warp - CP_EPI_WARP0) * (FUSE == 2 ? 4096 : 2048);
     float* stg = reinterpret_cast<float*>(wtile);
     uint8_t* xin = wtile;                          // FUSE: residual tiles by TMA
-    uint8_t* xout = FUSE == 2 ? wtile + 4096 : wtile;   // output tiles of the bulk stores
+    uint8_t* xout = wtile;                         // output tiles of the bulk stores
     uint64_t* xbar = x_bar + (warp - CP_EPI_WARP0) * 2;
     uint32_t xuse[2] = {0, 0};                     // completed uses of each residual tile buffer (mbarrier phase)
     float* wgate = s_gate + (warp - CP_EPI_WARP0) * (NCH * 16);   // this warp's SE gates of the current work item
@@ -332,8 +340,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int M = p.boards * 64;
     const int act = p.act;
     if (fused_gn) {
-      for (int c = epi_tid; c < p.N; c += 256) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = epi_tid; c < p.N; c += CP_EPI_WARPS * 32) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
+      asm volatile("bar.sync 1, %0;" ::"n"(CP_EPI_WARPS * 32) : "memory");
     }
     uint32_t unit = 0, nstore = 0;   // nstore: bulk stores issued by this warp (selects the output tile buffer)
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -346,16 +354,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         // the accumulator is ready
         if (resid) {
           if (lane == 0) {
+            tma_store_wait_read<0>();      // the tiles of the previous work item have been read by their bulk stores
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              if (k < NCH && cset + 2 * k < nchunks) {
+              if (k < NCH && cset + CP_CSETS * k < nchunks) {
                 mbar_expect_tx(&xbar[k], 2048);
-                tma_load_2d(xin + k * 2048, &tma_x, &xbar[k], cbase + (cset + 2 * k) * 16, row0);
+                tma_load_2d(xin + k * 2048, &tma_x, &xbar[k], cbase + (cset + CP_CSETS * k) * 16, row0);
               }
           }
           if (p.gate) {
             const int bq = row0 >> 6;
-            const int k = lane >> 2, q = lane & 3, ci = cset + 2 * k;
+            const int k = lane >> 2, q = lane & 3, ci = cset + CP_CSETS * k;
             if (k < NCH && ci < nchunks && row0 < M)
               *reinterpret_cast<float4*>(wgate + k * 16 + 4 * q) = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)bq * p.N + h * nh + ci * 16 + 4 * q));
           }
@@ -367,7 +376,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t r[NCH][16];
 #pragma unroll
         for (int k = 0; k < NCH; ++k)
-          if (cset + 2 * k < nchunks) tmem_ld_32x16(tmem_row + (uint32_t)((cset + 2 * k) * 16), r[k]);
+          if (cset + CP_CSETS * k < nchunks) tmem_ld_32x16(tmem_row + (uint32_t)((cset + CP_CSETS * k) * 16), r[k]);
         tmem_ld_wait();
         // the accumulator is free again: the MMAs of the work item after next may overwrite it while this one is stored
         tc_fence_before();
@@ -379,66 +388,45 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int sw = (lane >> 1) & 3;
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            const int ci = cset + 2 * k;
+            const int ci = cset + CP_CSETS * k;
             if (ci >= nchunks) break;
             const int col = cbase + ci * 16;
             const int xb = k & 1;
             mbar_wait(&xbar[xb], (xuse[xb]++) & 1u);
-            const uint8_t* xt = xin + xb * 2048 + lane * 64;
+            uint8_t* xt = xin + xb * 2048 + lane * 64;   // this lane's row: read, updated and written back in place
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 x4 = *reinterpret_cast<const float4*>(xt + ((q ^ sw) << 4));
+              float4* px = reinterpret_cast<float4*>(xt + ((q ^ sw) << 4));
+              const float4 x4 = *px;
               float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
               if (p.gate) g4 = *reinterpret_cast<const float4*>(wgate + k * 16 + 4 * q);
-              r[k][4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 0]), g4.x, x4.x));
-              r[k][4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 1]), g4.y, x4.y));
-              r[k][4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 2]), g4.z, x4.z));
-              r[k][4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(r[k][4 * q + 3]), g4.w, x4.w));
+              const float4 y4 = make_float4(fmaf(__uint_as_float(r[k][4 * q + 0]), g4.x, x4.x), fmaf(__uint_as_float(r[k][4 * q + 1]), g4.y, x4.y),
+                                            fmaf(__uint_as_float(r[k][4 * q + 2]), g4.z, x4.z), fmaf(__uint_as_float(r[k][4 * q + 3]), g4.w, x4.w));
+              *px = y4;
+              r[k][4 * q + 0] = __float_as_uint(y4.x); r[k][4 * q + 1] = __float_as_uint(y4.y);
+              r[k][4 * q + 2] = __float_as_uint(y4.z); r[k][4 * q + 3] = __float_as_uint(y4.w);
             }
-            if (lane == 0) tma_store_wait_read<1>();   // the output tile used two stores ago has been read
-            __syncwarp();                      // every lane has read the x tile (it can take the chunk after next); the output tile is free
-            if (lane == 0 && k + 2 < NCH && ci + 4 < nchunks) {
-              mbar_expect_tx(&xbar[xb], 2048);
-              tma_load_2d(xin + xb * 2048, &tma_x, &xbar[xb], col + 64, row0);
-            }
-            {   // x_new tile -> bulk store
-              uint8_t* tile = xout + (nstore & 1) * 2048;
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ sw) << 4)) = make_uint4(r[k][4 * q], r[k][4 * q + 1], r[k][4 * q + 2], r[k][4 * q + 3]);
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) { tma_store_2d(&tma_x, tile, col, row0); tma_store_commit(); }
-              ++nstore;
-            }
-            if (!fused_gn && p.out_half) {   // the attention qkv GEMM takes the raw residual stream in half precision
-              uint8_t* tile = xout + (nstore & 1) * 2048;
-              if (lane == 0) tma_store_wait_read<1>();
-              __syncwarp();
-              uint4 lo, hi;
-              lo.x = pack_half2(__uint_as_float(r[k][0]), __uint_as_float(r[k][1]), p.fp16);
-              lo.y = pack_half2(__uint_as_float(r[k][2]), __uint_as_float(r[k][3]), p.fp16);
-              lo.z = pack_half2(__uint_as_float(r[k][4]), __uint_as_float(r[k][5]), p.fp16);
-              lo.w = pack_half2(__uint_as_float(r[k][6]), __uint_as_float(r[k][7]), p.fp16);
-              hi.x = pack_half2(__uint_as_float(r[k][8]), __uint_as_float(r[k][9]), p.fp16);
-              hi.y = pack_half2(__uint_as_float(r[k][10]), __uint_as_float(r[k][11]), p.fp16);
-              hi.z = pack_half2(__uint_as_float(r[k][12]), __uint_as_float(r[k][13]), p.fp16);
-              hi.w = pack_half2(__uint_as_float(r[k][14]), __uint_as_float(r[k][15]), p.fp16);
-              *reinterpret_cast<uint4*>(tile + lane * 32) = lo;
-              *reinterpret_cast<uint4*>(tile + lane * 32 + 16) = hi;
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) { tma_store_2d(&tma_out, tile, col, row0); tma_store_commit(); }
-              ++nstore;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tma_x, xin + xb * 2048, col, row0);
+              tma_store_commit();
+              if (k + 2 < NCH && ci + 2 * CP_CSETS < nchunks) {   // refill this buffer with the chunk after next once the store has read it
+                tma_store_wait_read<0>();
+                mbar_expect_tx(&xbar[xb], 2048);
+                tma_load_2d(xin + xb * 2048, &tma_x, &xbar[xb], col + 2 * CP_CSETS * 16, row0);
+              }
             }
           }
-          if (!fused_gn) continue;
+          if (!fused_gn && !p.out_half) continue;   // (half(x_new) for the attention qkv GEMM goes out through the tile loop below)
+          if (lane == 0) tma_store_wait_read<0>();  // the residual tiles double as output tiles from here on
+          __syncwarp();
         }
         if (fused_gn) {
           // per (half board = this warp, group of 16 channels = one chunk) sum and sum of squares
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            if (cset + 2 * k < nchunks) {
+            if (cset + CP_CSETS * k < nchunks) {
               float s0 = 0.f, q0 = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -451,16 +439,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, off);
                 q0 += __shfl_xor_sync(0xFFFFFFFFu, q0, off);
               }
-              if (lane == 0) *reinterpret_cast<float2*>(stats + (quarter * 16 + cset + 2 * k) * 2) = make_float2(s0, q0);
+              if (lane == 0) *reinterpret_cast<float2*>(stats + (quarter * 16 + cset + CP_CSETS * k) * 2) = make_float2(s0, q0);
             }
           }
-          // the four warps that hold one board exchange their partial sums
-          if (quarter < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
-          else asm volatile("bar.sync 3, 128;" ::: "memory");
+          // the warps that hold one board (two lane quarters x CP_CSETS) exchange their partial sums
+          if (quarter < 2) asm volatile("bar.sync 2, %0;" ::"n"(CP_EPI_WARPS * 16) : "memory");
+          else asm volatile("bar.sync 3, %0;" ::"n"(CP_EPI_WARPS * 16) : "memory");
         }
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-          const int ci = cset + 2 * k;
+          const int ci = cset + CP_CSETS * k;
           if (ci >= nchunks) break;
           const int col = cbase + ci * 16;
           if (fused_gn) {
