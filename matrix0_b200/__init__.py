@@ -4,6 +4,7 @@ Drop-in surface (mirrors the reference modules named in SURVEY.md section 8b):
   matrix0_b200.encoding  <->  azchess/encoding.py   (encode_board, move_to_index, MoveEncoder ...)
   matrix0_b200.mcts      <->  azchess/mcts.py       (MCTS, MCTSConfig)
   matrix0_b200.model     <->  azchess/model/resnet.py inference forward (PolicyValueNet evaluator)
+  matrix0_b200.inference <->  azchess/selfplay/inference.py (shared-memory evaluation server + client)
   matrix0_b200.selfplay  <->  azchess/selfplay/      (selfplay_worker, batched device self-play)
 
 All compute runs in hand-written sm_100a CUDA kernels reached through the C ABI declared in
