@@ -339,17 +339,19 @@ M0_HD bool attacked_for_king(const Position& p, int us, u64 path, u64 occ) {
   return false;
 }
 
-// chess.Board.generate_castling_moves (standard chess; emitted as king e1g1 / e1c1)
-M0_HD void gen_castling(MoveGenCtx& c, u64 from_mask, u64 to_mask) {
-  const Position& p = *c.p;
-  u64 backrank = c.us ? RANK_1 : RANK_8;
-  u64 king = c.ours & p.kings & backrank & from_mask;
+// chess.Board.generate_castling_moves (standard chess; king e1g1 / e1c1), h-side before a-side.
+// Writes the king square and up to two destination squares; returns the number of castling moves.
+M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_mask, u64 to_mask, int* ksq_out, int* to_out) {
+  u64 backrank = us ? RANK_1 : RANK_8;
+  u64 king = ours & p.kings & backrank & from_mask;
   king &= (0 - king);
-  if (!king) return;
+  if (!king) return 0;
   int ksq = msb(king);
+  *ksq_out = ksq;
   u64 bb_c = (FILE_A << 2) & backrank, bb_d = (FILE_A << 3) & backrank;
   u64 bb_f = (FILE_A << 5) & backrank, bb_g = (FILE_A << 6) & backrank;
   u64 cand = castling_rook_mask(pos_castling(p)) & backrank & to_mask;
+  int n = 0;
   while (cand) {
     int rs = msb(cand);
     cand ^= sq_bb(rs);
@@ -359,18 +361,25 @@ M0_HD void gen_castling(MoveGenCtx& c, u64 from_mask, u64 to_mask) {
     u64 rook_to = a_side ? bb_d : bb_f;
     u64 king_path = between_bb(ksq, msb(king_to));
     u64 rook_path = between_bb(rs, msb(rook_to));
-    if (!(((c.occ ^ king ^ rook) & (king_path | rook_path | king_to | rook_to)) ||
-          attacked_for_king(p, c.us, king_path | king, c.occ ^ king) ||
-          attacked_for_king(p, c.us, king_to, c.occ ^ king ^ rook ^ rook_to))) {
+    if (!(((occ ^ king ^ rook) & (king_path | rook_path | king_to | rook_to)) ||
+          attacked_for_king(p, us, king_path | king, occ ^ king) ||
+          attacked_for_king(p, us, king_to, occ ^ king ^ rook ^ rook_to))) {
       // _from_chess960: e1->h1 becomes e1g1, e1->a1 becomes e1c1 (king on e-file in standard chess)
       int to = rs;
       if (ksq == SQ_E1 && rs == SQ_H1) to = SQ_G1;
       else if (ksq == SQ_E1 && rs == SQ_A1) to = SQ_C1;
       else if (ksq == SQ_E8 && rs == SQ_H8) to = SQ_G8;
       else if (ksq == SQ_E8 && rs == SQ_A8) to = SQ_C8;
-      emit(c, ksq, to, 0, true, false);
+      if (n < 2) to_out[n] = to;
+      n++;
     }
   }
+  return n < 2 ? n : 2;
+}
+M0_HD void gen_castling(MoveGenCtx& c, u64 from_mask, u64 to_mask) {
+  int ksq = 0, to[2];
+  int n = castling_moves(*c.p, c.us, c.occ, c.ours, from_mask, to_mask, &ksq, to);
+  for (int i = 0; i < n; ++i) emit(c, ksq, to[i], 0, true, false);
 }
 
 // chess.Board.generate_pseudo_legal_moves with the _is_safe filter applied at emission
@@ -479,6 +488,100 @@ M0_HD int generate_legal_moves(const Position& p, Move* out, u64* checkers_out =
   }
   if (checkers_out) *checkers_out = checkers;
   return c.n;
+}
+
+// ---- the legal moves as a SET (no order): the same moves as generate_legal_moves, organised per piece so that
+// the lanes of a warp can each take one piece of a position (encode_kernels.cu, legal-mask path).  The ordered
+// generator above stays the definition; tests/hostcheck and the GPU tests compare the two on every position.
+struct LegalCtx {
+  int us, king;             // king = msb(kings & ours) or -1
+  u64 occ, ours, theirs;
+  u64 blockers;             // _slider_blockers(king)
+  u64 checkers;
+  u64 to_mask;              // targets of non-king pieces: all squares, or between(king, checker) | checker in single check
+  u64 king_cand;            // king destinations BEFORE the attacked-square test (evasions exclude the checking rays)
+  bool others_move;         // false in double check
+  bool ep_open;             // an en-passant capture is generated at all (ep square set, empty, and admitted by the evasion rule)
+  int ep;
+};
+M0_HD LegalCtx make_legal_ctx(const Position& p) {
+  LegalCtx c;
+  c.us = pos_turn(p);
+  c.occ = pos_occ(p);
+  c.ours = pos_us(p);
+  c.theirs = pos_them(p);
+  c.blockers = 0;
+  c.checkers = 0;
+  c.to_mask = BB_ALL;
+  c.king_cand = 0;
+  c.others_move = true;
+  c.ep = pos_ep(p);
+  c.ep_open = c.ep != EP_NONE && c.ep != 0 && !(sq_bb(c.ep) & c.occ);
+  u64 king_mask = p.kings & c.ours;
+  c.king = king_mask ? msb(king_mask) : -1;
+  if (c.king < 0) return c;
+  c.blockers = slider_blockers(p, c.king, c.occ, c.ours, c.theirs);
+  c.checkers = attackers_of(p, !c.us, c.king, c.occ);
+  c.king_cand = king_attacks_bb(sq_bb(c.king)) & ~c.ours;
+  if (c.checkers) {
+    u64 sliders = c.checkers & (p.bishops | p.rooks | p.queens);
+    while (sliders) {
+      int ch = msb(sliders);
+      sliders ^= sq_bb(ch);
+      c.king_cand &= ~(ray_through(c.king, ch) & ~sq_bb(ch));
+    }
+    if (c.checkers & (c.checkers - 1)) {
+      c.others_move = false;
+      c.to_mask = 0;
+      c.ep_open = false;
+    } else {
+      int checker = msb(c.checkers);
+      c.to_mask = between_bb(c.king, checker) | c.checkers;
+      if (c.ep_open && !(sq_bb(c.ep) & c.to_mask) && (c.ep + (c.us ? -8 : 8)) != checker) c.ep_open = false;
+    }
+  }
+  return c;
+}
+// THE king may step to `to` (a bit of c.king_cand)
+M0_HD bool king_step_safe(const Position& p, const LegalCtx& c, int to) { return attackers_of(p, !c.us, to, c.occ) == 0; }
+// Destinations of the own piece on `from`, without castling, en passant and the steps of THE king (c.king).
+// For a pawn the set holds captures and pushes; a destination on the first / last rank stands for four promotions.
+M0_HD u64 piece_targets(const Position& p, const LegalCtx& c, int from) {
+  u64 fb = sq_bb(from);
+  if (from == c.king || !c.others_move) return 0;
+  if (c.checkers && (p.kings & fb)) return 0;          // evasions are generated with from_mask = ~kings
+  u64 t;
+  if (p.pawns & fb) {
+    u64 single = (c.us ? (fb << 8) : (fb >> 8)) & ~c.occ;
+    u64 dbl = (c.us ? (single << 8) : (single >> 8)) & ~c.occ & (c.us ? (RANK_3 | RANK_4) : (RANK_6 | RANK_5));
+    t = ((pawn_attacks_bb(c.us, fb) & c.theirs) | single | dbl) & c.to_mask;
+  } else {
+    t = attacks_from(p, from) & ~c.ours & c.to_mask;
+  }
+  if (c.king >= 0 && (c.blockers & fb)) t &= ray_through(from, c.king);   // _is_safe for a pinned piece
+  return t;
+}
+// the pawn on `from` may capture en passant
+M0_HD bool ep_capture_legal(const Position& p, const LegalCtx& c, int from) {
+  if (!c.ep_open) return false;
+  u64 capturers = p.pawns & c.ours & pawn_attacks_bb(!c.us, sq_bb(c.ep)) & (c.us ? RANK_5 : RANK_4);
+  if (!(capturers & sq_bb(from))) return false;
+  if (c.king < 0) return true;
+  return (pin_mask_for(p, c.king, from, c.occ, c.theirs) & sq_bb(c.ep)) != 0 &&
+         !ep_skewered(p, c.us, c.king, from, c.ep, c.occ, c.theirs);
+}
+// castling moves of the position (king square, up to two destinations); _is_safe passes them for THE king and applies
+// the pinned-piece rule to any other own king (boards with several kings)
+M0_HD int legal_castling(const Position& p, const LegalCtx& c, int* ksq_out, int* to_out) {
+  if (c.checkers) return 0;
+  int to[2];
+  int n = castling_moves(p, c.us, c.occ, c.ours, BB_ALL, BB_ALL, ksq_out, to), m = 0;
+  for (int i = 0; i < n; ++i) {
+    int ksq = *ksq_out;
+    bool ok = c.king < 0 || ksq == c.king || !(c.blockers & sq_bb(ksq)) || (ray_through(ksq, to[i]) & sq_bb(c.king)) != 0;
+    if (ok) to_out[m++] = to[i];
+  }
+  return m;
 }
 
 // chess.Board.has_legal_en_passant (used by the transposition key and is_irreversible):

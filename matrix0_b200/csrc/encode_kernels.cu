@@ -9,7 +9,13 @@
 // coalesced 8-byte loads, every thread then runs the ordered legal-move generator on one position
 // (integer ALU work, hidden under the stores of the other resident blocks), and the warps write
 // the outputs cooperatively with 16-byte vector stores so that every store instruction covers
-// 512 contiguous bytes.
+// 512 contiguous bytes.  That kernel (encode_positions_kernel) serves every call that wants the ORDERED
+// move / index lists.  Planes and mask alone -- the microbenchmark and encode_boards() -- go through
+// encode_mask_planes_kernel: a half warp per position, one own piece per lane (the legal moves as a set,
+// chess_core.cuh LegalCtx), the mask row assembled as 4,672 bits in shared memory and expanded to bytes on
+// the way out, so that the 32 lanes of a warp no longer wait for the slowest of 32 unrelated move lists
+// (ncu of the thread-per-position kernel: 1.3 k issued warp instructions per position at 25 % occupancy,
+// issue-bound at 58 % of the HBM roofline).
 #include "chess_core.cuh"
 #include "m0_common.cuh"
 
@@ -122,6 +128,121 @@ encode_positions_kernel(const u64* __restrict__ pos, int n, float* __restrict__ 
   }
 }
 
+
+// ---- planes + mask, half warp per position ----------------------------------------------------------
+static constexpr int ENCW_THREADS = 128;                   // 8 half warps
+static constexpr int ENCW_HALVES = ENCW_THREADS / 16;
+static constexpr int ENCW_POS_PER_HALF = 8;
+static constexpr int ENCW_POS_PER_BLOCK = ENCW_HALVES * ENCW_POS_PER_HALF;
+static constexpr int MASK_BIT_WORDS = 148;                 // 4,672 bits = 146 words, padded to 37 x 16 bytes
+static constexpr int MASK_CHUNKS = POLICY_SIZE / 16;       // 292 16-byte chunks per mask row
+
+// policy index of (from, to) without under-promotion: encoding.py:113-150 is a pure function of the two squares then
+// (a queen promotion shares the slot of the plain move).  Filled once per device by build_move_index_tab_kernel.
+__device__ u16 g_move_index_tab[64 * 64];
+
+__global__ void build_move_index_tab_kernel() {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  int from = i >> 6, to = i & 63;
+  int v = from == to ? -1 : policy_index(make_move(from, to, 0), 1);
+  g_move_index_tab[i] = v < 0 ? (u16)0xFFFF : (u16)v;
+}
+
+__device__ __forceinline__ void st_global_cs_u4(uint4* ptr, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// four mask bits -> four bytes of 0 / 1
+__device__ __forceinline__ u32 spread4(u32 nibble) { return (nibble * 0x00204081u) & 0x01010101u; }
+// j-th set bit of b (j < popcount)
+__device__ __forceinline__ int nth_set_bit(u64 b, int j) {
+  for (int i = 0; i < j; ++i) b &= b - 1;
+  return lsb(b);
+}
+__device__ __forceinline__ void set_mask_bit(u32* bits, int idx) { atomicOr(bits + (idx >> 5), 1u << (idx & 31)); }
+
+// 16 lanes write the 19x8x8 float32 planes of one position: 16 float4 chunks per plane, one per lane
+__device__ __forceinline__ void half_write_planes(const Position& p, float* __restrict__ out, int hl) {
+  float4* o4 = reinterpret_cast<float4*>(out) + hl;
+  const int sh = (7 - (hl >> 1)) * 8 + (hl & 1) * 4;       // row = 7 - rank (encoding.py:43-45), four files per chunk
+#pragma unroll
+  for (int plane = 0; plane < 12; ++plane) {
+    u32 bits = (u32)(piece_plane_bb(p, plane) >> sh) & 15u;
+    st_global_cs_f4(o4 + plane * 16, make_float4((bits & 1) ? 1.0f : 0.0f, (bits & 2) ? 1.0f : 0.0f,
+                                                 (bits & 4) ? 1.0f : 0.0f, (bits & 8) ? 1.0f : 0.0f));
+  }
+#pragma unroll
+  for (int plane = 12; plane < 19; ++plane) {
+    float f = const_plane_value(p, plane);
+    st_global_cs_f4(o4 + plane * 16, make_float4(f, f, f, f));
+  }
+}
+
+__global__ void __launch_bounds__(ENCW_THREADS)
+encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict__ planes, u8* __restrict__ mask) {
+  __shared__ __align__(16) u16 s_tab[64 * 64];
+  __shared__ __align__(16) u32 s_bits[ENCW_HALVES][MASK_BIT_WORDS];
+  const int tid = threadIdx.x, hl = tid & 15, half = tid >> 4;
+  const unsigned hmask = 0xFFFFu << (tid & 16);            // the 16 lanes that share a position
+  if (mask) {
+    const uint4* src = reinterpret_cast<const uint4*>(g_move_index_tab);
+    uint4* dst = reinterpret_cast<uint4*>(s_tab);
+    for (int i = tid; i < 64 * 64 * 2 / 16; i += ENCW_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  u32* bits = s_bits[half];
+  for (int k = 0; k < ENCW_POS_PER_HALF; ++k) {
+    const int t = blockIdx.x * ENCW_POS_PER_BLOCK + k * ENCW_HALVES + half;
+    if (t >= n) break;                                     // uniform within the half warp
+    const u64* w = pos + (size_t)t * POSITION_WORDS;       // 72 bytes, broadcast loads
+    Position p;
+    p.pawns = ld_global_nc_u64(w + 0); p.knights = ld_global_nc_u64(w + 1); p.bishops = ld_global_nc_u64(w + 2);
+    p.rooks = ld_global_nc_u64(w + 3); p.queens = ld_global_nc_u64(w + 4); p.kings = ld_global_nc_u64(w + 5);
+    p.occ_w = ld_global_nc_u64(w + 6); p.occ_b = ld_global_nc_u64(w + 7); p.state = ld_global_nc_u64(w + 8);
+    if (planes) half_write_planes(p, planes + (size_t)t * (19 * 64), hl);
+    if (!mask) continue;
+
+    for (int i = hl; i < MASK_BIT_WORDS / 4; i += 16) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp(hmask);
+    const LegalCtx c = make_legal_ctx(p);                  // the same for the 16 lanes
+    // steps of the king: one candidate square per lane (at most 8)
+    if (hl < popcnt(c.king_cand)) {
+      int to = nth_set_bit(c.king_cand, hl);
+      if (king_step_safe(p, c, to)) set_mask_bit(bits, s_tab[c.king * 64 + to]);
+    }
+    // every other own piece: lane hl takes pieces hl, hl + 16, ...
+    const int pieces = popcnt(c.ours);
+    for (int j = hl; j < pieces; j += 16) {
+      const int from = nth_set_bit(c.ours, j);
+      const bool pawn = (p.pawns >> from) & 1;
+      u64 tg = piece_targets(p, c, from);
+      while (tg) {
+        int to = lsb(tg);
+        tg &= tg - 1;
+        set_mask_bit(bits, s_tab[from * 64 + to]);
+        if (pawn && ((to >> 3) == 0 || (to >> 3) == 7)) {  // + the three under-promotions (the queen shares the plain slot)
+          for (int pr = PT_KNIGHT; pr <= PT_ROOK; ++pr) set_mask_bit(bits, policy_index(make_move(from, to, pr), c.us));
+        }
+      }
+      if (pawn && ep_capture_legal(p, c, from)) set_mask_bit(bits, s_tab[from * 64 + c.ep]);
+    }
+    if (hl == 15 && !c.checkers) {                         // castling: the lane least likely to hold a piece
+      int ksq = 0, to[2];
+      int nc = legal_castling(p, c, &ksq, to);
+      for (int i = 0; i < nc; ++i) set_mask_bit(bits, s_tab[ksq * 64 + to[i]]);
+    }
+    __syncwarp(hmask);
+    // bits -> bytes: every lane expands 16 bits into one 16-byte store, 256 contiguous bytes per half warp and step
+    uint4* row = reinterpret_cast<uint4*>(mask + (size_t)t * POLICY_SIZE);
+    const u16* b16 = reinterpret_cast<const u16*>(bits);
+    for (int i = hl; i < MASK_CHUNKS; i += 16) {
+      u32 v = b16[i];
+      st_global_cs_u4(row + i, make_uint4(spread4(v & 15u), spread4((v >> 4) & 15u), spread4((v >> 8) & 15u), spread4(v >> 12)));
+    }
+    __syncwarp(hmask);
+  }
+}
+
 }  // namespace m0
 
 using namespace m0;
@@ -144,6 +265,23 @@ int m0_random_playouts(uint64_t* d_pos, int n, uint64_t seed, int max_plies, voi
 int m0_encode_positions(const uint64_t* d_pos, int n, float* d_planes, uint8_t* d_mask, uint16_t* d_moves,
                         uint16_t* d_idx, int32_t* d_counts, void* stream) {
   if (n <= 0) return 0;
+  if (!d_moves && !d_idx && !d_counts) {                   // planes and / or mask only: the half-warp-per-position kernel
+    if (!d_planes && !d_mask) return 0;
+    if (d_mask) {
+      static bool tab_ready[64] = {};
+      int dev = 0;
+      M0_CUDA_TRY(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !tab_ready[dev]) {       // stream-ordered before the first use on this device
+        build_move_index_tab_kernel<<<16, 256, 0, (cudaStream_t)stream>>>();
+        int rc = m0_check_launch("build_move_index_tab_kernel");
+        if (rc != 0) return rc;
+        if (dev >= 0 && dev < 64) tab_ready[dev] = true;
+      }
+    }
+    int blocks = (n + ENCW_POS_PER_BLOCK - 1) / ENCW_POS_PER_BLOCK;
+    encode_mask_planes_kernel<<<blocks, ENCW_THREADS, 0, (cudaStream_t)stream>>>(d_pos, n, d_planes, d_mask);
+    return m0_check_launch("m0_encode_positions");
+  }
   int blocks = (n + ENC_THREADS - 1) / ENC_THREADS;
   encode_positions_kernel<<<blocks, ENC_THREADS, 0, (cudaStream_t)stream>>>(d_pos, n, d_planes, d_mask, d_moves, d_idx, d_counts);
   return m0_check_launch("m0_encode_positions");

@@ -68,3 +68,78 @@ void hc_ssl(const uint64_t* pos9, float* out) {
   }
 }
 }
+
+// legal mask through the per-piece SET interface (what the warp-cooperative encode kernel evaluates, one piece per lane)
+static int legal_set_mask(const Position& p, uint8_t* mask) {
+  memset(mask, 0, POLICY_SIZE);
+  LegalCtx c = make_legal_ctx(p);
+  int wtm = pos_turn(p), n = 0;
+  u64 own = c.ours;
+  while (own) {
+    int from = lsb(own);
+    own &= own - 1;
+    if (from == c.king) {
+      u64 t = c.king_cand;
+      while (t) {
+        int to = lsb(t);
+        t &= t - 1;
+        if (king_step_safe(p, c, to)) { mask[policy_index(make_move(from, to, 0), wtm)] = 1; n++; }
+      }
+      continue;
+    }
+    u64 t = piece_targets(p, c, from);
+    bool pawn = (p.pawns >> from) & 1;
+    while (t) {
+      int to = lsb(t);
+      t &= t - 1;
+      if (pawn && ((to >> 3) == 0 || (to >> 3) == 7)) {
+        for (int pr = PT_KNIGHT; pr <= PT_QUEEN; ++pr) { mask[policy_index(make_move(from, to, pr), wtm)] = 1; n++; }
+      } else {
+        mask[policy_index(make_move(from, to, 0), wtm)] = 1; n++;
+      }
+    }
+    if (pawn && ep_capture_legal(p, c, from)) { mask[policy_index(make_move(from, c.ep, 0), wtm)] = 1; n++; }
+  }
+  int ksq = 0, to[2];
+  int nc = legal_castling(p, c, &ksq, to);
+  for (int i = 0; i < nc; ++i) { mask[policy_index(make_move(ksq, to[i], 0), wtm)] = 1; n++; }
+  return n;
+}
+static int ordered_mask(const Position& p, uint8_t* mask) {
+  memset(mask, 0, POLICY_SIZE);
+  Move mv[MAX_MOVES];
+  int n = generate_legal_moves(p, mv);
+  int m = n < MAX_MOVES ? n : MAX_MOVES;
+  for (int i = 0; i < m; ++i) mask[policy_index(mv[i], pos_turn(p))] = 1;
+  return n;
+}
+extern "C" {
+// 0 when the SET interface gives the same move count and mask as the ordered generator
+int hc_legal_set_differs(const uint64_t* pos9) {
+  static uint8_t a[POLICY_SIZE], b[POLICY_SIZE];
+  Position p = load(pos9);
+  int na = legal_set_mask(p, a), nb = ordered_mask(p, b);
+  return (na != nb) || memcmp(a, b, POLICY_SIZE) != 0;
+}
+// random playouts from `start9`: returns the number of positions visited, *bad = positions where the two disagree
+long hc_legal_set_sweep(const uint64_t* start9, uint64_t seed, int games, int max_plies, long* bad, uint64_t* first_bad9) {
+  static uint8_t a[POLICY_SIZE], b[POLICY_SIZE];
+  long seen = 0;
+  *bad = 0;
+  u64 rng = seed;
+  for (int g = 0; g < games; ++g) {
+    Position p = load(start9);
+    for (int ply = 0; ply < max_plies; ++ply) {
+      int na = legal_set_mask(p, a), nb = ordered_mask(p, b);
+      seen++;
+      if (na != nb || memcmp(a, b, POLICY_SIZE) != 0) { if (!*bad) store(p, first_bad9); (*bad)++; }
+      Move mv[MAX_MOVES];
+      int n = generate_legal_moves(p, mv);
+      if (n == 0 || is_insufficient_material(p) || pos_halfmove(p) >= 150) break;
+      rng = mix64(rng + 0x9E3779B97F4A7C15ull);
+      push_move(p, mv[(int)(rng % (u64)n)]);
+    }
+  }
+  return seen;
+}
+}

@@ -91,3 +91,40 @@ def test_ssl_core_matches_reference_goldens(hc, golden_dir):
         assert np.array_equal(out[14], g["pin"][i]), fen
         assert np.array_equal(out[15], g["fork"][i]), fen
         assert np.array_equal(out[16], g["control"][i]), fen
+
+
+WEIRD_FENS = [
+    "8/8/8/3pP3/8/8/8/8 w - d6 0 2",                                   # kingless, en passant
+    "8/8/8/8/k2Pp2Q/8/8/3K4 b - d3 0 1",                               # en passant skewered along the rank
+    "4k3/8/8/8/8/8/8/R3K2R w KQkq - 0 1",                              # dirty castling rights
+    "R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - - 0 1",            # 218 moves
+    "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1",   # Kiwipete
+    "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1",
+    "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1",
+    "rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8",
+    "4k3/8/8/8/8/8/4r3/R3K2R w KQ - 0 1",                              # castling while in check
+    "4k3/8/8/8/8/8/5r2/R3K2R w KQ - 0 1",                              # castling through an attacked square
+    "8/8/8/2k5/3Pp3/8/8/4K2B b - d3 0 1",                              # en passant removes the checker
+    "8/8/3k4/8/3Pp3/8/8/3RK3 b - d3 0 1",                              # pinned en passant capturer
+    "k7/8/8/8/8/8/8/K6K w - - 0 1", "kk6/8/8/8/8/8/8/KR5K w - - 0 1",  # several kings of one colour
+    "4k3/P6P/8/8/8/8/p6p/4K3 w - - 0 1", "4k3/P6P/8/8/8/8/p6p/4K3 b - - 0 1",   # promotions
+    "3rk3/8/8/8/8/8/3B4/3K4 w - - 0 1", "4k3/8/8/8/7b/8/5P2/4K3 w - - 0 1",     # pins
+    "4k3/8/8/8/8/5n2/8/4K2r w - - 0 1",                                # double check
+]
+
+
+def test_legal_set_equals_ordered_generator(hc):
+    """The per-piece SET interface of chess_core.cuh (the warp-cooperative mask path of the encode kernel) yields exactly
+    the moves of the ordered generator: constructed edge positions, oracle playouts, and a 300 k-position C++ sweep."""
+    boards = [chess.Board(f) for f in WEIRD_FENS] + random_playout_boards(30, 200, seed=77)
+    for b in boards:
+        assert hc.hc_legal_set_differs(pack(hc, b).ctypes.data_as(U64P)) == 0, b.fen()
+    hc.hc_legal_set_sweep.restype = ctypes.c_long
+    bad = ctypes.c_long(0)
+    first = np.zeros(9, dtype=np.uint64)
+    seen = 0
+    for i, f in enumerate([chess.STARTING_FEN, WEIRD_FENS[4], WEIRD_FENS[6], WEIRD_FENS[7], WEIRD_FENS[14]]):
+        seen += hc.hc_legal_set_sweep(pack(hc, chess.Board(f)).ctypes.data_as(U64P), ctypes.c_uint64(1000 + i), 600, 300,
+                                      ctypes.byref(bad), first.ctypes.data_as(U64P))
+        assert bad.value == 0, (f, [hex(int(x)) for x in first])
+    assert seen > 300_000
