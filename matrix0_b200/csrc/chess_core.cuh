@@ -150,6 +150,9 @@ M0_HD u64 diag_attacks(int sq, u64 occ) {
   u64 s = sq_bb(sq);
   return line_attacks(occ, diag_mask(sq), s) | line_attacks(occ, anti_mask(sq), s);
 }
+// rays on an empty board: line_attacks(0, mask, s) == mask & ~s
+M0_HD u64 rook_rays_empty(int sq) { return (rank_mask(sq) | file_mask(sq)) & ~sq_bb(sq); }
+M0_HD u64 bishop_rays_empty(int sq) { return (diag_mask(sq) | anti_mask(sq)) & ~sq_bb(sq); }
 M0_HD u64 knight_attacks_bb(u64 b) {
   return ((b << 17) & ~FILE_A) | ((b << 15) & ~FILE_H) | ((b << 10) & ~(FILE_A | FILE_B)) |
          ((b << 6) & ~(FILE_G | FILE_H)) | ((b >> 17) & ~FILE_H) | ((b >> 15) & ~FILE_A) |
@@ -244,7 +247,7 @@ struct MoveGenCtx {
 // chess.Board._slider_blockers
 M0_HD u64 slider_blockers(const Position& p, int king, u64 occ, u64 ours, u64 theirs) {
   u64 rq = p.rooks | p.queens, bq = p.bishops | p.queens;
-  u64 snipers = ((rank_attacks(king, 0) | file_attacks(king, 0)) & rq) | (diag_attacks(king, 0) & bq);
+  u64 snipers = (rook_rays_empty(king) & rq) | (bishop_rays_empty(king) & bq);
   u64 blockers = 0;
   u64 s = snipers & theirs;
   while (s) {
@@ -261,7 +264,7 @@ M0_HD u64 pin_mask_for(const Position& p, int king, int sq, u64 occ, u64 theirs)
   u64 sm = sq_bb(sq);
   u64 rq = p.rooks | p.queens, bq = p.bishops | p.queens;
   for (int k = 0; k < 3; ++k) {
-    u64 rays = k == 0 ? file_attacks(king, 0) : (k == 1 ? rank_attacks(king, 0) : diag_attacks(king, 0));
+    u64 rays = k == 0 ? (file_mask(king) & ~sq_bb(king)) : (k == 1 ? (rank_mask(king) & ~sq_bb(king)) : bishop_rays_empty(king));
     if (rays & sm) {
       u64 snipers = rays & (k == 2 ? bq : rq) & theirs;
       while (snipers) {
@@ -341,7 +344,13 @@ M0_HD bool attacked_for_king(const Position& p, int us, u64 path, u64 occ) {
 
 // chess.Board.generate_castling_moves (standard chess; king e1g1 / e1c1), h-side before a-side.
 // Writes the king square and up to two destination squares; returns the number of castling moves.
-M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_mask, u64 to_mask, int* ksq_out, int* to_out) {
+// `danger` (optional): the squares attacked by the opponent under the full occupancy.  With the king on its e-file
+// home square, the rooks in the corners (the only rights clean_castling_bits keeps) and the side NOT in check, the
+// per-square tests below -- which lift the king, and for the destination also move the rook -- see the same attackers
+// as the plain map: the only line through two back-rank squares is the back rank, an attacker on it beyond the king
+// would give check, the corners have nothing behind them, and the rook's new square shields what the king shielded.
+M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_mask, u64 to_mask, int* ksq_out, int* to_out,
+                         const u64* danger = nullptr) {
   u64 backrank = us ? RANK_1 : RANK_8;
   u64 king = ours & p.kings & backrank & from_mask;
   king &= (0 - king);
@@ -361,9 +370,13 @@ M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_
     u64 rook_to = a_side ? bb_d : bb_f;
     u64 king_path = between_bb(ksq, msb(king_to));
     u64 rook_path = between_bb(rs, msb(rook_to));
-    if (!(((occ ^ king ^ rook) & (king_path | rook_path | king_to | rook_to)) ||
-          attacked_for_king(p, us, king_path | king, occ ^ king) ||
-          attacked_for_king(p, us, king_to, occ ^ king ^ rook ^ rook_to))) {
+    bool blocked = ((occ ^ king ^ rook) & (king_path | rook_path | king_to | rook_to)) != 0;
+    bool attacked;
+    if (blocked) attacked = true;
+    else if (danger && ksq == (us ? SQ_E1 : SQ_E8)) attacked = ((king_path | king | king_to) & *danger) != 0;
+    else attacked = attacked_for_king(p, us, king_path | king, occ ^ king) ||
+                    attacked_for_king(p, us, king_to, occ ^ king ^ rook ^ rook_to);
+    if (!attacked) {
       // _from_chess960: e1->h1 becomes e1g1, e1->a1 becomes e1c1 (king on e-file in standard chess)
       int to = rs;
       if (ksq == SQ_E1 && rs == SQ_H1) to = SQ_G1;
@@ -504,7 +517,8 @@ struct LegalCtx {
   bool ep_open;             // an en-passant capture is generated at all (ep square set, empty, and admitted by the evasion rule)
   int ep;
 };
-M0_HD LegalCtx make_legal_ctx(const Position& p) {
+// `checkers_in` (optional): the opponent's pieces that attack the king, when the caller already has them
+M0_HD LegalCtx make_legal_ctx(const Position& p, const u64* checkers_in = nullptr) {
   LegalCtx c;
   c.us = pos_turn(p);
   c.occ = pos_occ(p);
@@ -521,7 +535,7 @@ M0_HD LegalCtx make_legal_ctx(const Position& p) {
   c.king = king_mask ? msb(king_mask) : -1;
   if (c.king < 0) return c;
   c.blockers = slider_blockers(p, c.king, c.occ, c.ours, c.theirs);
-  c.checkers = attackers_of(p, !c.us, c.king, c.occ);
+  c.checkers = checkers_in ? *checkers_in : attackers_of(p, !c.us, c.king, c.occ);
   c.king_cand = king_attacks_bb(sq_bb(c.king)) & ~c.ours;
   if (c.checkers) {
     u64 sliders = c.checkers & (p.bishops | p.rooks | p.queens);
@@ -542,11 +556,30 @@ M0_HD LegalCtx make_legal_ctx(const Position& p) {
   }
   return c;
 }
+// attack set of the piece on `sq` and whether it reaches the king: OR-ed over the opponent's pieces these give the
+// danger map (every square the opponent attacks under the full occupancy) and the checkers
+M0_HD u64 enemy_attacks(const Position& p, int sq, u64 king_bb, u64* checkers) {
+  u64 a = attacks_from(p, sq);
+  if (a & king_bb) *checkers |= sq_bb(sq);
+  return a;
+}
+// attacks_from with the knight / king steps read from two 64-entry tables (filled with knight_attacks_bb / king_attacks_bb)
+M0_HD u64 attacks_from_lut(const Position& p, int sq, const u64* knight_tab, const u64* king_tab) {
+  u64 s = sq_bb(sq);
+  if (s & p.pawns) return pawn_attacks_bb((s & p.occ_w) ? 1 : 0, s);
+  if (s & p.knights) return knight_tab[sq];
+  if (s & p.kings) return king_tab[sq];
+  u64 occ = pos_occ(p), a = 0;
+  if (s & (p.bishops | p.queens)) a = diag_attacks(sq, occ);
+  if (s & (p.rooks | p.queens)) a |= rank_attacks(sq, occ) | file_attacks(sq, occ);
+  return a;
+}
 // THE king may step to `to` (a bit of c.king_cand)
 M0_HD bool king_step_safe(const Position& p, const LegalCtx& c, int to) { return attackers_of(p, !c.us, to, c.occ) == 0; }
 // Destinations of the own piece on `from`, without castling, en passant and the steps of THE king (c.king).
 // For a pawn the set holds captures and pushes; a destination on the first / last rank stands for four promotions.
-M0_HD u64 piece_targets(const Position& p, const LegalCtx& c, int from) {
+// `attacks` = attacks_from(p, from); not read for a pawn
+M0_HD u64 piece_targets_given(const Position& p, const LegalCtx& c, int from, u64 attacks) {
   u64 fb = sq_bb(from);
   if (from == c.king || !c.others_move) return 0;
   if (c.checkers && (p.kings & fb)) return 0;          // evasions are generated with from_mask = ~kings
@@ -556,10 +589,13 @@ M0_HD u64 piece_targets(const Position& p, const LegalCtx& c, int from) {
     u64 dbl = (c.us ? (single << 8) : (single >> 8)) & ~c.occ & (c.us ? (RANK_3 | RANK_4) : (RANK_6 | RANK_5));
     t = ((pawn_attacks_bb(c.us, fb) & c.theirs) | single | dbl) & c.to_mask;
   } else {
-    t = attacks_from(p, from) & ~c.ours & c.to_mask;
+    t = attacks & ~c.ours & c.to_mask;
   }
   if (c.king >= 0 && (c.blockers & fb)) t &= ray_through(from, c.king);   // _is_safe for a pinned piece
   return t;
+}
+M0_HD u64 piece_targets(const Position& p, const LegalCtx& c, int from) {
+  return piece_targets_given(p, c, from, (p.pawns & sq_bb(from)) ? 0 : attacks_from(p, from));
 }
 // the pawn on `from` may capture en passant
 M0_HD bool ep_capture_legal(const Position& p, const LegalCtx& c, int from) {
@@ -572,10 +608,11 @@ M0_HD bool ep_capture_legal(const Position& p, const LegalCtx& c, int from) {
 }
 // castling moves of the position (king square, up to two destinations); _is_safe passes them for THE king and applies
 // the pinned-piece rule to any other own king (boards with several kings)
-M0_HD int legal_castling(const Position& p, const LegalCtx& c, int* ksq_out, int* to_out) {
+M0_HD int legal_castling(const Position& p, const LegalCtx& c, int* ksq_out, int* to_out, const u64* danger = nullptr) {
   if (c.checkers) return 0;
   int to[2];
-  int n = castling_moves(p, c.us, c.occ, c.ours, BB_ALL, BB_ALL, ksq_out, to), m = 0;
+  if (danger && (p.kings & c.ours & (p.kings & c.ours) - 1)) danger = nullptr;   // several own kings: exact tests
+  int n = castling_moves(p, c.us, c.occ, c.ours, BB_ALL, BB_ALL, ksq_out, to, danger), m = 0;
   for (int i = 0; i < n; ++i) {
     int ksq = *ksq_out;
     bool ok = c.king < 0 || ksq == c.king || !(c.blockers & sq_bb(ksq)) || (ray_through(ksq, to[i]) & sq_bb(c.king)) != 0;

@@ -164,10 +164,15 @@ __device__ __forceinline__ void set_mask_bit(u32* bits, int idx) { atomicOr(bits
 // 16 lanes write the 19x8x8 float32 planes of one position: 16 float4 chunks per plane, one per lane
 __device__ __forceinline__ void half_write_planes(const Position& p, float* __restrict__ out, int hl) {
   float4* o4 = reinterpret_cast<float4*>(out) + hl;
-  const int sh = (7 - (hl >> 1)) * 8 + (hl & 1) * 4;       // row = 7 - rank (encoding.py:43-45), four files per chunk
+  // row = 7 - rank (encoding.py:43-45), four files per chunk: the lane's nibble lies in one 32-bit half of a bitboard
+  const bool hi = (hl >> 1) < 4;
+  const int sh = ((7 - (hl >> 1)) & 3) * 8 + (hl & 1) * 4;
+  auto half32 = [&](u64 bb) { return hi ? (u32)(bb >> 32) : (u32)bb; };
+  const u32 side[2] = {half32(p.occ_w), half32(p.occ_b)};
+  const u32 kind[6] = {half32(p.pawns), half32(p.knights), half32(p.bishops), half32(p.rooks), half32(p.queens), half32(p.kings)};
 #pragma unroll
-  for (int plane = 0; plane < 12; ++plane) {
-    u32 bits = (u32)(piece_plane_bb(p, plane) >> sh) & 15u;
+  for (int plane = 0; plane < 12; ++plane) {              // plane order of piece_plane_bb: white P N B R Q K, black P N B R Q K
+    u32 bits = ((kind[plane % 6] & side[plane / 6]) >> sh) & 15u;
     st_global_cs_f4(o4 + plane * 16, make_float4((bits & 1) ? 1.0f : 0.0f, (bits & 2) ? 1.0f : 0.0f,
                                                  (bits & 4) ? 1.0f : 0.0f, (bits & 8) ? 1.0f : 0.0f));
   }
@@ -178,13 +183,21 @@ __device__ __forceinline__ void half_write_planes(const Position& p, float* __re
   }
 }
 
-__global__ void __launch_bounds__(ENCW_THREADS)
+// 8 blocks per SM (64 registers, 32 warps): measured 2.02 ms against 2.27 ms at the natural 92 registers / 5 blocks on the
+// same box; 10 and 12 blocks spill and are slower (tools/scratch/enc_variants.py)
+#ifndef ENCW_MIN_BLOCKS
+#define ENCW_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(ENCW_THREADS, ENCW_MIN_BLOCKS)
 encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict__ planes, u8* __restrict__ mask) {
   __shared__ __align__(16) u16 s_tab[64 * 64];
   __shared__ __align__(16) u32 s_bits[ENCW_HALVES][MASK_BIT_WORDS];
+  __shared__ u64 s_knight[64], s_king[64];
   const int tid = threadIdx.x, hl = tid & 15, half = tid >> 4;
   const unsigned hmask = 0xFFFFu << (tid & 16);            // the 16 lanes that share a position
   if (mask) {
+    if (tid < 64) s_knight[tid] = knight_attacks_bb(sq_bb(tid));
+    else s_king[tid - 64] = king_attacks_bb(sq_bb(tid - 64));
     const uint4* src = reinterpret_cast<const uint4*>(g_move_index_tab);
     uint4* dst = reinterpret_cast<uint4*>(s_tab);
     for (int i = tid; i < 64 * 64 * 2 / 16; i += ENCW_THREADS) dst[i] = src[i];
@@ -204,18 +217,37 @@ encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict_
 
     for (int i = hl; i < MASK_BIT_WORDS / 4; i += 16) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp(hmask);
-    const LegalCtx c = make_legal_ctx(p);                  // the same for the 16 lanes
-    // steps of the king: one candidate square per lane (at most 8)
-    if (hl < popcnt(c.king_cand)) {
-      int to = nth_set_bit(c.king_cand, hl);
-      if (king_step_safe(p, c, to)) set_mask_bit(bits, s_tab[c.king * 64 + to]);
+#ifndef ENC_EXP_STORES_ONLY   // timing experiment (tools/scratch): the store pattern without the move logic
+    // danger map (squares the opponent attacks) and checkers: one opposing piece per lane, OR-reduced over the 16 lanes
+    u64 danger = 0, checkers = 0;
+    {
+      const u64 theirs = pos_them(p), own_kings = p.kings & pos_us(p);
+      const u64 king_bb = own_kings ? sq_bb(msb(own_kings)) : 0;
+      const int enemies = popcnt(theirs);
+      for (int j = hl; j < enemies; j += 16) {
+        const int e = nth_set_bit(theirs, j);
+        const u64 a = attacks_from_lut(p, e, s_knight, s_king);
+        danger |= a;
+        if (a & king_bb) checkers |= sq_bb(e);
+      }
+#pragma unroll
+      for (int o = 8; o; o >>= 1) {
+        danger |= __shfl_xor_sync(hmask, danger, o);
+        checkers |= __shfl_xor_sync(hmask, checkers, o);
+      }
+    }
+    const LegalCtx c = make_legal_ctx(p, &checkers);       // the same for the 16 lanes
+    // steps of the king: the k-th safe square goes to lane k (at most 8)
+    {
+      const u64 steps = c.king_cand & ~danger;
+      if (hl < popcnt(steps)) set_mask_bit(bits, s_tab[c.king * 64 + nth_set_bit(steps, hl)]);
     }
     // every other own piece: lane hl takes pieces hl, hl + 16, ...
     const int pieces = popcnt(c.ours);
     for (int j = hl; j < pieces; j += 16) {
       const int from = nth_set_bit(c.ours, j);
       const bool pawn = (p.pawns >> from) & 1;
-      u64 tg = piece_targets(p, c, from);
+      u64 tg = piece_targets_given(p, c, from, pawn ? 0 : attacks_from_lut(p, from, s_knight, s_king));
       while (tg) {
         int to = lsb(tg);
         tg &= tg - 1;
@@ -228,16 +260,21 @@ encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict_
     }
     if (hl == 15 && !c.checkers) {                         // castling: the lane least likely to hold a piece
       int ksq = 0, to[2];
-      int nc = legal_castling(p, c, &ksq, to);
+      int nc = legal_castling(p, c, &ksq, to, &danger);
       for (int i = 0; i < nc; ++i) set_mask_bit(bits, s_tab[ksq * 64 + to[i]]);
     }
+#endif
     __syncwarp(hmask);
     // bits -> bytes: every lane expands 16 bits into one 16-byte store, 256 contiguous bytes per half warp and step
     uint4* row = reinterpret_cast<uint4*>(mask + (size_t)t * POLICY_SIZE);
     const u16* b16 = reinterpret_cast<const u16*>(bits);
-    for (int i = hl; i < MASK_CHUNKS; i += 16) {
-      u32 v = b16[i];
-      st_global_cs_u4(row + i, make_uint4(spread4(v & 15u), spread4((v >> 4) & 15u), spread4((v >> 8) & 15u), spread4(v >> 12)));
+#pragma unroll 1
+    for (int i0 = 0; i0 < MASK_CHUNKS; i0 += 16) {         // 18 full steps and a 4-lane tail
+      const int i = i0 + hl;
+      if (i0 + 16 <= MASK_CHUNKS || i < MASK_CHUNKS) {
+        u32 v = b16[i];
+        st_global_cs_u4(row + i, make_uint4(spread4(v & 15u), spread4((v >> 4) & 15u), spread4((v >> 8) & 15u), spread4(v >> 12)));
+      }
     }
     __syncwarp(hmask);
   }

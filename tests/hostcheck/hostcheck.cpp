@@ -72,18 +72,25 @@ void hc_ssl(const uint64_t* pos9, float* out) {
 // legal mask through the per-piece SET interface (what the warp-cooperative encode kernel evaluates, one piece per lane)
 static int legal_set_mask(const Position& p, uint8_t* mask) {
   memset(mask, 0, POLICY_SIZE);
-  LegalCtx c = make_legal_ctx(p);
+  u64 danger = 0, checkers = 0, theirs = pos_them(p), kings = p.kings & pos_us(p);
+  u64 king_bb = kings ? sq_bb(msb(kings)) : 0;
+  while (theirs) {
+    int e = lsb(theirs);
+    theirs &= theirs - 1;
+    danger |= enemy_attacks(p, e, king_bb, &checkers);
+  }
+  LegalCtx c = make_legal_ctx(p, &checkers);
   int wtm = pos_turn(p), n = 0;
   u64 own = c.ours;
   while (own) {
     int from = lsb(own);
     own &= own - 1;
     if (from == c.king) {
-      u64 t = c.king_cand;
+      u64 t = c.king_cand & ~danger;
       while (t) {
         int to = lsb(t);
         t &= t - 1;
-        if (king_step_safe(p, c, to)) { mask[policy_index(make_move(from, to, 0), wtm)] = 1; n++; }
+        mask[policy_index(make_move(from, to, 0), wtm)] = 1; n++;
       }
       continue;
     }
@@ -101,7 +108,7 @@ static int legal_set_mask(const Position& p, uint8_t* mask) {
     if (pawn && ep_capture_legal(p, c, from)) { mask[policy_index(make_move(from, c.ep, 0), wtm)] = 1; n++; }
   }
   int ksq = 0, to[2];
-  int nc = legal_castling(p, c, &ksq, to);
+  int nc = legal_castling(p, c, &ksq, to, &danger);
   for (int i = 0; i < nc; ++i) { mask[policy_index(make_move(ksq, to[i], 0), wtm)] = 1; n++; }
   return n;
 }
