@@ -119,6 +119,17 @@ def barrier(world: int):
 ENC_BYTES_PER_POS = 72 + 19 * 64 * 4 + 4672   # packed position read + float32 planes + uint8 mask written
 
 
+def encode_traffic(n):
+    """DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json), when that capture
+    ran the same number of positions (the file stores bytes per launch of the 1 Mi-position default)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get("encode_mask_planes_kernel")
+        return float(e["dram_bytes_per_launch"]) if e and n == 1 << 20 else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def bench_encode(args, rank, world, local):
     import numpy as np
     import torch
@@ -206,7 +217,7 @@ def bench_encode(args, rank, world, local):
                 "d2h_bytes_per_step": ne * (19 * 64 * 4 + 4672), "positions_per_step": ne},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peaks["source"], "kernel": "encode_positions_kernel",
+                     "traffic": encode_traffic(n), "peak_source": peaks["source"], "kernel": "encode_mask_planes_kernel",
                      "algorithmic_bytes_per_launch": n * ENC_BYTES_PER_POS, "kernel_ms": kern_ms},
     }
     if rank == 0:

@@ -344,13 +344,12 @@ M0_HD bool attacked_for_king(const Position& p, int us, u64 path, u64 occ) {
 
 // chess.Board.generate_castling_moves (standard chess; king e1g1 / e1c1), h-side before a-side.
 // Writes the king square and up to two destination squares; returns the number of castling moves.
-// `danger` (optional): the squares attacked by the opponent under the full occupancy.  With the king on its e-file
-// home square, the rooks in the corners (the only rights clean_castling_bits keeps) and the side NOT in check, the
-// per-square tests below -- which lift the king, and for the destination also move the rook -- see the same attackers
-// as the plain map: the only line through two back-rank squares is the back rank, an attacker on it beyond the king
-// would give check, the corners have nothing behind them, and the rook's new square shields what the king shielded.
-M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_mask, u64 to_mask, int* ksq_out, int* to_out,
-                         const u64* danger = nullptr) {
+// Note for legal_castling(): with the king on its e-file home square, the rooks in the corners (the only rights
+// clean_castling_bits keeps) and the side NOT in check, the per-square tests below -- which lift the king, and for the
+// destination also move the rook -- see the same attackers as the plain attack map under the full occupancy: the only
+// line through two back-rank squares is the back rank, an attacker on it beyond the king would give check, the corners
+// have nothing behind them, and the rook's new square shields what the king shielded.
+M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_mask, u64 to_mask, int* ksq_out, int* to_out) {
   u64 backrank = us ? RANK_1 : RANK_8;
   u64 king = ours & p.kings & backrank & from_mask;
   king &= (0 - king);
@@ -373,7 +372,6 @@ M0_HD int castling_moves(const Position& p, int us, u64 occ, u64 ours, u64 from_
     bool blocked = ((occ ^ king ^ rook) & (king_path | rook_path | king_to | rook_to)) != 0;
     bool attacked;
     if (blocked) attacked = true;
-    else if (danger && ksq == (us ? SQ_E1 : SQ_E8)) attacked = ((king_path | king | king_to) & *danger) != 0;
     else attacked = attacked_for_king(p, us, king_path | king, occ ^ king) ||
                     attacked_for_king(p, us, king_to, occ ^ king ^ rook ^ rook_to);
     if (!attacked) {
@@ -608,17 +606,36 @@ M0_HD bool ep_capture_legal(const Position& p, const LegalCtx& c, int from) {
 }
 // castling moves of the position (king square, up to two destinations); _is_safe passes them for THE king and applies
 // the pinned-piece rule to any other own king (boards with several kings)
-M0_HD int legal_castling(const Position& p, const LegalCtx& c, int* ksq_out, int* to_out, const u64* danger = nullptr) {
+// castling moves of the position through castling_moves() with its per-square attack tests
+M0_HD int legal_castling_exact(const Position& p, const LegalCtx& c, int* ksq_out, int* to_out) {
   if (c.checkers) return 0;
   int to[2];
-  if (danger && (p.kings & c.ours & (p.kings & c.ours) - 1)) danger = nullptr;   // several own kings: exact tests
-  int n = castling_moves(p, c.us, c.occ, c.ours, BB_ALL, BB_ALL, ksq_out, to, danger), m = 0;
+  int n = castling_moves(p, c.us, c.occ, c.ours, BB_ALL, BB_ALL, ksq_out, to), m = 0;
   for (int i = 0; i < n; ++i) {
     int ksq = *ksq_out;
     bool ok = c.king < 0 || ksq == c.king || !(c.blockers & sq_bb(ksq)) || (ray_through(ksq, to[i]) & sq_bb(c.king)) != 0;
     if (ok) to_out[m++] = to[i];
   }
   return m;
+}
+// With the danger map (squares the opponent attacks under the full occupancy), a single own king on its home square and
+// the side not in check, castling_moves() reduces to constant masks: f/g (b/c/d) empty, e/f/g (c/d/e) not attacked -- see
+// the note at castling_moves() for why lifting the king and moving the rook does not change the attackers.
+// Returns -1 when the board is not of that kind (several own kings, king elsewhere): use legal_castling_exact then.
+M0_HD int legal_castling_fast(const Position& p, const LegalCtx& c, u64 danger, int* ksq_out, int* to_out) {
+  if (c.checkers) return 0;
+  const u64 own_kings = p.kings & c.ours;
+  if (!own_kings || (own_kings & (own_kings - 1)) || c.king != (c.us ? SQ_E1 : SQ_E8)) return -1;
+  const int bits = pos_castling(p), sh = c.us ? 0 : 56;
+  int m = 0;
+  *ksq_out = c.king;
+  if ((bits & (c.us ? CR_WK : CR_BK)) && !(c.occ & (0x60ull << sh)) && !(danger & (0x70ull << sh))) to_out[m++] = c.king + 2;
+  if ((bits & (c.us ? CR_WQ : CR_BQ)) && !(c.occ & (0x0Eull << sh)) && !(danger & (0x1Cull << sh))) to_out[m++] = c.king - 2;
+  return m;
+}
+M0_HD int legal_castling(const Position& p, const LegalCtx& c, int* ksq_out, int* to_out, const u64* danger = nullptr) {
+  int m = danger ? legal_castling_fast(p, c, *danger, ksq_out, to_out) : -1;
+  return m >= 0 ? m : legal_castling_exact(p, c, ksq_out, to_out);
 }
 
 // chess.Board.has_legal_en_passant (used by the transposition key and is_irreversible):

@@ -130,7 +130,7 @@ encode_positions_kernel(const u64* __restrict__ pos, int n, float* __restrict__ 
 
 
 // ---- planes + mask, half warp per position ----------------------------------------------------------
-static constexpr int ENCW_THREADS = 128;                   // 8 half warps
+static constexpr int ENCW_THREADS = 128;                   // 8 half warps (the table fills below assume 128)
 static constexpr int ENCW_HALVES = ENCW_THREADS / 16;
 static constexpr int ENCW_POS_PER_HALF = 8;
 static constexpr int ENCW_POS_PER_BLOCK = ENCW_HALVES * ENCW_POS_PER_HALF;
@@ -154,10 +154,16 @@ __device__ __forceinline__ void st_global_cs_u4(uint4* ptr, uint4 v) {
 }
 // four mask bits -> four bytes of 0 / 1
 __device__ __forceinline__ u32 spread4(u32 nibble) { return (nibble * 0x00204081u) & 0x01010101u; }
-// j-th set bit of b (j < popcount)
+// j-th set bit of b (j < popcount): halving steps on population counts, no loop
 __device__ __forceinline__ int nth_set_bit(u64 b, int j) {
-  for (int i = 0; i < j; ++i) b &= b - 1;
-  return lsb(b);
+  u32 w = (u32)b;
+  int pos = 0, c = __popc(w);
+  if (j >= c) { j -= c; w = (u32)(b >> 32); pos = 32; }
+  c = __popc(w & 0xFFFFu); if (j >= c) { j -= c; w >>= 16; pos += 16; }
+  c = __popc(w & 0xFFu);   if (j >= c) { j -= c; w >>= 8;  pos += 8; }
+  c = __popc(w & 0xFu);    if (j >= c) { j -= c; w >>= 4;  pos += 4; }
+  c = __popc(w & 0x3u);    if (j >= c) { j -= c; w >>= 2;  pos += 2; }
+  return pos + (j >= (int)(w & 1u) ? 1 : 0);
 }
 __device__ __forceinline__ void set_mask_bit(u32* bits, int idx) { atomicOr(bits + (idx >> 5), 1u << (idx & 31)); }
 
@@ -193,9 +199,11 @@ encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict_
   __shared__ __align__(16) u16 s_tab[64 * 64];
   __shared__ __align__(16) u32 s_bits[ENCW_HALVES][MASK_BIT_WORDS];
   __shared__ u64 s_knight[64], s_king[64];
+  __shared__ uint2 s_spread[256];                          // eight mask bits -> eight bytes of 0 / 1
   const int tid = threadIdx.x, hl = tid & 15, half = tid >> 4;
   const unsigned hmask = 0xFFFFu << (tid & 16);            // the 16 lanes that share a position
   if (mask) {
+    for (int b = tid; b < 256; b += ENCW_THREADS) s_spread[b] = make_uint2(spread4(b & 15), spread4(b >> 4));
     if (tid < 64) s_knight[tid] = knight_attacks_bb(sq_bb(tid));
     else s_king[tid - 64] = king_attacks_bb(sq_bb(tid - 64));
     const uint4* src = reinterpret_cast<const uint4*>(g_move_index_tab);
@@ -260,6 +268,7 @@ encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict_
     }
     if (hl == 15 && !c.checkers) {                         // castling: the lane least likely to hold a piece
       int ksq = 0, to[2];
+      // (an out-of-line cold path for the exact tests, by reference or by value, doubled the kernel time: keep it inline)
       int nc = legal_castling(p, c, &ksq, to, &danger);
       for (int i = 0; i < nc; ++i) set_mask_bit(bits, s_tab[ksq * 64 + to[i]]);
     }
@@ -273,7 +282,8 @@ encode_mask_planes_kernel(const u64* __restrict__ pos, int n, float* __restrict_
       const int i = i0 + hl;
       if (i0 + 16 <= MASK_CHUNKS || i < MASK_CHUNKS) {
         u32 v = b16[i];
-        st_global_cs_u4(row + i, make_uint4(spread4(v & 15u), spread4((v >> 4) & 15u), spread4((v >> 8) & 15u), spread4(v >> 12)));
+        const uint2 lo = s_spread[v & 255u], hi8 = s_spread[v >> 8];
+        st_global_cs_u4(row + i, make_uint4(lo.x, lo.y, hi8.x, hi8.y));
       }
     }
     __syncwarp(hmask);

@@ -25,7 +25,12 @@ for r in data:
 for e in out.values():
     e["dram_bytes_per_launch"] = e["dram_bytes"] / e["launches"]
     e["time_us_per_launch"] = e["time_us"] / e["launches"]
-out["_source"] = os.path.basename(rep)
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+for e in out.values():
+    e["source"] = os.path.basename(rep)
+if os.path.exists(path):                       # keep the entries of kernels captured in other reports
+    old = {k: v for k, v in json.load(open(path)).items() if isinstance(v, dict)}
+    old.update(out)
+    out = old
 json.dump(out, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -1,4 +1,11 @@
-"""Timing experiment (not a product path): variants of encode_mask_planes_kernel built as separate libraries."""
+"""Timing experiment (not a product path): variants of encode_mask_planes_kernel built as separate libraries and timed on
+the same box, checked against the product library's output.  Build the variants first, e.g.
+    F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC -cudart static -I include -shared"
+    SRC="matrix0_b200/csrc/encode_kernels.cu matrix0_b200/csrc/capi_common.cu"
+    nvcc $F -o tools/scratch/libenc_final.so $SRC -lcuda
+    nvcc $F -DENC_EXP_STORES_ONLY -o tools/scratch/libenc_stores.so $SRC -lcuda     # store pattern without the move logic
+    nvcc $F -DENCW_MIN_BLOCKS=6 -o tools/scratch/libenc_mb6.so $SRC -lcuda          # occupancy variants
+then `gpurun -- python tools/scratch/enc_variants.py` (writes gpurun_out/enc_variants.json)."""
 import ctypes, glob, json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
