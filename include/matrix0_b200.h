@@ -52,7 +52,10 @@ int m0_positions_pack(const uint64_t* d_raw, int n, uint64_t* d_pos, void* strea
 int m0_random_playouts(uint64_t* d_pos, int n, uint64_t seed, int max_plies, void* stream);
 
 /* ---- encoding: azchess/encoding.py ------------------------------------------------------------
- * m0_encode_positions is the fused kernel; any output pointer may be NULL.
+ * m0_encode_positions is the fused entry point; any output pointer may be NULL.  Planes and / or mask alone run the
+ * half-warp-per-position kernel (legal moves as a set, HBM-roofline); a call that asks for the ORDERED lists
+ * (d_moves / d_idx / d_counts) runs the thread-per-position kernel with the python-chess ordered generator for all outputs.
+ * Both produce identical planes and masks (tests/test_encoding_gpu.py compares them on 1 Mi positions).
  *   d_planes float32[n][19][8][8]   = encode_board          (encoding.py:11-37, row = 7 - rank)
  *   d_mask   uint8[n][4672]         = MoveEncoder.get_legal_actions (encoding.py:243-253)
  *   d_moves  uint16[n][256]         = list(board.legal_moves) in python-chess generation order,
