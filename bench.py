@@ -277,6 +277,15 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--precision", default=os.environ.get("M0_BENCH_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on the first
+    # collective), so file descriptor 1 points at stderr while the run lasts and the line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.workload == "auto":
         try:
             from matrix0_b200 import bench_selfplay  # noqa: F401
@@ -296,7 +305,7 @@ def main():
             out = bench_selfplay.reference_arm(args)
         else:
             out = reference_encode(args)
-        print(json.dumps(out), flush=True)
+        emit(out)
         return
 
     rank, world, local = dist_setup(args.gpus)
@@ -306,7 +315,7 @@ def main():
     else:
         out = bench_encode(args, rank, world, local)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
