@@ -110,6 +110,10 @@ WEIRD_FENS = [
     "4k3/P6P/8/8/8/8/p6p/4K3 w - - 0 1", "4k3/P6P/8/8/8/8/p6p/4K3 b - - 0 1",   # promotions
     "3rk3/8/8/8/8/8/3B4/3K4 w - - 0 1", "4k3/8/8/8/7b/8/5P2/4K3 w - - 0 1",     # pins
     "4k3/8/8/8/8/5n2/8/4K2r w - - 0 1",                                # double check
+    "r3k2r/8/8/8/8/8/8/4K3 b kq - 0 1", "r3k2r/8/8/8/8/8/4R3/4K3 b kq - 0 1",   # black castling: free, in check
+    "r3k2r/8/8/8/8/8/5R2/4K3 b kq - 0 1", "r3k2r/8/8/8/8/8/3R4/4K3 b kq - 0 1",   # ... through f8 / d8 attacked
+    "r3k2r/8/8/8/8/8/1R6/4K3 b kq - 0 1", "4k3/1r6/8/8/8/8/8/R3K2R w KQ - 0 1",   # b-file attacked: long castling stays legal
+    "r3k2r/8/8/8/8/8/6R1/4K3 b kq - 0 1", "4k3/8/8/8/8/8/8/RN2K1NR w KQ - 0 1",   # g8 attacked; pieces in the way
 ]
 
 
