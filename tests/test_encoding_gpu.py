@@ -135,3 +135,22 @@ def test_ssl_targets_match_reference_goldens(golden_dir):
         for k in ("piece", "threat", "pin", "fork", "control"):
             assert t[k].dtype == np.float32
             assert np.array_equal(t[k], g[k][:n]), (k, n)
+
+
+def test_set_kernel_edge_positions(enc):
+    """The half-warp-per-position kernel (legal moves as a per-piece set, danger map, constant-mask castling) on constructed
+    edge positions -- kingless, several kings of one colour, castling in / through check, pinned and check-removing en passant,
+    promotions, double check, 218 moves -- against the oracle AND against the ordered thread-per-position kernel."""
+    import torch
+    from test_hostcheck import WEIRD_FENS
+    boards = [chess.Board(f) for f in WEIRD_FENS]
+    planes, mask = enc.encode_boards(boards)                                  # planes + mask only: the set kernel
+    for i, b in enumerate(boards):
+        assert planes[i].tobytes() == E.encode_board(b).tobytes(), b.fen()
+        assert (mask[i] == E.get_legal_actions(b)).all(), b.fen()
+    pos = enc.upload_positions(boards)
+    p2, m2, _, _, cnt = enc.encode_positions_device(pos, True, True, True)    # with the lists: the ordered kernel
+    assert np.array_equal(p2.cpu().numpy(), planes) and np.array_equal(m2.cpu().numpy().astype(bool), mask.astype(bool))
+    assert torch.equal(m2.sum(dim=1, dtype=torch.int32), cnt)
+    m3 = enc.encode_positions_device(pos, False, True, False)[1]              # mask alone
+    assert torch.equal(m3, m2)
