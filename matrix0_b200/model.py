@@ -144,6 +144,126 @@ def parameter_shapes(cfg: NetConfig) -> Dict[str, Tuple[int, ...]]:
     return sh
 
 
+def reference_init(cfg: NetConfig) -> Dict[str, Any]:
+    """Parameter values of a freshly constructed reference ``PolicyValueNet(cfg)``, drawn from torch's GLOBAL CPU generator in
+    the order the reference's constructor consumes it, so that ``torch.manual_seed(s)`` gives the reference's weights.
+
+    Construction order (``resnet.py:313-550``): stem conv -> ChessSpecificFeatures (pst_conv, interaction_conv, then
+    ``torch.randn`` for the position encoding followed by ``normal_(0, 0.1)``, ``:217-235``) -> tower (per block conv1, conv2,
+    se_fc1, se_fc2, ``:30-41``; ChessAttention qkv, proj, ``:97-98``, rel_bias zeros ``:135``) -> SSL heads in ModuleDict order
+    -> policy_head conv -> aux heads -> policy_fc1/fc2 (or policy_fc) -> value head convs, value_fc1, value_fc2, value_gate,
+    value_fc3 -> SSRL heads; PyTorch defaults: Conv2d / Linear weight ``kaiming_uniform_(a=sqrt(5))``, Linear bias
+    ``U(-1/sqrt(fan_in), 1/sqrt(fan_in))``, norm weight 1 / bias 0.  Then ``_init_weights`` (``:591-654``) re-draws the head
+    weights (kaiming_normal fan_out for the head convs, xavier_uniform for the fully connected layers, zero biases),
+    scales ``policy_fc2`` (or ``policy_fc``) by 0.8 and gives the piece SSL head xavier_uniform(gain=0.1).
+    Training-only modules that this engine does not hold (aux / SSRL heads) still consume the generator and are drawn and dropped."""
+    import torch
+    from torch.nn import init
+    C, sd = cfg.channels, {}
+
+    def conv(name, co, ci, k):
+        w = torch.empty(co, ci, k, k)
+        init.kaiming_uniform_(w, a=math.sqrt(5))
+        if name:
+            sd[name + ".weight"] = w
+        return w
+
+    def linear(name, fo, fi):
+        w = torch.empty(fo, fi)
+        init.kaiming_uniform_(w, a=math.sqrt(5))
+        b = torch.empty(fo)
+        bound = 1.0 / math.sqrt(fi) if fi > 0 else 0
+        init.uniform_(b, -bound, bound)
+        if name:
+            sd[name + ".weight"], sd[name + ".bias"] = w, b
+        return w, b
+
+    def norm(name, c):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+
+    conv("stem.0", C, cfg.planes, 3)
+    norm("stem.1", C)
+    if cfg.chess_features:
+        if cfg.piece_square_tables:
+            conv("chess_features.pst_conv", C, C, 1)
+            norm("chess_features.pst_norm", C)
+        conv("chess_features.interaction_conv", C, C, 3)
+        norm("chess_features.interaction_norm", C)
+        pe = torch.randn(1, C, 8, 8)
+        init.normal_(pe, mean=0.0, std=0.1)
+        sd["chess_features.position_encoding"] = pe
+    hid = max(8, int(C * cfg.se_ratio))
+    for bi, ai in tower_layout(cfg):
+        p = f"tower.{bi}"
+        conv(p + ".conv1", C, C, 3)
+        norm(p + ".bn1", C)
+        conv(p + ".conv2", C, C, 3)
+        norm(p + ".bn2", C)
+        if cfg.se:
+            linear(p + ".se_fc1", hid, C)
+            linear(p + ".se_fc2", C, hid)
+        if ai is not None:
+            a = f"tower.{ai}"
+            conv(a + ".qkv", 3 * C, C, 1)
+            conv(a + ".proj", C, C, 1)
+            norm(a + ".norm", C)
+            if cfg.attention_relbias:
+                sd[a + ".rel_bias"] = torch.zeros(1, cfg.attention_heads, 64, 64)
+    if cfg.self_supervised:
+        for t in SSL_ORDER:
+            if t in cfg.ssl_tasks:
+                p = f"ssl_heads.{t}"
+                conv(p + ".0", C // 2, C, 1)
+                norm(p + ".1", C // 2)
+                conv(p + ".3", SSL_CHANNELS[t], C // 2, 1)
+    conv("policy_head.0", 64, C, 1)
+    norm("policy_head.1", 64)
+    if cfg.aux_policy_from_square:
+        conv(None, 32, C, 1)
+        conv(None, 64, 32, 1)
+    if cfg.aux_policy_move_type:
+        conv(None, 32, C, 1)
+        conv(None, 12, 32, 1)
+    safe_init = max(0.2 - 1e-3, 1e-6)  # policy_logit_init_scale is not a NetConfig field: getattr default, resnet.py:476-480
+    sd["_policy_logit_scale_raw"] = torch.tensor(math.log(math.expm1(safe_init)), dtype=torch.float32)
+    if cfg.policy_factor_rank > 0:
+        linear("policy_fc1", cfg.policy_factor_rank, 4096)
+        linear("policy_fc2", cfg.policy_size, cfg.policy_factor_rank)
+    else:
+        linear("policy_fc", cfg.policy_size, 4096)
+    conv("value_head.0", 128, C, 1)
+    norm("value_head.1", 128)
+    conv("value_head.3", 128, 128, 1)
+    norm("value_head.4", 128)
+    linear("value_fc1", 2 * C, 8192)
+    linear("value_fc2", C, 2 * C)
+    linear("value_gate.0", C, C)
+    linear("value_fc3", 1, C)
+    ssrl = [(t, {"position": 64, "material": 12, "rotation": 4}[t]) for t in cfg.ssrl_tasks if t in ("position", "material", "rotation")]
+    ssrl_w = []
+    for _, n_out in ssrl:
+        ssrl_w.append((linear(None, C // 2, C)[0], linear(None, n_out, C // 2)[0]))
+    # ---- _init_weights, resnet.py:591-654 ----
+    init.kaiming_normal_(sd["policy_head.0.weight"], mode="fan_out", nonlinearity="relu")
+    for n in (("policy_fc1", "policy_fc2") if cfg.policy_factor_rank > 0 else ("policy_fc",)):
+        init.xavier_uniform_(sd[n + ".weight"], gain=1.0)
+        sd[n + ".bias"].zero_()
+    init.kaiming_normal_(sd["value_head.0.weight"], mode="fan_out", nonlinearity="relu")
+    init.kaiming_normal_(sd["value_head.3.weight"], mode="fan_out", nonlinearity="relu")
+    for n in ("value_fc1", "value_fc2", "value_fc3", "value_gate.0"):
+        init.xavier_uniform_(sd[n + ".weight"], gain=1.0)
+    for n in ("value_fc1", "value_fc2", "value_fc3", "value_gate.0"):
+        sd[n + ".bias"].zero_()
+    sd["policy_fc2.weight" if cfg.policy_factor_rank > 0 else "policy_fc.weight"].mul_(0.8)
+    if cfg.self_supervised and "piece" in cfg.ssl_tasks:
+        init.xavier_uniform_(sd["ssl_heads.piece.0.weight"], gain=0.1)
+        init.xavier_uniform_(sd["ssl_heads.piece.3.weight"], gain=0.1)
+    for w1, w2 in ssrl_w:
+        init.xavier_uniform_(w1, gain=1.0)
+        init.xavier_uniform_(w2, gain=1.0)
+    return sd
+
+
 class PolicyValueNet:
     def __init__(self, cfg: NetConfig, device: Optional[str] = None, precision: str = "fp16", seed: Optional[int] = None):
         import torch
@@ -225,28 +345,26 @@ class PolicyValueNet:
 
     # ---- parameters --------------------------------------------------------------------------------
     def _init_parameters(self, seed: Optional[int]) -> None:
-        """Random initialisation in the spirit of the reference (PyTorch layer defaults + resnet.py:591-640)."""
+        """Random initialisation: the parameter values ``PolicyValueNet(cfg)`` of the reference holds after ``__init__``
+        (``resnet.py:286-589`` module construction with the PyTorch layer defaults, then ``_init_weights`` ``:591-654``).
+        ``seed=None`` draws from torch's global generator exactly like the reference (``torch.manual_seed(s)`` before
+        ``from_config`` gives the same weights as the reference module under the same seed, pinned by per-tensor digests in
+        tests/golden/refinit_digest.json); an integer seed does the same inside a forked generator state."""
         import torch
-        g = torch.Generator(device="cpu")
-        g.manual_seed(int(seed) if seed is not None else 0)
-        for name, shape in self._shapes.items():
-            if name == "_policy_logit_scale_raw":
-                t = torch.tensor(math.log(math.expm1(max(0.2 - 1e-3, 1e-6))), dtype=torch.float32)  # resnet.py:476-480
-            elif name.endswith("position_encoding"):
-                t = torch.randn(shape, generator=g) * 0.1
-            elif name.endswith("rel_bias"):
-                t = torch.zeros(shape)
-            elif len(shape) == 1:
-                t = torch.ones(shape) if name.endswith("weight") and ("bn" in name or "norm" in name or ".1." in name or ".4." in name) else torch.zeros(shape)
-            else:
-                fan_in = int(np.prod(shape[1:]))
-                bound = 1.0 / math.sqrt(fan_in)
-                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
-                if name == "policy_fc2.weight" or name == "policy_fc.weight":
-                    t = t * 0.8
-            self._params[name] = t.to(self.device, dtype=torch.float32).contiguous()
+        if seed is None:
+            sd = reference_init(self.cfg)
+        else:
+            with torch.random.fork_rng(devices=[]):
+                torch.manual_seed(int(seed))
+                sd = reference_init(self.cfg)
+        for name in self._shapes:
+            self._params[name] = sd[name].to(self.device, dtype=torch.float32).contiguous()
 
     def _release(self) -> None:
+        # a captured CUDA graph of the old net (SelfPlayEngine._forward) must not be replayed against freed weights /
+        # workspaces: bump the workspace epoch that is part of its cache key
+        self._ws_epoch = getattr(self, "_ws_epoch", 0) + 1
+        self._max_batch = 0
         if self._handle is not None:
             _native.load_library().m0_net_destroy(self._handle)
             self._handle = None

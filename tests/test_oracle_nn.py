@@ -45,3 +45,47 @@ def test_restatement_matches_reference_module_live(golden_dir):
         p2, v2 = nn_ref.forward(sd, cfg, x)
     assert (p1 - p2).abs().max() < 2e-5 and (v1 - v2).abs().max() < 2e-5
     assert sorted(k for k in ref.state_dict() if k in sd) == sorted(sd)  # every key we model exists in the reference
+
+
+def _refinit_cfg(golden_dir):
+    d = json.load(open(os.path.join(golden_dir, "refinit_digest.json")))
+    known = set(NetConfig.__dataclass_fields__)
+    return d, NetConfig(**{k: v for k, v in d["model"].items() if k in known})
+
+
+def test_reference_init_matches_committed_digests(golden_dir):
+    """matrix0_b200.model.reference_init under torch.manual_seed(0) == the unmodified reference PolicyValueNet's own random
+    initialisation (resnet.py:286-654), tensor by tensor (SHA-256 committed by tests/golden/make_refinit_golden.py)."""
+    import hashlib
+    from matrix0_b200.model import reference_init
+    d, cfg = _refinit_cfg(golden_dir)
+    torch.manual_seed(int(d["seed"]))
+    sd = reference_init(cfg)
+    shapes = parameter_shapes(cfg)
+    assert set(shapes) <= set(d["sha256"])
+    for k in shapes:
+        assert tuple(sd[k].shape) == tuple(shapes[k]), k
+        assert hashlib.sha256(sd[k].contiguous().numpy().tobytes()).hexdigest() == d["sha256"][k], k
+
+
+@pytest.mark.skipif(not refload.reference_available(), reason="/root/reference not present")
+def test_reference_init_matches_reference_module_live(golden_dir):
+    from matrix0_b200.model import reference_init
+    resnet = refload.load_reference("model.resnet")
+    for over, seed in ((dict(channels=64, blocks=6, attention_heads=4, policy_factor_rank=32), 3),
+                       (dict(channels=48, blocks=4, attention_heads=3, policy_factor_rank=0, ssl_tasks=["piece", "control"],
+                             aux_policy_move_type=False, ssrl_tasks=["position", "rotation"]), 11)):
+        d, _ = _refinit_cfg(golden_dir)
+        m = dict(d["model"])
+        m.update(over)
+        torch.manual_seed(seed)
+        ref = resnet.PolicyValueNet.from_config(m)
+        after_ref = torch.rand(1)
+        known = set(NetConfig.__dataclass_fields__)
+        cfg = NetConfig(**{k: v for k, v in m.items() if k in known})
+        torch.manual_seed(seed)
+        sd = reference_init(cfg)
+        assert torch.equal(torch.rand(1), after_ref)          # the generator was consumed exactly as the reference does
+        rsd = ref.state_dict()
+        for k in parameter_shapes(cfg):
+            assert torch.equal(sd[k], rsd[k]), k
