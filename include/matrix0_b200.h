@@ -91,6 +91,10 @@ typedef struct m0_search_config {
   int cpuct_len;
   unsigned long long seed;
   const double* cpuct_by_depth; /* HOST pointer */
+  int max_children;        /* MCTS._prune_children (mcts.py:806-826): keep the max_children largest priors; 0 = off */
+  int raw_logit_priors;    /* 1 = the reference's direct-model path (no inference backend, legal_softmax): non-root leaves are expanded by
+                              Node._expand_with_legal_priors on the RAW logits of the legal moves (mcts.py:697-703, :227-256) */
+  double min_child_prior;  /* drop children whose prior is below this (mcts.py:817-818); 0 = off */
 } m0_search_config;
 
 int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, int max_depth, int hist_cap, m0_engine** out);
@@ -122,6 +126,23 @@ int m0_search_pending_counts(m0_engine* e, int32_t* d_counts_out, void* stream);
 /* MCTS.run results (mcts.py:431, :465, :504-507) in child (= legal move) order; d_child_q/d_prior/d_pi may be NULL */
 int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double* d_child_q, double* d_prior, int32_t* d_count,
                      float* d_pi, double* d_root_q, int32_t* d_root_n, void* stream);
+/* ---- the mini-batch as shipped (selection_jitter in force, config.yaml:138): every simulation of a batch selects with its own
+ * random.random() draws (mcts.py:893-897), so a batch holds up to batch_n different leaves; duplicated leaves share a network row.
+ * Sequence per mini-batch: m0_search_select_multi -> m0_search_multi_encode -> evaluator -> m0_search_expand_backup_multi. */
+int m0_search_multi_enable(m0_engine* e, int samples_per_batch);
+/* caller-supplied draws (parity with the reference under a seeded RNG): d_jitter float64[G][jitter_stride] = random.random() values in
+ * consumption order, d_normal float64[G][normal_stride] = np.random.normal(0, 0.1) values of the entropy noise (mcts.py:181);
+ * NULL = device generator.  Status bit 16 is set for a game that exhausts a stream. */
+int m0_search_set_streams(m0_engine* e, const double* d_jitter, long long jitter_stride, const double* d_normal, long long normal_stride, void* stream);
+/* _collect_leaf_position x batch_n (mcts.py:535-558, :742-769); d_row_base int32[G+1] / d_n_samples int32[G] (either may be NULL) receive
+ * the compact row numbering (row_base[G] = number of rows to evaluate) and the samples collected per game */
+int m0_search_select_multi(m0_engine* e, int batch_n, int32_t* d_sims_left, int32_t* d_row_base, int32_t* d_n_samples, void* stream);
+/* encode_board of the collected leaves of games [g0, g1) into d_planes float32[rows][19][8][8]; mode 0 compact rows (row_base[g] + slot
+ * - row0), 1 dense per leaf ((g - g0) * samples_per_batch + slot), 2 one row per sample in collection order */
+int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, float* d_planes, void* stream);
+/* expansion (+ entropy noise, pruning, TT registration) and backup of the samples of games [g0, g1) in collection order (mcts.py:654-670) */
+int m0_search_expand_backup_multi(m0_engine* e, int g0, int g1, const float* d_logits, int logits_stride, const float* d_values, int row0,
+                                  int per_sample, void* stream);
 int m0_engine_counters(m0_engine* e, unsigned long long* h_out16); /* host buffer; synchronises */
 int m0_engine_status(m0_engine* e, int32_t* d_status_out, int32_t* d_node_count_out, void* stream);
 

@@ -50,6 +50,11 @@ SIGNATURES = {
     "m0_search_pending": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_search_pending_counts": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_search_result": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_search_multi_enable": (c_int, [c_void_p, c_int]),
+    "m0_search_set_streams": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "m0_search_select_multi": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "m0_search_multi_encode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "m0_search_expand_backup_multi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "m0_engine_counters": (c_int, [c_void_p, c_void_p]),
     "m0_engine_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_search_select_var": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -77,6 +82,7 @@ class SearchConfigStruct(ctypes.Structure):
         ("deterministic", c_int), ("no_instant_backtrack", c_int), ("legal_softmax", c_int),
         ("enable_entropy_noise", c_int), ("value_from_white", c_int), ("cpuct_len", c_int),
         ("seed", c_uint64), ("cpuct_by_depth", ctypes.POINTER(c_double)),
+        ("max_children", c_int), ("raw_logit_priors", c_int), ("min_child_prior", c_double),
     ]
 
 

@@ -14,10 +14,11 @@ namespace m0 {
 // pend_flags bits
 enum { PEND_ACTIVE = 1, PEND_EXPAND = 2, PEND_REGISTER = 4, PEND_SET_Q = 8, PEND_ROOT = 16 };
 // status bits (sticky, per game)
-enum { ST_NODE_OVERFLOW = 1, ST_TT_OVERFLOW = 2, ST_DEPTH_CAP = 4, ST_HIST_OVERFLOW = 8 };
+enum { ST_NODE_OVERFLOW = 1, ST_TT_OVERFLOW = 2, ST_DEPTH_CAP = 4, ST_HIST_OVERFLOW = 8, ST_STREAM_EXHAUSTED = 16 };
 // counters
 enum { CTR_SIMS = 0, CTR_TERMINAL_SIMS, CTR_NN_EVALS, CTR_EXPANSIONS, CTR_TT_HOPS, CTR_CHILDREN_SCANNED,
-       CTR_PATH_NODES, CTR_CHILDREN_CREATED, CTR_GAMES_FINISHED, CTR_POSITIONS_PLAYED, CTR_COUNT = 16 };
+       CTR_PATH_NODES, CTR_CHILDREN_CREATED, CTR_GAMES_FINISHED, CTR_POSITIONS_PLAYED, CTR_NOISY_EXPANSIONS, CTR_LEAF_SAMPLES,
+       CTR_COUNT = 16 };
 
 struct SearchParams {
   double fpu_reduction;     // mcts.py:868-869
@@ -32,6 +33,9 @@ struct SearchParams {
   int value_from_white;     // mcts.py:1184 (root evaluation only)
   int cpuct_len;            // entries of the per-depth cpuct table (mcts.py:927-944)
   unsigned long long seed;
+  int max_children;         // _prune_children, mcts.py:806-826 (0 = off)
+  int raw_logit_priors;     // non-root leaves get logits[idx] / sum(logits[idx]) (_expand_with_legal_priors, mcts.py:227-256, :697-703)
+  double min_child_prior;   // mcts.py:817-818 (0 = off)
 };
 
 struct EngineView {
@@ -76,6 +80,25 @@ struct EngineView {
   unsigned long long* counters;  // [CTR_COUNT]
   const SearchParams* params;
   const double* cpuct;    // [cpuct_len]
+  // random draws of the stochastic mode: caller-supplied streams (parity: the values random.random() / np.random.normal
+  // would have returned, consumed in the reference's order) or, when NULL, a counter-based device generator
+  const double* jit_stream;       // [G][jit_stride] uniforms in [0,1)   (mcts.py:893-897)
+  const double* nrm_stream;       // [G][nrm_stride] N(0, 0.1) variates  (mcts.py:181)
+  long long jit_stride, nrm_stride;
+  unsigned long long* jit_cursor; // [G] draws consumed so far
+  unsigned long long* nrm_cursor; // [G]
+  // as-shipped mini-batches (tree_multi_kernels.cu): every simulation of a batch selects with its own jitter and the
+  // distinct leaves each get a network row; allocated by m0_search_multi_enable (ml_cap = 0: not enabled)
+  int ml_cap;             // samples per game and batch (>= inference_batch_size)
+  int* ml_n_samples;      // [G] non-terminal samples collected by the last select
+  int* ml_n_leaves;       // [G] distinct leaf nodes among them
+  int* ml_smp_leaf;       // [G][ml_cap] sample -> leaf slot
+  int* ml_smp_len;        // [G][ml_cap] path length of the sample
+  int* ml_smp_path;       // [G][ml_cap][max_depth] path nodes (root first)
+  int* ml_leaf_node;      // [G][ml_cap] leaf slot -> node
+  int* ml_leaf_first;     // [G][ml_cap] leaf slot -> first sample that reached it
+  u64* ml_leaf_pos;       // [G][ml_cap][9]
+  int* ml_row_base;       // [G + 1] exclusive prefix of ml_n_leaves: compact network rows
 };
 
 static constexpr u32 MOVE_NONE = 0xFFFFu;

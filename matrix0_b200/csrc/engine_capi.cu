@@ -15,6 +15,12 @@ __global__ void search_expand_backup_kernel(EngineView E, const float* logits, i
 __global__ void search_result_kernel(EngineView E, u16* out_moves, int* out_visits, double* out_child_q, double* out_prior,
                                      int* out_count, float* out_pi, double* out_root_q, int* out_root_n);
 __global__ void search_add_dirichlet_kernel(EngineView E, const double* noise, const int* apply, unsigned long long rng_step);
+// kernels (tree_multi_kernels.cu)
+__global__ void search_select_multi_kernel(EngineView E, int batch_cap, int* sims_left);
+__global__ void multi_scan_kernel(EngineView E);
+__global__ void multi_encode_kernel(EngineView E, int g0, int g1, int row0, int mode, float* planes);
+__global__ void search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* logits, int logits_stride, const float* values,
+                                                  int row0, int per_sample);
 }  // namespace m0
 
 using namespace m0;
@@ -65,6 +71,8 @@ static int engine_alloc(m0_engine* e) {
   TRY(dev_alloc(e, &v.pend_flags, G));
   TRY(dev_alloc(e, &v.status, G));
   TRY(dev_alloc(e, &v.counters, (size_t)CTR_COUNT));
+  TRY(dev_alloc(e, &v.jit_cursor, G));
+  TRY(dev_alloc(e, &v.nrm_cursor, G));
   TRY(dev_alloc(e, &e->d_params, 1));
   e->cpuct_cap = v.max_depth + 1;
   TRY(dev_alloc(e, &e->d_cpuct, (size_t)e->cpuct_cap));
@@ -135,6 +143,14 @@ int m0_engine_configure(m0_engine* e, const m0_search_config* c, void* stream) {
   int len = c->cpuct_len < e->cpuct_cap ? c->cpuct_len : e->cpuct_cap;
   p.cpuct_len = len;
   p.seed = c->seed;
+  p.max_children = c->max_children > 0 ? c->max_children : 0;
+  p.min_child_prior = c->min_child_prior > 0.0 ? c->min_child_prior : 0.0;
+  p.raw_logit_priors = c->raw_logit_priors ? 1 : 0;
+  if (p.entropy_noise && !p.legal_softmax) {
+    m0_set_error("m0_engine_configure: enable_entropy_noise with legal_softmax = false (noise over all 4672 entries, mcts.py:164-186) is not "
+                 "implemented on the device; set legal_softmax = true, enable_entropy_noise = false, or deterministic = 1");
+    return M0_ERR_ARG;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   M0_CUDA_TRY(cudaMemcpyAsync(e->d_params, &p, sizeof(p), cudaMemcpyHostToDevice, s));
   M0_CUDA_TRY(cudaMemcpyAsync(e->d_cpuct, c->cpuct_by_depth, sizeof(double) * len, cudaMemcpyHostToDevice, s));
@@ -234,6 +250,84 @@ int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double*
   if (!e || !d_moves || !d_visits || !d_count || !d_root_q || !d_root_n) { m0_set_error("m0_search_result: invalid argument"); return M0_ERR_ARG; }
   search_result_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, d_moves, d_visits, d_child_q, d_prior, d_count, d_pi, d_root_q, d_root_n);
   return m0_check_launch("m0_search_result");
+}
+
+// ---- the reference's mini-batch as shipped: per-simulation jitter, distinct leaves (tree_multi_kernels.cu) ---------------------
+// Allocates the per-game sample / leaf tables for mini-batches of up to `samples_per_batch` simulations (inference_batch_size).
+int m0_search_multi_enable(m0_engine* e, int samples_per_batch) {
+  if (!e || samples_per_batch <= 0 || samples_per_batch > 4096) { m0_set_error("m0_search_multi_enable: invalid argument"); return M0_ERR_ARG; }
+  if (e->v.ml_cap >= samples_per_batch) return M0_OK;
+  if (e->v.ml_cap > 0) { m0_set_error("m0_search_multi_enable: already enabled with a smaller batch (%d)", e->v.ml_cap); return M0_ERR_STATE; }
+  M0_CUDA_TRY(cudaSetDevice(e->device));
+  EngineView& v = e->v;
+  const size_t G = v.G, S = G * (size_t)samples_per_batch;
+  TRY(dev_alloc(e, &v.ml_n_samples, G));
+  TRY(dev_alloc(e, &v.ml_n_leaves, G));
+  TRY(dev_alloc(e, &v.ml_smp_leaf, S, false));
+  TRY(dev_alloc(e, &v.ml_smp_len, S, false));
+  TRY(dev_alloc(e, &v.ml_smp_path, S * (size_t)v.max_depth, false));
+  TRY(dev_alloc(e, &v.ml_leaf_node, S, false));
+  TRY(dev_alloc(e, &v.ml_leaf_first, S, false));
+  TRY(dev_alloc(e, &v.ml_leaf_pos, S * POSITION_WORDS, false));
+  TRY(dev_alloc(e, &v.ml_row_base, G + 1));
+  v.ml_cap = samples_per_batch;
+  return M0_OK;
+}
+
+// Random draws of the stochastic search.  d_jitter float64[G][jitter_stride]: the values random.random() returns, consumed one per
+// child per visited node in selection order (mcts.py:893-897); d_normal float64[G][normal_stride]: the N(0, 0.1) variates of the
+// entropy noise, k per noisy expansion in expansion order (mcts.py:181).  NULL selects the counter-based device generator.  Resets the
+// per-game cursors; a game that runs past its stream sets status bit 16 and continues on the device generator.
+int m0_search_set_streams(m0_engine* e, const double* d_jitter, long long jitter_stride, const double* d_normal, long long normal_stride, void* stream) {
+  if (!e || (d_jitter && jitter_stride <= 0) || (d_normal && normal_stride <= 0)) { m0_set_error("m0_search_set_streams: invalid argument"); return M0_ERR_ARG; }
+  e->v.jit_stream = d_jitter;
+  e->v.jit_stride = d_jitter ? jitter_stride : 0;
+  e->v.nrm_stream = d_normal;
+  e->v.nrm_stride = d_normal ? normal_stride : 0;
+  M0_CUDA_TRY(cudaMemsetAsync(e->v.jit_cursor, 0, sizeof(unsigned long long) * e->v.G, (cudaStream_t)stream));
+  M0_CUDA_TRY(cudaMemsetAsync(e->v.nrm_cursor, 0, sizeof(unsigned long long) * e->v.G, (cudaStream_t)stream));
+  return M0_OK;
+}
+
+// Collection of one mini-batch per game (mcts.py:535-558 + _collect_leaf_position :742-769): batch_n selections with per-simulation
+// jitter, terminal leaves backed up immediately, the other samples recorded.  d_sims_left int32[G] (or NULL) as in m0_search_select_var.
+// Afterwards the compact row numbering is computed; d_row_base int32[G + 1] (row_base[G] = total rows) and d_n_samples int32[G] receive
+// copies when not NULL.
+int m0_search_select_multi(m0_engine* e, int batch_n, int32_t* d_sims_left, int32_t* d_row_base, int32_t* d_n_samples, void* stream) {
+  if (!e || batch_n <= 0) { m0_set_error("m0_search_select_multi: invalid argument"); return M0_ERR_ARG; }
+  if (e->v.ml_cap < batch_n) { m0_set_error("m0_search_select_multi: call m0_search_multi_enable(%d) first", batch_n); return M0_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  search_select_multi_kernel<<<tree_blocks(e), TREE_WARPS * 32, 0, s>>>(e->v, batch_n, d_sims_left);
+  TRY(m0_check_launch("m0_search_select_multi"));
+  multi_scan_kernel<<<1, 1024, 0, s>>>(e->v);
+  TRY(m0_check_launch("m0_search_select_multi(scan)"));
+  if (d_row_base) M0_CUDA_TRY(cudaMemcpyAsync(d_row_base, e->v.ml_row_base, sizeof(int) * (e->v.G + 1), cudaMemcpyDeviceToDevice, s));
+  if (d_n_samples) M0_CUDA_TRY(cudaMemcpyAsync(d_n_samples, e->v.ml_n_samples, sizeof(int) * e->v.G, cudaMemcpyDeviceToDevice, s));
+  return M0_OK;
+}
+
+// encode_board of the collected leaves of games [g0, g1) (mcts.py:571-583).  mode 0: compact rows, row = row_base[g] + slot - row0;
+// mode 1: dense per leaf, row = (g - g0) * samples_per_batch + slot; mode 2: one row per SAMPLE in collection order (duplicates
+// repeated, as the reference's batch tensor holds them), row = (g - g0) * samples_per_batch + sample.
+int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, float* d_planes, void* stream) {
+  if (!e || !d_planes || g0 < 0 || g1 > e->v.G || g0 >= g1 || e->v.ml_cap <= 0 || mode < 0 || mode > 2) { m0_set_error("m0_search_multi_encode: invalid argument"); return M0_ERR_ARG; }
+  const long long warps = (long long)(g1 - g0) * e->v.ml_cap;
+  multi_encode_kernel<<<(unsigned)((warps + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, g0, g1, row0, mode, d_planes);
+  return m0_check_launch("m0_search_multi_encode");
+}
+
+// Node._expand + _prune_children + _register_children_in_tt + _backpropagate for the samples of games [g0, g1) in collection order
+// (mcts.py:654-670).  per_sample = 0: d_logits / d_values rows are the compact rows starting at row0 (one row per distinct leaf);
+// per_sample = 1: one row per sample, game g's rows start at (g - g0) * samples_per_batch (mode 2 of m0_search_multi_encode).
+int m0_search_expand_backup_multi(m0_engine* e, int g0, int g1, const float* d_logits, int logits_stride, const float* d_values, int row0,
+                                  int per_sample, void* stream) {
+  if (!e || !d_logits || !d_values || logits_stride < POLICY_SIZE || g0 < 0 || g1 > e->v.G || g0 >= g1 || e->v.ml_cap <= 0) {
+    m0_set_error("m0_search_expand_backup_multi: invalid argument");
+    return M0_ERR_ARG;
+  }
+  search_expand_backup_multi_kernel<<<(g1 - g0 + TREE_WARPS - 1) / TREE_WARPS, TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      e->v, g0, g1, d_logits, logits_stride, d_values, row0, per_sample);
+  return m0_check_launch("m0_search_expand_backup_multi");
 }
 
 // Engine counters (uint64[16], see engine.cuh CTR_*) and sticky per-game status bits (int32[G])

@@ -14,6 +14,9 @@ struct m0_search_config {
   int cpuct_len;
   unsigned long long seed;
   const double* cpuct_by_depth;  // host pointer, cpuct_len entries (mcts.py:927-944 evaluated per depth)
+  int max_children;              // _prune_children (mcts.py:806-826), 0 = off
+  int raw_logit_priors;          // SURVEY Q3 switch: the direct-model path's _expand_with_legal_priors(logits[idx]) for non-root leaves
+  double min_child_prior;        // 0 = off
 };
 
 struct m0_engine {

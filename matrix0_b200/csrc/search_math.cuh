@@ -17,6 +17,7 @@ M0_HD double d_sqrt(double a) { return __dsqrt_rn(a); }
 M0_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
 M0_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
 M0_HD float f_div(float a, float b) { return __fdiv_rn(a, b); }
+M0_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
 #else
 }  // namespace m0
 #include <math.h>
@@ -29,6 +30,7 @@ M0_HD double d_sqrt(double a) { return sqrt(a); }
 M0_HD float f_add(float a, float b) { return a + b; }
 M0_HD float f_sub(float a, float b) { return a - b; }
 M0_HD float f_div(float a, float b) { return a / b; }
+M0_HD float f_mul(float a, float b) { return a * b; }
 #endif
 
 // azchess/mcts.py:878-881:  u = eff_cpuct * child.prior * (math.sqrt(parent_visits) / (1.0 + child.n));
@@ -75,6 +77,34 @@ template <>
 M0_HD float np_pairwise_sum_rec<0>(const float* a, int n) { return np_pairwise_block_f32(a, n); }
 // valid for n <= 1024 (three halvings); legal-move lists have n <= 256
 M0_HD float np_pairwise_sum_f32(const float* a, int n) { return np_pairwise_sum_rec<3>(a, n); }
+
+// the same reduction for float64 arrays (DOUBLE_pairwise_sum): `dist.sum()` at azchess/mcts.py:184 after the float64 noise was added
+M0_HD double np_pairwise_block_f64(const double* a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = d_add(res, a[i]);
+    return res;
+  }
+  double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+  int i;
+  for (i = 8; i < n - (n % 8); i += 8) {
+    r0 = d_add(r0, a[i + 0]); r1 = d_add(r1, a[i + 1]); r2 = d_add(r2, a[i + 2]); r3 = d_add(r3, a[i + 3]);
+    r4 = d_add(r4, a[i + 4]); r5 = d_add(r5, a[i + 5]); r6 = d_add(r6, a[i + 6]); r7 = d_add(r7, a[i + 7]);
+  }
+  double res = d_add(d_add(d_add(r0, r1), d_add(r2, r3)), d_add(d_add(r4, r5), d_add(r6, r7)));
+  for (; i < n; ++i) res = d_add(res, a[i]);
+  return res;
+}
+template <int DEPTH>
+M0_HD double np_pairwise_sum_rec_f64(const double* a, int n) {
+  if (n <= 128) return np_pairwise_block_f64(a, n);
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return d_add(np_pairwise_sum_rec_f64<DEPTH - 1>(a, n2), np_pairwise_sum_rec_f64<DEPTH - 1>(a + n2, n - n2));
+}
+template <>
+M0_HD double np_pairwise_sum_rec_f64<0>(const double* a, int n) { return np_pairwise_block_f64(a, n); }
+M0_HD double np_pairwise_sum_f64(const double* a, int n) { return np_pairwise_sum_rec_f64<3>(a, n); }
 
 // azchess/mcts.py:948: v = max(-1.0, min(1.0, float(value)))  with Python's min/max NaN behaviour
 M0_HD double py_clip_unit(double x) {

@@ -9,74 +9,9 @@
 // per-game node arrays, so the PUCT scan reads prior/n/q/move with fully coalesced lane-strided
 // loads (24 B per child); the leaf position lives in registers of every lane (no broadcast
 // traffic) and the leaf move list is staged in shared memory.
-#include "engine.cuh"
+#include "tree_common.cuh"
 
 namespace m0 {
-
-static constexpr int TREE_WARPS = 4;
-static constexpr int TREE_THREADS = TREE_WARPS * 32;
-static constexpr unsigned FULL = 0xFFFFFFFFu;
-
-__device__ __forceinline__ double uniform01(u64 x) { return (double)(x >> 11) * (1.0 / 9007199254740992.0); }
-
-// ---- backup: azchess/mcts.py:946-953, `times` identical backprops of value v_leaf along the path ---
-__device__ void warp_backup(const EngineView& E, int g, int len, double v_leaf, int times, int lane) {
-  const size_t nb = (size_t)g * E.max_nodes;
-  const int* path = E.path_node + (size_t)g * E.max_depth;
-  // a node can occur twice in a path (transposition back to an ancestor): then the sequential
-  // interleaving of the reference matters and one lane replays it literally
-  bool dup = false;
-  for (int i = lane; i < len; i += 32) {
-    int a = path[i];
-    for (int j = 0; j < i; ++j) dup |= (path[j] == a);
-  }
-  dup = __any_sync(FULL, dup);
-  if (!dup) {
-    for (int i = lane; i < len; i += 32) {
-      int node = path[i];
-      double v = ((len - 1 - i) & 1) ? -v_leaf : v_leaf;
-      int n = E.node_n[nb + node];
-      double w = E.node_w[nb + node], q;
-      backup_repeated(n, w, q, v, times);
-      E.node_n[nb + node] = n;
-      E.node_w[nb + node] = w;
-      E.node_q[nb + node] = q;
-    }
-  } else if (lane == 0) {
-    for (int t = 0; t < times; ++t) {
-      double v = v_leaf;
-      for (int i = len - 1; i >= 0; --i) {
-        int node = path[i];
-        int n = E.node_n[nb + node] + 1;
-        double w = d_add(E.node_w[nb + node], v);
-        E.node_n[nb + node] = n;
-        E.node_w[nb + node] = w;
-        E.node_q[nb + node] = d_div(w, (double)n);
-        v = -v;
-      }
-    }
-  }
-  __syncwarp();
-}
-
-// chess.Board.is_repetition(5) for the leaf: occurrences of the leaf key among the positions since
-// the last irreversible move, walking the search path and then the game history backwards
-__device__ bool leaf_is_fivefold(const EngineView& E, int g, int depth, const Key128& cur) {
-  int count = 0;
-  const Key128* pk = E.path_key + (size_t)g * E.max_depth;
-  const u8* pi = E.path_irrev + (size_t)g * E.max_depth;
-  for (int d = depth - 1; d >= 0; --d) {
-    if (pi[d]) return false;
-    if (key_eq(pk[d], cur) && ++count >= 4) return true;
-  }
-  const Key128* hk = E.hist_key + (size_t)g * E.hist_cap;
-  const u8* hi = E.hist_irrev + (size_t)g * E.hist_cap;
-  for (int i = E.hist_len[g] - 1; i >= 0; --i) {
-    if (hi[i]) return false;
-    if (key_eq(hk[i], cur) && ++count >= 4) return true;
-  }
-  return false;
-}
 
 // ---- game bookkeeping -------------------------------------------------------------------------------
 __global__ void reset_games_kernel(EngineView E, const int* __restrict__ games, int n_games) {
@@ -387,8 +322,7 @@ search_select_kernel(EngineView E, int batch_cap, int* __restrict__ sims_left, f
 // ---- expansion + backup: azchess/mcts.py:135-225 (Node._expand), :1330-1346, :654-670 ---------------------
 __global__ void __launch_bounds__(TREE_THREADS)
 search_expand_backup_kernel(EngineView E, const float* __restrict__ logits, int logits_stride, const float* __restrict__ values) {
-  __shared__ float s_p[TREE_WARPS][MAX_MOVES];
-  __shared__ Key128 s_key[TREE_WARPS][MAX_MOVES];
+  __shared__ ExpandSmem s_x[TREE_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * TREE_WARPS + wib;
   if (g >= E.G || !E.active[g]) return;
@@ -406,101 +340,9 @@ search_expand_backup_kernel(EngineView E, const float* __restrict__ logits, int 
   if ((flags & PEND_ROOT) && P.value_from_white && !pos_turn(pos)) v = -v;  // mcts.py:1184-1186
 
   const int k = E.leaf_n[g];
-  if ((flags & PEND_EXPAND) && E.node_first[nb + node] < 0 && k > 0) {
-    const float* lg = logits + (size_t)g * logits_stride;
-    const u16* idx = E.leaf_idx + (size_t)g * MAX_MOVES;
-    const u16* mvs = E.leaf_moves + (size_t)g * MAX_MOVES;
-    // np.any(np.isnan(logits)) or np.any(np.isinf(logits)) over the whole vector (mcts.py:147)
-    bool bad = false;
-    for (int i = lane; i < POLICY_SIZE; i += 32) bad |= !isfinite(lg[i]);
-    bad = __any_sync(FULL, bad);
-    const float uniform = (float)(1.0 / (double)k);
-    if (bad) {
-      for (int j = lane; j < k; j += 32) s_p[wib][j] = uniform;
-    } else {
-      float mx = -INFINITY;
-      if (P.legal_softmax) {
-        for (int j = lane; j < k; j += 32) mx = fmaxf(mx, lg[idx[j]]);
-      } else {
-        for (int i = lane; i < POLICY_SIZE; i += 32) mx = fmaxf(mx, lg[i]);
-      }
-      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, off));
-      float sum = 0.0f;
-      if (P.legal_softmax) {
-        for (int j = lane; j < k; j += 32) {
-          float e = expf(f_sub(lg[idx[j]], mx));
-          s_p[wib][j] = e;
-          sum = f_add(sum, e);
-        }
-      } else {
-        for (int i = lane; i < POLICY_SIZE; i += 32) sum = f_add(sum, expf(f_sub(lg[i], mx)));
-        for (int j = lane; j < k; j += 32) s_p[wib][j] = expf(f_sub(lg[idx[j]], mx));
-      }
-      for (int off = 16; off > 0; off >>= 1) sum = f_add(sum, __shfl_xor_sync(FULL, sum, off));
-      __syncwarp();
-      for (int j = lane; j < k; j += 32) {
-        float p = f_div(s_p[wib][j], sum);
-        if (!(p >= 0.0f) || isinf(p)) p = 0.0f;  // mcts.py:198-199
-        s_p[wib][j] = p;
-      }
-      __syncwarp();
-      float total = 0.0f;
-      if (lane == 0) total = np_pairwise_sum_f32(s_p[wib], k);  // lp.sum(), mcts.py:206
-      total = __shfl_sync(FULL, total, 0);
-      if (total > 0.0f && isfinite(total)) {
-        for (int j = lane; j < k; j += 32) s_p[wib][j] = f_div(s_p[wib][j], total);  // mcts.py:210
-      } else {
-        for (int j = lane; j < k; j += 32) s_p[wib][j] = uniform;
-      }
-    }
-    __syncwarp();
-    int first = 0;
-    if (lane == 0) {
-      first = E.node_count[g];
-      if (first + k > E.max_nodes) {
-        E.status[g] |= ST_NODE_OVERFLOW;
-        first = -1;
-      } else {
-        E.node_count[g] = first + k;
-      }
-    }
-    first = __shfl_sync(FULL, first, 0);
-    if (first >= 0) {
-      // child.q = -self.parent.q when the expanding node's creator has q != 0 (mcts.py:221-222)
-      const int creator = E.node_creator[nb + node];
-      double q0 = 0.0;
-      if (creator >= 0) {
-        double cq = E.node_q[nb + creator];
-        if (cq != 0.0) q0 = -cq;
-      }
-      for (int j = lane; j < k; j += 32) {
-        const size_t c = nb + first + j;
-        E.node_prior[c] = (double)s_p[wib][j];
-        E.node_w[c] = 0.0;
-        E.node_q[c] = q0;
-        E.node_n[c] = 0;
-        E.node_first[c] = -1;
-        E.node_creator[c] = node;
-        E.node_mv[c] = (u32)mvs[j] | ((u32)idx[j] << 16);
-        E.node_nchild[c] = 0;
-        if (flags & PEND_REGISTER) {
-          Position cp = pos;
-          push_move(cp, mvs[j]);
-          s_key[wib][j] = position_key(cp);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        E.node_first[nb + node] = first;
-        E.node_nchild[nb + node] = (u16)k;
-        if (flags & PEND_REGISTER)
-          for (int j = 0; j < k; ++j) tt_put(E, g, s_key[wib][j], first + j);  // last writer wins, child order
-        atomicAdd(&E.counters[CTR_EXPANSIONS], 1ull);
-        atomicAdd(&E.counters[CTR_CHILDREN_CREATED], (unsigned long long)k);
-      }
-      __syncwarp();
-    }
-  }
+  if ((flags & PEND_EXPAND) && E.node_first[nb + node] < 0 && k > 0)
+    warp_expand(E, P, g, node, pos, E.leaf_moves + (size_t)g * MAX_MOVES, E.leaf_idx + (size_t)g * MAX_MOVES, k,
+                logits + (size_t)g * logits_stride, (flags & PEND_REGISTER) != 0, (flags & PEND_ROOT) != 0, s_x[wib], lane);
   if ((flags & PEND_SET_Q) && lane == 0) E.node_q[nb + node] = v;  // root.q = v (mcts.py:412-413)
   __syncwarp();
   if (times > 0) warp_backup(E, g, E.path_len[g], py_clip_unit(v), times, lane);

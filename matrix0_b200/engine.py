@@ -15,7 +15,8 @@ from . import _native
 from .boards import MAX_MOVES, PLANES, POLICY_SIZE, POSITION_WORDS, board_to_raw, move_to_code
 
 COUNTER_NAMES = ["sims", "terminal_sims", "nn_evals", "expansions", "tt_hops", "children_scanned", "path_nodes",
-                 "children_created", "games_finished", "positions_played"]
+                 "children_created", "games_finished", "positions_played", "noisy_expansions", "leaf_samples"]
+ST_NODE_OVERFLOW, ST_TT_OVERFLOW, ST_DEPTH_CAP, ST_HIST_OVERFLOW, ST_STREAM_EXHAUSTED = 1, 2, 4, 8, 16
 
 
 def cpuct_table(cfg, length: int) -> np.ndarray:
@@ -86,7 +87,9 @@ class SearchEngine:
         return _native.current_stream()
 
     # ---- configuration ---------------------------------------------------------------------------
-    def configure(self, cfg, deterministic: bool, seed: int = 0) -> None:
+    def configure(self, cfg, deterministic: bool, seed: int = 0, raw_logit_priors: bool = False) -> None:
+        """``raw_logit_priors``: SURVEY Q3 switch -- the reference's direct-model path (``MCTS(cfg, model)`` without an inference
+        backend and ``legal_softmax``) expands non-root leaves from the raw legal logits (mcts.py:697-703)."""
         table = np.ascontiguousarray(cpuct_table(cfg, self.max_depth + 1))
         s = _native.SearchConfigStruct()
         s.fpu_reduction = float(cfg.fpu_reduction)
@@ -102,6 +105,9 @@ class SearchEngine:
         s.cpuct_len = len(table)
         s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         s.cpuct_by_depth = table.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        s.max_children = int(getattr(cfg, "max_children", 0) or 0)
+        s.min_child_prior = float(getattr(cfg, "min_child_prior", 0.0) or 0.0)
+        s.raw_logit_priors = 1 if raw_logit_priors else 0
         _native.check(self._lib.m0_engine_configure(self._h, ctypes.byref(s), self._stream()), "m0_engine_configure")
 
     # ---- games -----------------------------------------------------------------------------------
@@ -176,6 +182,38 @@ class SearchEngine:
                                                  self.res_prior.data_ptr(), self.res_count.data_ptr(),
                                                  self.res_pi.data_ptr() if with_pi else None, self.res_root_q.data_ptr(),
                                                  self.res_root_n.data_ptr(), self._stream()), "m0_search_result")
+
+    # ---- the mini-batch as shipped: per-simulation jitter, distinct leaves (csrc/tree_multi_kernels.cu) -------------
+    def enable_multi(self, samples_per_batch: int) -> None:
+        import torch
+        _native.check(self._lib.m0_search_multi_enable(self._h, int(samples_per_batch)), "m0_search_multi_enable")
+        self.ml_cap = int(samples_per_batch)
+        self.row_base = torch.zeros((self.G + 1,), dtype=torch.int32, device=self.device)
+        self.n_samples = torch.zeros((self.G,), dtype=torch.int32, device=self.device)
+
+    def set_streams(self, jitter=None, normal=None) -> None:
+        """jitter / normal: float64 [G, n] device tensors holding the values ``random.random()`` / ``np.random.normal(0, 0.1)``
+        would return, in the reference's consumption order; None = device generator.  The tensors must stay alive."""
+        self._streams = (jitter, normal)
+        for t in (jitter, normal):
+            assert t is None or (t.dtype.is_floating_point and t.element_size() == 8 and t.is_contiguous() and t.shape[0] == self.G)
+        _native.check(self._lib.m0_search_set_streams(self._h, _native.ptr(jitter), 0 if jitter is None else jitter.shape[1],
+                                                      _native.ptr(normal), 0 if normal is None else normal.shape[1], self._stream()),
+                      "m0_search_set_streams")
+
+    def select_multi(self, batch_n: int, sims_left=None) -> None:
+        _native.check(self._lib.m0_search_select_multi(self._h, int(batch_n), _native.ptr(sims_left), self.row_base.data_ptr(),
+                                                       self.n_samples.data_ptr(), self._stream()), "m0_search_select_multi")
+
+    def multi_encode(self, g0: int, g1: int, row0: int, mode: int, planes) -> None:
+        _native.check(self._lib.m0_search_multi_encode(self._h, int(g0), int(g1), int(row0), int(mode), planes.data_ptr(), self._stream()),
+                      "m0_search_multi_encode")
+
+    def expand_backup_multi(self, g0: int, g1: int, logits, values, row0: int, per_sample: bool) -> None:
+        assert logits.dtype.is_floating_point and logits.element_size() == 4 and logits.is_contiguous()
+        assert values.element_size() == 4 and values.is_contiguous()
+        _native.check(self._lib.m0_search_expand_backup_multi(self._h, int(g0), int(g1), logits.data_ptr(), logits.shape[1], values.data_ptr(),
+                                                              int(row0), 1 if per_sample else 0, self._stream()), "m0_search_expand_backup_multi")
 
     def counters(self) -> dict:
         buf = (ctypes.c_uint64 * 16)()

@@ -7,9 +7,15 @@ evaluator is either any object with ``infer_np`` (the reference's inference-back
 ``selfplay/inference.py:585``; test fakes such as ``ConstantBackend``) or a native evaluator
 exposing ``forward_planes(planes_cuda) -> (logits_cuda, values_cuda)`` (``matrix0_b200.model``).
 
-Determinism: the reference adds ``(random.random() - 0.5) * jitter`` to every PUCT score
-(``mcts.py:893-897``).  ``deterministic=True`` (or env ``MATRIX0_DETERMINISTIC=1``) reproduces the
-reference run with ``random.random`` patched to 0.5 and noise off, bit for bit (visit counts).
+Two search modes.  ``deterministic=True`` (or env ``MATRIX0_DETERMINISTIC=1``) reproduces the reference run with
+``random.random`` patched to 0.5 and noise off, bit for bit (visit counts): every simulation of a mini-batch then
+selects the same leaf and the engine backs it up with the batch's multiplicity.  Otherwise the search runs
+as the reference ships it: ``(random.random() - 0.5) * jitter`` on every PUCT score (``mcts.py:893-897``) drawn per
+child per simulation, so a mini-batch collects many different leaves, each with its own evaluator row; entropy noise
+on near-uniform priors (``mcts.py:170-186``), Dirichlet noise and playout-cap randomisation as configured.  The draws
+come from a counter-based device generator; ``set_random_streams`` substitutes caller-supplied draws (the values
+``random.random()`` / ``np.random.normal(0, 0.1)`` would return) so that a run can be compared with the reference
+under a seeded RNG -- visit counts are then bit-exact (tests/test_mcts_stochastic_gpu.py).
 """
 from __future__ import annotations
 
@@ -94,7 +100,8 @@ class _RootView:
 
 class MCTS:
     def __init__(self, model_or_cfg, cfg_or_model, device: str = "cuda", inference_backend=None, num_threads: int = None,
-                 *, deterministic: Optional[bool] = None, max_nodes: Optional[int] = None, seed: Optional[int] = None):
+                 *, deterministic: Optional[bool] = None, max_nodes: Optional[int] = None, seed: Optional[int] = None,
+                 direct_model_priors: Optional[bool] = None):
         # both argument orders, mcts.py:270-277
         if isinstance(model_or_cfg, MCTSConfig):
             cfg, model = model_or_cfg, cfg_or_model
@@ -115,11 +122,23 @@ class MCTS:
         self.deterministic = bool(deterministic)
         if max_nodes is None:
             max_nodes = int(min(max(getattr(cfg, "max_tree_nodes", 100000), 1024), 1 << 20))
+        if direct_model_priors is None:
+            direct_model_priors = os.environ.get("MATRIX0_DIRECT_MODEL_PRIORS", "") in ("1", "true", "yes")
+        # SURVEY Q3 switch: the reference WITHOUT an inference backend expands non-root leaves from raw logits (mcts.py:697-703)
+        self.direct_model_priors = bool(direct_model_priors) and bool(getattr(cfg, "legal_softmax", False))
+        self._max_batch = int(getattr(cfg, "inference_batch_size", None) or getattr(cfg, "simulation_batch_size", 96))
+        if self._max_batch <= 0:
+            self._max_batch = 96
         with torch.cuda.device(dev):
             self._engine = SearchEngine(1, max_nodes=max_nodes, device=dev.index if dev.index is not None else torch.cuda.current_device())
-            self._engine.configure(cfg, self.deterministic, seed if seed is not None else random.getrandbits(63))
-        self._logits = torch.zeros((1, POLICY_SIZE), dtype=torch.float32, device=dev)
-        self._values = torch.zeros((1,), dtype=torch.float32, device=dev)
+            self._engine.configure(cfg, self.deterministic, seed if seed is not None else random.getrandbits(63),
+                                   raw_logit_priors=self.direct_model_priors)
+            if not self.deterministic:
+                self._engine.enable_multi(self._max_batch)
+        rows = 1 if self.deterministic else self._max_batch
+        self._logits = torch.zeros((rows, POLICY_SIZE), dtype=torch.float32, device=dev)
+        self._values = torch.zeros((rows,), dtype=torch.float32, device=dev)
+        self._sample_planes = None if self.deterministic else torch.zeros((rows, 19, 8, 8), dtype=torch.float32, device=dev)
         self._nn_cache: Dict[Tuple[int, int], float] = {}
         self.simulations_run = 0
         self._last_sims_run = 0
@@ -159,6 +178,51 @@ class MCTS:
             raise RuntimeError("MCTS needs an inference_backend with infer_np() or a native evaluator with forward_planes(); "
                                "matrix0_b200 has no PyTorch/CPU fallback evaluator")
         eng.expand_backup(self._logits, self._values)
+
+    def set_random_streams(self, jitter=None, normal=None) -> None:
+        """Caller-supplied draws for the stochastic search (parity testing): ``jitter`` = the values ``random.random()`` would
+        return (one per child per visited node, selection order, mcts.py:893-897), ``normal`` = the ``np.random.normal(0, 0.1)``
+        values of the entropy noise (k per noisy expansion, expansion order, mcts.py:181).  1-D float64 arrays; ``None`` returns to
+        the device generator.  A run that exhausts a stream raises."""
+        import torch
+        if self.deterministic:
+            raise RuntimeError("set_random_streams: the deterministic mode draws nothing")
+
+        def dev(a):
+            return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(1, -1)).to(self.device)
+        self._engine.set_streams(dev(jitter), dev(normal))
+
+    def _evaluate_samples(self, n_samples: int) -> None:
+        """The collected mini-batch (mcts.py:571-670).  An ``infer_np`` backend receives one row per SAMPLE in collection order,
+        duplicates included, exactly the batch tensor the reference stacks (:604); each sample then backs up the value of its own
+        row.  A native evaluator gets one row per distinct leaf."""
+        import torch
+        eng = self._engine
+        if self.inference_backend is not None:
+            eng.multi_encode(0, 1, 0, 2, self._sample_planes)
+            batch = np.ascontiguousarray(self._sample_planes[:n_samples].cpu().numpy())
+            policies, values = self.inference_backend.infer_np(batch)
+            if policies is None or values is None:
+                raise RuntimeError("Inference backend returned None results")
+            policies = np.asarray(policies, dtype=np.float32)
+            values = np.asarray(values, dtype=np.float32).reshape(-1)
+            if policies.ndim == 1:
+                policies = policies[None]
+            if len(policies) != n_samples or len(values) != n_samples:
+                raise RuntimeError(f"Inference result shape mismatch: expected {n_samples}, got policies={len(policies)}, values={len(values)}")
+            self._logits[:n_samples].copy_(torch.from_numpy(np.ascontiguousarray(policies[:, :POLICY_SIZE])))
+            self._values[:n_samples].copy_(torch.from_numpy(values.copy()))
+            eng.expand_backup_multi(0, 1, self._logits, self._values, 0, per_sample=True)
+        elif hasattr(self.model, "forward_planes"):
+            rows = int(eng.row_base[1])
+            eng.multi_encode(0, 1, 0, 0, self._sample_planes)
+            logits, values = self.model.forward_planes(self._sample_planes[:rows + (rows & 1)])
+            self._logits[:rows].copy_(logits[:rows, :POLICY_SIZE].float())
+            self._values[:rows].copy_(values.reshape(-1)[:rows].float())
+            eng.expand_backup_multi(0, 1, self._logits, self._values, 0, per_sample=False)
+        else:
+            raise RuntimeError("MCTS needs an inference_backend with infer_np() or a native evaluator with forward_planes(); "
+                               "matrix0_b200 has no PyTorch/CPU fallback evaluator")
 
     def _infer(self, board) -> Tuple[np.ndarray, float]:
         """``mcts.py:995-1221`` single-position evaluation (used by tests and for the reused-root value)."""
@@ -256,19 +320,24 @@ class MCTS:
             high = int(max(low, sims_to_run * (1.0 + frac)))
             sims_to_run = random.randint(low, high)
 
-        max_batch = int(getattr(self.cfg, "inference_batch_size", None) or getattr(self.cfg, "simulation_batch_size", 96))
-        if max_batch <= 0:
-            max_batch = 96
+        max_batch = self._max_batch
         total, done = int(max(0, sims_to_run)), 0
         failures = attempts = 0
         while done < total:  # mcts.py:535-740
             batch_n = min(max_batch, total - done)
-            eng.select(batch_n)
-            m = int(eng.pending_counts()[0])
+            if self.deterministic:
+                eng.select(batch_n)
+                m = int(eng.pending_counts()[0])
+            else:
+                eng.select_multi(batch_n)
+                m = int(eng.n_samples[0])
             if m > 0:
                 attempts += 1
                 try:
-                    self._evaluate_pending(m)
+                    if self.deterministic:
+                        self._evaluate_pending(m)
+                    else:
+                        self._evaluate_samples(m)
                     failures = 0
                 except (TimeoutError, RuntimeError) as err:
                     if self.inference_backend is None:
@@ -293,6 +362,8 @@ class MCTS:
         st, _ = eng.status()
         if int(st[0]) & 3:
             raise RuntimeError("search tree capacity exhausted (raise max_nodes / max_tree_nodes)")
+        if int(st[0]) & 16:
+            raise RuntimeError("set_random_streams: a supplied stream of random draws was exhausted during the search")
         mv_objs = [code_to_move(int(c)) for c in moves]
         visit_counts = {m: int(n) for m, n in zip(mv_objs, visits)}
         if sum(visit_counts.values()) == 0:  # mcts.py:433-463

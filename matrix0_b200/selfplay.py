@@ -75,8 +75,18 @@ def resolve_mcts_config(cfg_dict: Dict[str, Any]) -> MCTSConfig:
 
 class SelfPlayEngine:
     def __init__(self, model, cfg_dict: Dict[str, Any], games: int = 4096, device: Optional[int] = None, deterministic: bool = False,
-                 seed: int = 1234, precision: Optional[str] = None, max_nodes: int = 4096, cuda_graph: bool = True):
+                 seed: int = 1234, precision: Optional[str] = None, max_nodes: Optional[int] = None, cuda_graph: bool = True,
+                 search_mode: str = "collapsed", forward_rows: int = 4096):
+        """``search_mode``:
+        ``"collapsed"``   one selection per game and mini-batch, backed up with the multiplicity of the batch: exactly the reference
+                          when its jitter is neutralised (SURVEY Q1; ``deterministic=True`` is bit-exact), and the throughput mode;
+        ``"as_shipped"``  the reference with ``selection_jitter`` in force (config.yaml:138): every simulation of a mini-batch
+                          selects with its own jitter draws (mcts.py:893-897), the distinct leaves of all games are compacted into
+                          evaluator batches of ``forward_rows`` rows, samples are expanded / backed up in collection order."""
         import torch
+        if search_mode not in ("collapsed", "as_shipped"):
+            raise ValueError(f"search_mode must be 'collapsed' or 'as_shipped', got {search_mode!r}")
+        self.search_mode = search_mode
         self.model = model
         self.cfg_dict = cfg_dict
         self.mcfg = resolve_mcts_config(cfg_dict)
@@ -86,10 +96,24 @@ class SelfPlayEngine:
         self.precision = precision
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
+        bs = max(1, int(self.mcfg.inference_batch_size))
+        if max_nodes is None:
+            # a fresh tree per move: every evaluated leaf adds its children (<= ~40 on average, 218 at most)
+            sims_hi = int(self.mcfg.num_simulations * (1.0 + max(0.0, float(self.mcfg.playout_random_frac)))) + 1
+            leaves = (sims_hi if search_mode == "as_shipped" else (sims_hi + bs - 1) // bs) + 2
+            max_nodes = max(4096, 1 << int(math.ceil(math.log2(leaves * 48 + 256))))
+        opening = int(self.sp.get("opening_random_plies", cfg_dict.get("openings", {}).get("random_plies", 0)))
         with torch.cuda.device(self.device):
-            self.engine = SearchEngine(self.G, max_nodes=max_nodes, max_depth=128, hist_cap=int(self.sp.get("max_game_len", 200)) + 64,
-                                       device=self.device_index)
+            self.engine = SearchEngine(self.G, max_nodes=max_nodes, max_depth=128,
+                                       hist_cap=int(self.sp.get("max_game_len", 200)) + opening + 64, device=self.device_index)
             self.engine.configure(self.mcfg, deterministic, seed)
+            if search_mode == "as_shipped":
+                self.engine.enable_multi(bs)
+                self.forward_rows = max(bs, min(int(forward_rows), self.G * bs))
+                self.forward_rows += self.forward_rows & 1
+                # evaluator batch sizes: full chunks of forward_rows rows, the tail chunk in the smallest size that holds it
+                self.forward_sizes = sorted({self.forward_rows} | {s for s in (256, 512, 1024, 2048) if bs <= s < self.forward_rows})
+                self.ml_planes = torch.zeros((self.forward_rows, 19, 8, 8), dtype=torch.float32, device=self.device)
             s = SelfPlayConfigStruct()
             s.temperature_start = float(self.sp.get("temperature_start", 1.0))
             s.temperature_end = float(self.sp.get("temperature_end", 0.1))
@@ -113,11 +137,12 @@ class SelfPlayEngine:
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed))
         self.cuda_graph = bool(cuda_graph) and hasattr(model, "capture_forward")   # replay the evaluator's launches as one CUDA graph
-        self._graph = None
+        self._graphs: Dict[Any, Any] = {}
         self.graph_kernels = 0      # kernels inside the captured forward
         self.graph_replays = 0
         self.nn_evals = 0
         self.nn_rows = 0
+        self.nn_rows_padded = 0
         self.moves = 0
         self.steps = 0
 
@@ -137,14 +162,18 @@ class SelfPlayEngine:
         self.nn_rows += planes.shape[0]
         if self.cuda_graph and (self.precision or getattr(self.model, "precision", "fp32")) != "fp32":
             key = (planes.data_ptr(), planes.shape[0], self.model.ws_epoch)
-            if self._graph is None or self._graph[0] != key:
+            if key not in self._graphs:
                 lib = _native.lib()
+                self._graphs = {k: v for k, v in self._graphs.items() if k[2] == self.model.ws_epoch}   # stale captures (old weights / workspaces)
                 g, lg, v = self.model.capture_forward(planes, self.precision)
+                if self.model.ws_epoch != key[2]:                           # the capture grew the workspaces: earlier graphs are stale
+                    self._graphs = {}
+                    key = (planes.data_ptr(), planes.shape[0], self.model.ws_epoch)
                 n0 = int(lib.m0_launch_count())
                 self.model.forward_planes(planes, self.precision)          # one eager pass to count the kernels the graph replays
                 self.graph_kernels = int(lib.m0_launch_count()) - n0
-                self._graph = ((planes.data_ptr(), planes.shape[0], self.model.ws_epoch), g, lg, v)
-            _, g, lg, v = self._graph
+                self._graphs[key] = (g, lg, v)
+            g, lg, v = self._graphs[key]
             g.replay()
             self.graph_replays += 1
             return lg, v
@@ -176,10 +205,36 @@ class SelfPlayEngine:
     def search_step(self) -> None:
         """One mini-batch: select -> evaluate the pending leaves of all games -> expand + backup."""
         eng = self.engine
+        if self.search_mode == "as_shipped":
+            return self._search_step_as_shipped()
         _native.check(self._lib.m0_search_select_var(eng._h, int(self.mcfg.inference_batch_size), self.sims_left.data_ptr(),
                                                      eng.planes.data_ptr(), _native.current_stream()), "m0_search_select_var")
         logits, values = self._forward(eng.planes)
         eng.expand_backup(logits, values)
+        self.steps += 1
+
+    def _search_step_as_shipped(self) -> None:
+        """mcts.py:535-740 with jitter in force: collect batch_n samples per game, evaluate the distinct leaves of all games in
+        compact batches (a chunk = a run of consecutive games whose rows fit ``forward_rows``), then expand / back up per game in
+        collection order.  One small D2H read (the row numbering) per mini-batch sizes the evaluator calls."""
+        eng = self.engine
+        eng.select_multi(int(self.mcfg.inference_batch_size), self.sims_left)
+        rb = eng.row_base.cpu().numpy()
+        G, cap = self.G, self.forward_rows
+        g0 = 0
+        while g0 < G:
+            g1 = int(np.searchsorted(rb, rb[g0] + cap, side="right")) - 1   # largest g1 with rb[g1] - rb[g0] <= cap
+            g1 = min(max(g1, g0 + 1), G)
+            rows = int(rb[g1] - rb[g0])
+            if rows > 0:
+                size = next(s for s in self.forward_sizes if s >= rows)
+                planes = self.ml_planes[:size]
+                eng.multi_encode(g0, g1, int(rb[g0]), 0, planes)
+                logits, values = self._forward(planes)
+                self.nn_rows += rows - size                                 # count the rows that carry a leaf, not the padding
+                self.nn_rows_padded += size
+                eng.expand_backup_multi(g0, g1, logits, values, int(rb[g0]), per_sample=False)
+            g0 = g1
         self.steps += 1
 
     def end_move(self) -> None:

@@ -50,6 +50,8 @@ class RefConfig:
         self.inference_batch_size = 96
         self.playout_random_frac = 0.0
         self.enable_entropy_noise = True
+        self.max_children = 0
+        self.min_child_prior = 0.0
         for k, v in kw.items():
             if hasattr(self, k):
                 setattr(self, k, v)
@@ -65,8 +67,28 @@ class RefNode:
         self.move, self.expanded, self.move_idx = move, False, None
 
 
-def expand(node: RefNode, board, logits: np.ndarray, legal_only: bool, allow_noise: bool) -> None:
-    """Node._expand, mcts.py:135-225."""
+def expand_with_legal_priors(node: RefNode, board, legal, pri: np.ndarray) -> None:
+    """Node._expand_with_legal_priors, mcts.py:227-256 (fed RAW logits by the direct-model path)."""
+    if node.expanded or not legal:
+        return
+    pri = pri.astype(np.float32, copy=False)
+    total = float(pri.sum())
+    if not np.isfinite(total) or total <= 0:
+        pri = np.full(len(legal), 1.0 / len(legal), dtype=np.float32)
+    else:
+        pri = pri / total
+    wtm = board.turn == chess.WHITE
+    for i, m in enumerate(legal):
+        c = RefNode(prior=float(pri[i]), move=m, parent=node)
+        c.move_idx = int(move_to_index_unchecked(wtm, m.from_square, m.to_square, m.promotion))
+        if node.parent and node.parent.q != 0.0:
+            c.q = -node.parent.q
+        node.children[m] = c
+    node.expanded = True
+
+
+def expand(node: RefNode, board, logits: np.ndarray, legal_only: bool, allow_noise: bool, normal=None) -> None:
+    """Node._expand, mcts.py:135-225.  normal(shape) stands in for np.random.normal(0, 0.1, shape)."""
     if node.expanded:
         return
     legal = list(board.legal_moves)
@@ -85,7 +107,7 @@ def expand(node: RefNode, board, logits: np.ndarray, legal_only: bool, allow_noi
         ent = -np.sum(dist * np.log(dist + 1e-8))  # :171-176
         ratio = ent / max(1e-9, np.log(max(1, len(legal))))
         if allow_noise and ratio > 0.9:  # :179-186
-            dist = dist + np.random.normal(0, 0.1, dist.shape)
+            dist = dist + (normal(dist.shape) if normal is not None else np.random.normal(0, 0.1, dist.shape))
             dist = np.maximum(dist, 1e-8)
             dist = dist / dist.sum()
         pri = []
@@ -110,19 +132,62 @@ def expand(node: RefNode, board, logits: np.ndarray, legal_only: bool, allow_noi
 
 
 class RefMCTS:
-    def __init__(self, cfg: RefConfig, backend, jitter_value: Optional[float] = 0.5):
+    def __init__(self, cfg: RefConfig, backend, jitter_value: Optional[float] = 0.5, jitter_stream=None, normal_stream=None,
+                 direct_model: bool = False):
         """backend: object with infer_np; jitter_value: constant standing in for random.random()
-        (None = call random.random() like the reference)."""
+        (None = call random.random() like the reference).  jitter_stream / normal_stream: 1-D arrays consumed in order
+        instead of random.random() / np.random.normal(0, 0.1) (the draws a seeded reference run would make).
+        direct_model: the reference WITHOUT an inference backend -- non-root leaves of a legal_softmax search are expanded by
+        _expand_with_legal_priors on the raw legal logits (mcts.py:697-703)."""
         self.cfg, self.backend, self.jv = cfg, backend, jitter_value
+        self.jitter_stream, self.normal_stream, self.jit_used, self.nrm_used = jitter_stream, normal_stream, 0, 0
+        self.direct_model = direct_model
+        self.min_gap = float("inf")   # smallest top-2 score gap over all selections (diagnostic for tolerance-limited parity)
         self.tt: "OrderedDict[tuple, RefNode]" = OrderedDict()
         self.nn_cache: Dict[tuple, tuple] = {}
         self.unique_evals = 0
+        self.sample_rows = 0      # rows the reference evaluates (one per collected sample, duplicates included)
+        self.distinct_rows = 0    # distinct leaf nodes among them (the rows the engine evaluates)
         self._last_root = None
         self._last_sims_run = 0
 
     # -- helpers ---------------------------------------------------------------------------------
     def _rand(self) -> float:
+        if self.jitter_stream is not None:
+            self.jit_used += 1
+            return float(self.jitter_stream[self.jit_used - 1])
         return self.jv if self.jv is not None else random.random()
+
+    def _normal(self, shape):
+        if self.normal_stream is None:
+            return np.random.normal(0, 0.1, shape)
+        n = int(np.prod(shape))
+        self.nrm_used += n
+        return np.asarray(self.normal_stream[self.nrm_used - n:self.nrm_used], dtype=np.float64).reshape(shape)
+
+    def _prune_children(self, node: RefNode) -> None:  # mcts.py:806-826
+        if not node.children:
+            return
+        items = list(node.children.items())
+        if self.cfg.min_child_prior > 0.0:
+            items = [(m, c) for (m, c) in items if float(c.prior) >= float(self.cfg.min_child_prior)]
+        if self.cfg.max_children and self.cfg.max_children > 0 and len(items) > self.cfg.max_children:
+            items.sort(key=lambda mc: float(mc[1].prior), reverse=True)
+            items = items[: int(self.cfg.max_children)]
+        node.children = {m: c for (m, c) in items}
+
+    def _expand_leaf(self, node: RefNode, lb, pol, allow_noise: bool) -> None:
+        """mcts.py:654-665 (backend path) / :690-712 (direct-model path)."""
+        if self.direct_model and self.cfg.legal_softmax:
+            legal = list(lb.legal_moves)
+            if legal:
+                wtm = lb.turn == chess.WHITE
+                idxs = [move_to_index_unchecked(wtm, m.from_square, m.to_square, m.promotion) for m in legal]
+                expand_with_legal_priors(node, lb, legal, np.asarray(pol)[idxs])
+        else:
+            expand(node, lb, np.asarray(pol), self.cfg.legal_softmax, allow_noise, self._normal)
+        self._prune_children(node)
+        self._register_children(node, lb)
 
     def _cpuct_at(self, ply: int) -> float:  # mcts.py:927-944
         c = self.cfg
@@ -169,7 +234,7 @@ class RefMCTS:
             if not node.children:
                 break
             pv = max(1, node.n)
-            best, best_s = None, -1e9
+            best, best_s, second_s = None, -1e9, -1e9
             cp = self._cpuct_at(max(0, len(path) - 1))
             for child in node.children.values():
                 q = (float(node.q) - float(cfg.fpu_reduction)) if child.n == 0 else child.q
@@ -180,7 +245,11 @@ class RefMCTS:
                         s -= 0.01
                 s += (self._rand() - 0.5) * (cfg.selection_jitter if cfg.selection_jitter > 0 else 0.001)
                 if s > best_s:
-                    best_s, best = s, child
+                    second_s, best_s, best = best_s, s, child
+                elif s > second_s:
+                    second_s = s
+            if len(node.children) > 1:
+                self.min_gap = min(self.min_gap, best_s - second_s)
             if best is None:
                 best = next(iter(node.children.values()))
             b.push(best.move)
@@ -201,7 +270,8 @@ class RefMCTS:
             root = RefNode()
             logits, v = self._infer(board)
             self.unique_evals += 1
-            expand(root, board, logits, cfg.legal_softmax, allow_noise)
+            expand(root, board, logits, cfg.legal_softmax, allow_noise, self._normal)
+            self._prune_children(root)
             self.tt[key] = root
         else:
             if key not in self.nn_cache:
@@ -218,7 +288,8 @@ class RefMCTS:
         if not root.expanded:  # :399-413
             logits, v = self._infer(board)
             self.unique_evals += 1
-            expand(root, board, logits, cfg.legal_softmax, allow_noise)
+            expand(root, board, logits, cfg.legal_softmax, allow_noise, self._normal)
+            self._prune_children(root)
             self._register_children(root, board)
             v = float(np.clip(v, -1.0, 1.0))
             root.q = v
@@ -237,10 +308,11 @@ class RefMCTS:
                 batch = np.stack([encode_board(s[0]) for s in samples], axis=0)
                 policies, values = self.backend.infer_np(batch)
                 self.unique_evals += 1
+                self.sample_rows += len(samples)
+                self.distinct_rows += len({id(s[1]) for s in samples})
                 for (lb, node, path), pol, val in zip(samples, policies, values):
                     if not node.expanded:
-                        expand(node, lb, np.asarray(pol), cfg.legal_softmax, allow_noise)
-                        self._register_children(node, lb)
+                        self._expand_leaf(node, lb, pol, allow_noise)
                     self._backprop(path, float(np.clip(val, -1.0, 1.0)))
             done += batch_n
         counts = {m: c.n for m, c in root.children.items()}
