@@ -46,4 +46,6 @@ def check(case, vc, pi, v, root, prior_rtol):
     if prior_rtol == 0.0:
         assert pr == e["child_prior"], tag
     else:
-        np.testing.assert_allclose(pr, e["child_prior"], rtol=prior_rtol, atol=1e-12, err_msg=str(tag))
+        # with entropy noise a prior is (softmax + noise) renormalised: the <= 2 ulp float32 softmax difference is an ABSOLUTE
+        # error of ~1e-8 on a value that the noise may have cancelled down to 1e-4, hence the absolute term
+        np.testing.assert_allclose(pr, e["child_prior"], rtol=prior_rtol, atol=2e-8, err_msg=str(tag))
