@@ -153,17 +153,26 @@ typedef struct m0_selfplay_config { /* selfplay: section of the reference config
   unsigned long long seed;
   int argmax_after_plies; /* >= 0: arena move rule (arena.py:75-91): sample at temperature_start while plies < this, then argmax;
                              < 0: the self-play temperature schedule (internal.py:386-394) */
-  int reserved;
+  int low_visit_threshold; /* internal.py:419-425: max visit count below this -> temperature at least 0.8; 0 = off */
+  /* heuristic half of should_adjudicate_draw (draw.py:43-82), the merged `draw:` / `selfplay.draw:` sections (config.py:37-49) */
+  int draw_enabled, draw_min_plies, draw_window, draw_min_unique, draw_halfmove_cap, draw_material_threshold;
 } m0_selfplay_config;
 typedef struct m0_finished_game {
   int game, plies; /* slot, len(states) */
   float z;         /* result from White's point of view (internal.py:587-599) */
-  int reason;      /* 1 checkmate 2 stalemate 3 insufficient material 4 fifty-move claim 5 repetition claim 6 max_game_len 7 resignation */
+  int reason;      /* 1 checkmate 2 stalemate 3 insufficient material 4 fifty-move claim 5 repetition claim 6 max_game_len 7 resignation
+                      8 heuristic draw adjudication (draw.py:43-82; z = last search value, internal.py:587-599) */
   float avg_entropy;
 } m0_finished_game;
 int m0_selfplay_configure(m0_engine* e, const m0_selfplay_config* cfg, void* stream);
 int m0_selfplay_start(m0_engine* e, void* stream);                      /* new game in every slot, internal.py:326-379 */
 int m0_selfplay_advance(m0_engine* e, uint16_t* d_out_move, void* stream); /* one ply: sample, resign, push, finish/restart */
+/* `games` argument of selfplay_worker (internal.py:94, :326): at most `games` more games are started (initial start + restarts), idle
+ * slots afterwards, so every started game is played to its end; < 0 = unlimited (default) */
+int m0_selfplay_set_start_budget(m0_engine* e, long long games, void* stream);
+int m0_selfplay_active_games(m0_engine* e, int* h_out, void* stream);       /* slots holding a game; host int; synchronises */
+/* d_uniforms float64[G]: the np.random.choice draw of sample_move_from_counts (internal.py:734) for the next advances; NULL = device RNG */
+int m0_selfplay_set_uniforms(m0_engine* e, const double* d_uniforms);
 int m0_selfplay_plies(m0_engine* e, int32_t* d_out, void* stream);        /* len(states) per slot, int32[G] */
 int m0_trees_clear(m0_engine* e, void* stream);                         /* fresh MCTS per move (keeps positions + histories) */
 int m0_selfplay_finished(m0_engine* e, m0_finished_game* h_out, int max_records, int* n_out, void* stream); /* host buffer; syncs */

@@ -62,6 +62,9 @@ SIGNATURES = {
     "m0_selfplay_configure": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_selfplay_start": (c_int, [c_void_p, c_void_p]),
     "m0_selfplay_advance": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "m0_selfplay_set_start_budget": (c_int, [c_void_p, c_int64, c_void_p]),
+    "m0_selfplay_active_games": (c_int, [c_void_p, ctypes.POINTER(c_int), c_void_p]),
+    "m0_selfplay_set_uniforms": (c_int, [c_void_p, c_void_p]),
     "m0_trees_clear": (c_int, [c_void_p, c_void_p]),
     "m0_selfplay_finished": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p]),
     "m0_net_create": (c_int, [c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),

@@ -13,7 +13,8 @@ struct m0_selfplay_config {
   double temperature_start, temperature_end, resign_threshold, resign_min_entropy, resign_value_margin;
   int temperature_moves, max_game_len, min_resign_plies, resign_window, resign_consecutive_bad, opening_random_plies;
   unsigned long long seed;
-  int argmax_after_plies, reserved;
+  int argmax_after_plies, low_visit_threshold;
+  int draw_enabled, draw_min_plies, draw_window, draw_min_unique, draw_halfmove_cap, draw_material_threshold;
 };
 
 struct m0_finished_game {
@@ -44,6 +45,13 @@ static int sp_ensure(m0_engine* e) {
   TRY(dev_alloc(e, &s.last_value, G));
   TRY(dev_alloc(e, &s.games_started, G));
   TRY(dev_alloc(e, &s.need_start, G));
+  TRY(dev_alloc(e, &s.hist_move, G * (size_t)e->v.hist_cap));
+  TRY(dev_alloc(e, &s.start_budget, 1));
+  {
+    const int unlimited = 1 << 30;
+    M0_CUDA_TRY(cudaMemcpy(s.start_budget, &unlimited, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  s.uniforms = nullptr;
   s.finished_cap = (int)(G * 4 > 65536 ? G * 4 : 65536);
   TRY(dev_alloc(e, &s.finished, (size_t)s.finished_cap));
   TRY(dev_alloc(e, &s.finished_count, 1));
@@ -76,6 +84,13 @@ int m0_selfplay_configure(m0_engine* e, const m0_selfplay_config* c, void* strea
   p.opening_random_plies = c->opening_random_plies;
   p.seed = c->seed;
   p.argmax_after_plies = c->argmax_after_plies;
+  p.low_visit_threshold = c->low_visit_threshold;
+  p.draw_enabled = c->draw_enabled;
+  p.draw_min_plies = c->draw_min_plies;
+  p.draw_window = c->draw_window;
+  p.draw_min_unique = c->draw_min_unique;
+  p.draw_halfmove_cap = c->draw_halfmove_cap;
+  p.draw_material_threshold = c->draw_material_threshold;
   M0_CUDA_TRY(cudaMemcpyAsync(e->d_sp_params, &p, sizeof(p), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   M0_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return M0_OK;
@@ -88,6 +103,39 @@ int m0_selfplay_start(m0_engine* e, void* stream) {
   e->sp_step += 1;
   selfplay_start_kernel<<<(e->v.G + 3) / 4, 128, 0, (cudaStream_t)stream>>>(e->v, e->sp, 1, e->sp_step);
   return m0_check_launch("m0_selfplay_start");
+}
+
+// selfplay_worker plays exactly `games` games (internal.py:326): at most `games` more games are STARTED from now on (by
+// m0_selfplay_start and by the restarts of finished slots); slots that find the budget empty go idle, so every started game is played
+// to its end and none is discarded.  games < 0: unlimited (the default).
+int m0_selfplay_set_start_budget(m0_engine* e, long long games, void* stream) {
+  if (!e) { m0_set_error("m0_selfplay_set_start_budget: invalid argument"); return M0_ERR_ARG; }
+  TRY(sp_ensure(e));
+  const int v = (games < 0 || games >= (1 << 30)) ? (1 << 30) : (int)games;
+  M0_CUDA_TRY(cudaMemcpyAsync(e->sp.start_budget, &v, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  M0_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return M0_OK;
+}
+
+// d_uniforms float64[G]: the np.random draw sample_move_from_counts makes for each game in the NEXT m0_selfplay_advance calls
+// (internal.py:734 np.random.choice -> one uniform in [0, 1)); NULL returns to the device generator.  The buffer must stay alive.
+int m0_selfplay_set_uniforms(m0_engine* e, const double* d_uniforms) {
+  if (!e) { m0_set_error("m0_selfplay_set_uniforms: invalid argument"); return M0_ERR_ARG; }
+  TRY(sp_ensure(e));
+  e->sp.uniforms = d_uniforms;
+  return M0_OK;
+}
+
+// number of slots that currently hold a game (int, host): 0 once the start budget is spent and every started game has ended
+int m0_selfplay_active_games(m0_engine* e, int* h_out, void* stream) {
+  if (!e || !h_out) { m0_set_error("m0_selfplay_active_games: invalid argument"); return M0_ERR_ARG; }
+  std::vector<unsigned char> act((size_t)e->v.G);
+  M0_CUDA_TRY(cudaMemcpyAsync(act.data(), e->v.active, (size_t)e->v.G, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  M0_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  int n = 0;
+  for (unsigned char a : act) n += a ? 1 : 0;
+  *h_out = n;
+  return M0_OK;
 }
 
 // One ply of the game loop for every slot whose search has finished (internal.py:408-539 + loop condition :382-384):

@@ -39,7 +39,35 @@ __device__ int hist_occurrences(const EngineView& E, int g, const Key128& key) {
 }
 
 enum { END_NONE = 0, END_CHECKMATE = 1, END_STALEMATE = 2, END_INSUFFICIENT = 3, END_FIFTY = 4, END_REPETITION = 5,
-       END_MAX_LEN = 6, END_RESIGN = 7 };
+       END_MAX_LEN = 6, END_RESIGN = 7, END_ADJUDICATED = 8 };
+
+// The heuristic half of should_adjudicate_draw (draw.py:43-82; the standard rules above it are game_end_reason): after min_plies
+// moves, fewer than min_unique different moves among the last `window`, a halfmove clock at the cap, or little material left.
+__device__ bool draw_heuristics(const EngineView& E, const SelfPlayState& S, int g, const Position& pos, int lane) {
+  const SelfPlayParams& P = *S.params;
+  if (!P.draw_enabled) return false;
+  const int L = E.hist_len[g];                       // len(moves)
+  if (L < P.draw_min_plies) return false;
+  if (P.draw_window > 0 && P.draw_min_unique > 0 && L >= P.draw_window) {
+    const u16* mv = S.hist_move + (size_t)g * E.hist_cap + (L - P.draw_window);
+    int unique = 0;
+    for (int i = lane; i < P.draw_window; i += 32) {  // len(set(str(m) for m in recent)): a move is new if no earlier one equals it
+      bool seen = false;
+      for (int j = 0; j < i; ++j) seen |= (mv[j] == mv[i]);
+      unique += seen ? 0 : 1;
+    }
+    for (int off = 16; off > 0; off >>= 1) unique += __shfl_xor_sync(FULLM, unique, off);
+    if (unique < P.draw_min_unique) return true;
+  }
+  if (P.draw_halfmove_cap && pos_halfmove(pos) >= P.draw_halfmove_cap) return true;
+  if (P.draw_material_threshold > 0) {
+    const u64 occ = pos.occ_w | pos.occ_b;
+    const int material = popcnt(pos.pawns & occ) + 3 * popcnt(pos.knights & occ) + 3 * popcnt(pos.bishops & occ) +
+                         5 * popcnt(pos.rooks & occ) + 9 * popcnt(pos.queens & occ);
+    if (material <= P.draw_material_threshold) return true;
+  }
+  return false;
+}
 
 // Does the game end at `pos` before another search?  (warp-cooperative; s_moves = this warp's scratch)
 //   board.is_game_over()                                      internal.py:382
@@ -96,15 +124,34 @@ __device__ int game_end_reason(const EngineView& E, int g, const Position& pos, 
   return END_NONE;
 }
 
-__device__ void append_history(const EngineView& E, int g, const Key128& key, bool irrev) {
+__device__ void append_history(const EngineView& E, const SelfPlayState& S, int g, const Key128& key, bool irrev, Move mv) {
   int L = E.hist_len[g];
   if (L >= E.hist_cap) {
     E.status[g] |= ST_HIST_OVERFLOW;
     return;
   }
+  S.hist_move[(size_t)g * E.hist_cap + L] = mv;
   E.hist_key[(size_t)g * E.hist_cap + L] = key;
   E.hist_irrev[(size_t)g * E.hist_cap + L] = irrev ? 1 : 0;
   E.hist_len[g] = L + 1;
+}
+
+// take one game from the start budget (selfplay_worker plays exactly `games` games, internal.py:326): false -> the slot goes idle
+__device__ bool take_start_budget(const EngineView& E, const SelfPlayState& S, int g, int lane) {
+  int ok = 1;
+  if (lane == 0) {
+    if (*S.start_budget < (1 << 30)) {
+      int old = atomicSub(S.start_budget, 1);
+      if (old <= 0) { atomicAdd(S.start_budget, 1); ok = 0; }
+    }
+    if (!ok) {
+      E.active[g] = 0;
+      E.root_node[g] = -1;
+      E.pend_flags[g] = 0;
+      E.pend_count[g] = 0;
+    }
+  }
+  return __shfl_sync(FULLM, ok, 0) != 0;
 }
 
 // start a fresh game in slot g: start position + opening_random_plies uniformly random legal moves
@@ -135,7 +182,7 @@ __device__ void start_game(const EngineView& E, const SelfPlayState& S, int g, u
     bool epl;
     const Key128 key = position_key(pos, &epl);
     PushInfo info = push_move(pos, mv);
-    if (lane == 0) append_history(E, g, key, info.zeroing || info.reduced_castling || epl);
+    if (lane == 0) append_history(E, S, g, key, info.zeroing || info.reduced_castling || epl, mv);
     __syncwarp();
   }
   if (lane == 0) {
@@ -158,7 +205,7 @@ selfplay_start_kernel(EngineView E, SelfPlayState S, int all, unsigned long long
   if (g >= E.G) return;
   if (!all && !S.need_start[g]) return;
   u64 rng = mix64(S.params->seed ^ mix64(step * 0xA0761D6478BD642Full + (u64)(g + 1)));
-  start_game(E, S, g, s_moves[wib], lane, rng);
+  if (take_start_budget(E, S, g, lane)) start_game(E, S, g, s_moves[wib], lane, rng);
   if (lane == 0) S.need_start[g] = 0;
 }
 
@@ -171,11 +218,13 @@ __device__ void settle_game(const EngineView& E, const SelfPlayState& S, int g, 
     int reason = game_end_reason(E, g, pos, s_moves, lane);
     const int ply = S.ply[g];
     if (reason == END_NONE && ply >= S.params->max_game_len) reason = END_MAX_LEN;
+    if (reason == END_NONE && draw_heuristics(E, S, g, pos, lane)) reason = END_ADJUDICATED;
     if (reason == END_NONE) return;
-    // z from White's point of view: game_result() (internal.py:738-750) or the last search value (:595-599)
+    // z from White's point of view: game_result() (internal.py:738-750) or, where no formal result exists (length cap, heuristic
+    // adjudication), the last search value -- 0.0 before the first search (:587-599)
     double z = 0.0;
     if (reason == END_CHECKMATE) z = pos_turn(pos) ? -1.0 : 1.0;
-    else if (reason == END_MAX_LEN) z = S.last_value[g];
+    else if (reason == END_MAX_LEN || reason == END_ADJUDICATED) z = ply > 0 ? S.last_value[g] : 0.0;
     if (lane == 0) {
       unsigned slot = atomicAdd(S.finished_count, 1u);
       FinishedGame* f = S.finished + (slot % S.finished_cap);
@@ -188,6 +237,7 @@ __device__ void settle_game(const EngineView& E, const SelfPlayState& S, int g, 
       S.ent_total[g] = 0;
     }
     __syncwarp();
+    if (!take_start_budget(E, S, g, lane)) return;
     start_game(E, S, g, s_moves, lane, rng);
   }
 }
@@ -234,6 +284,9 @@ selfplay_advance_kernel(EngineView E, SelfPlayState S, unsigned long long step, 
   }
   int pick = best_j;
   double entropy = 0.0;
+  // the one np.random draw sample_move_from_counts makes (np.random.choice): supplied by the caller or from the device generator
+  const double u01 = S.uniforms ? S.uniforms[g] : sp_uniform(rng);
+  if (P.low_visit_threshold > 0 && best_n < P.low_visit_threshold && temperature < 0.8) temperature = 0.8;   // internal.py:419-425
   if (total > 0) {
     // policy entropy of pi = n / total, pi clipped to [1e-12, 1] over all 4672 entries (internal.py:433-441)
     double e = 0.0;
@@ -245,31 +298,36 @@ selfplay_advance_kernel(EngineView E, SelfPlayState S, unsigned long long step, 
     for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(FULLM, e, off);
     entropy = e - (double)(POLICY_SIZE - nc) * (1e-12 * log(1e-12));
     if (temperature >= 1e-3) {
+      // visits.astype(float32) ** (1 / T), float32 pairwise sum, float32 divide; np.random.choice(k, p): p as float64, cdf = cumsum(p),
+      // cdf /= cdf[-1], index = searchsorted(cdf, u, 'right') (internal.py:713-734)
       const float inv_t = (float)(1.0 / temperature);
-      float sum = 0.0f;
-      for (int j = lane; j < nc; j += 32) {
-        float w = powf((float)E.node_n[nb + fc + j], inv_t);
-        s_w[wib][j] = w;
-        sum += w;
-      }
-      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(FULLM, sum, off);
+      for (int j = lane; j < nc; j += 32) s_w[wib][j] = powf((float)E.node_n[nb + fc + j], inv_t);
       __syncwarp();
-      if (sum > 0.0f && isfinite(sum)) {
-        if (lane == 0) {
-          double u = sp_uniform(rng) * (double)sum, acc = 0.0;
-          int sel = -1;
+      if (lane == 0) {
+        const float sum = np_pairwise_sum_f32(s_w[wib], nc);
+        if (sum > 0.0f && isfinite(sum)) {
+          double last = 0.0;
+          for (int j = 0; j < nc; ++j) last = d_add(last, (double)f_div(s_w[wib][j], sum));
+          double acc = 0.0;
+          int sel = nc - 1;
           for (int j = 0; j < nc; ++j) {
-            acc += (double)s_w[wib][j];
-            if (u < acc && s_w[wib][j] > 0.0f) { sel = j; break; }
+            acc = d_add(acc, (double)f_div(s_w[wib][j], sum));
+            if (d_div(acc, last) > u01) { sel = j; break; }
           }
-          if (sel < 0) sel = best_j;
           pick = sel;
+        } else if (!(sum <= 0.0f)) {
+          // the float32 sum overflowed: visit_dist /= inf leaves NaNs and the reference falls back to np.random.choice(legal_moves)
+          pick = (int)(u01 * nc);
+          if (pick >= nc) pick = nc - 1;
+        } else {
+          pick = (int)(u01 * nc);   // visit_sum <= 0: uniform over the legal moves (:717-722)
+          if (pick >= nc) pick = nc - 1;
         }
-        pick = __shfl_sync(FULLM, pick, 0);
       }
+      pick = __shfl_sync(FULLM, pick, 0);
     }
   } else if (nc > 0) {
-    if (lane == 0) pick = (int)(sp_uniform(rng) * nc);  // uniform over legal moves (internal.py:701-707)
+    if (lane == 0) pick = (int)(u01 * nc);  // uniform over legal moves (internal.py:701-707)
     pick = __shfl_sync(FULLM, pick, 0);
     if (pick >= nc) pick = nc - 1;
   }
@@ -333,6 +391,7 @@ selfplay_advance_kernel(EngineView E, SelfPlayState S, unsigned long long step, 
       S.ent_total[g] = 0;
     }
     __syncwarp();
+    if (!take_start_budget(E, S, g, lane)) return;
     start_game(E, S, g, s_moves[wib], lane, rng);
     settle_game(E, S, g, s_moves[wib], lane, rng);
     return;
@@ -342,7 +401,7 @@ selfplay_advance_kernel(EngineView E, SelfPlayState S, unsigned long long step, 
   const Key128 key = position_key(pos, &epl);
   PushInfo info = push_move(pos, mv);
   if (lane == 0) {
-    append_history(E, g, key, info.zeroing || info.reduced_castling || epl);
+    append_history(E, S, g, key, info.zeroing || info.reduced_castling || epl, mv);
     store_position(E.root_pos + (size_t)g * POSITION_WORDS, pos);
     E.root_node[g] = -1;
   }

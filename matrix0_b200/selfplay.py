@@ -29,7 +29,15 @@ from . import _native
 from .engine import SearchEngine
 from .mcts import MCTSConfig
 
-END_REASONS = {1: "checkmate", 2: "stalemate", 3: "insufficient_material", 4: "fifty_moves", 5: "repetition", 6: "max_game_len", 7: "resign"}
+END_REASONS = {1: "checkmate", 2: "stalemate", 3: "insufficient_material", 4: "fifty_moves", 5: "repetition", 6: "max_game_len", 7: "resign",
+               8: "draw_adjudicated"}
+
+
+def resolve_draw_config(cfg_dict: Dict[str, Any]) -> Dict[str, Any]:
+    """``Config.draw()`` (azchess/config.py:37-49): top-level ``draw:`` merged with ``selfplay.draw:``, the latter winning."""
+    merged = dict(cfg_dict.get("draw", {}) or {})
+    merged.update((cfg_dict.get("selfplay", {}) or {}).get("draw", {}) or {})
+    return merged
 
 
 class SelfPlayConfigStruct(ctypes.Structure):
@@ -38,7 +46,9 @@ class SelfPlayConfigStruct(ctypes.Structure):
                                                "resign_value_margin")] \
         + [(n, ctypes.c_int) for n in ("temperature_moves", "max_game_len", "min_resign_plies", "resign_window",
                                        "resign_consecutive_bad", "opening_random_plies")] \
-        + [("seed", ctypes.c_uint64), ("argmax_after_plies", ctypes.c_int), ("reserved", ctypes.c_int)]
+        + [("seed", ctypes.c_uint64)] \
+        + [(n, ctypes.c_int) for n in ("argmax_after_plies", "low_visit_threshold", "draw_enabled", "draw_min_plies", "draw_window",
+                                       "draw_min_unique", "draw_halfmove_cap", "draw_material_threshold")]
 
 
 class FinishedGameStruct(ctypes.Structure):
@@ -128,6 +138,14 @@ class SelfPlayEngine:
             s.opening_random_plies = int(self.sp.get("opening_random_plies", cfg_dict.get("openings", {}).get("random_plies", 0)))
             s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
             s.argmax_after_plies = int(self.sp.get("argmax_after_plies", -1))
+            s.low_visit_threshold = int(self.sp.get("low_visit_threshold", 0) or 0)
+            draw = resolve_draw_config(cfg_dict)                 # should_adjudicate_draw(board, move_history, draw_cfg), internal.py:383
+            s.draw_enabled = 1 if bool(draw.get("enabled", False)) else 0
+            s.draw_min_plies = int(draw.get("min_plies", 30))
+            s.draw_window = int(draw.get("window", 12))
+            s.draw_min_unique = int(draw.get("min_unique", 3))
+            s.draw_halfmove_cap = int(draw.get("halfmove_cap", 50))
+            s.draw_material_threshold = int(draw.get("material_draw_threshold", 10))
             lib = _native.lib()
             _native.check(lib.m0_selfplay_configure(self.engine._h, ctypes.byref(s), _native.current_stream()), "m0_selfplay_configure")
         self._lib = lib
@@ -154,8 +172,31 @@ class SelfPlayEngine:
         bs = max(1, int(self.mcfg.inference_batch_size))
         return (hi + bs - 1) // bs
 
-    def start(self) -> None:
-        _native.check(self._lib.m0_selfplay_start(self.engine._h, _native.current_stream()), "m0_selfplay_start")
+    def start(self, games: Optional[int] = None) -> None:
+        """New games in the slots.  ``games``: play exactly this many games in total (``selfplay_worker``'s argument, internal.py:326):
+        slots restart finished games until that many have been started, then go idle, and every started game is played to its end."""
+        st = _native.current_stream()
+        _native.check(self._lib.m0_selfplay_set_start_budget(self.engine._h, -1 if games is None else int(games), st), "m0_selfplay_set_start_budget")
+        _native.check(self._lib.m0_selfplay_start(self.engine._h, st), "m0_selfplay_start")
+
+    def active_games(self) -> int:
+        n = ctypes.c_int(0)
+        _native.check(self._lib.m0_selfplay_active_games(self.engine._h, ctypes.byref(n), _native.current_stream()), "m0_selfplay_active_games")
+        return n.value
+
+    def set_sampling_uniforms(self, uniforms) -> None:
+        """uniforms: float64 [G] device tensor (or None): the np.random.choice draw of sample_move_from_counts for the next plies."""
+        self._uniforms = uniforms
+        _native.check(self._lib.m0_selfplay_set_uniforms(self.engine._h, _native.ptr(uniforms)), "m0_selfplay_set_uniforms")
+
+    def check_status(self) -> None:
+        """Raise when a game ran out of tree nodes / table slots / history (the reference bounds its memory by cleanups instead)."""
+        st, _ = self.engine.status()
+        bits = int(st.max()) if st.numel() else 0
+        if bits & 0b11011:
+            bad = int((st != 0).sum())
+            raise RuntimeError(f"search capacity exhausted in {bad} game(s) (status bits {bits:#x}: 1 nodes, 2 transposition table, 8 history, "
+                               f"16 random stream): raise max_nodes / hist_cap")
 
     def _forward(self, planes):
         self.nn_evals += 1
@@ -261,7 +302,8 @@ class SelfPlayEngine:
 
 
 def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[str], games: int, q=None, shared_memory_resource=None,
-                    device: Optional[int] = None, concurrent_games: Optional[int] = None, precision: str = "fp16", data_manager=None) -> int:
+                    device: Optional[int] = None, concurrent_games: Optional[int] = None, precision: str = "fp16", data_manager=None,
+                    search_mode: str = "as_shipped") -> int:
     """Drop-in for ``azchess.selfplay.internal.selfplay_worker`` (internal.py:94): plays ``games`` self-play games and emits the same
     artefacts -- one NPZ shard per game (internal.py:626-651) and the orchestrator's queue messages (``heartbeat`` :546-556,
     ``game`` :666-679).  One call drives a whole GPU: ``concurrent_games`` games (default min(games, 4096)) advance in lock step on
@@ -282,20 +324,26 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
         sd = state.get("model_ema", state.get("model", state)) if isinstance(state, dict) else state   # internal.py:172-174
         model.load_state_dict(sd, strict=False)
     G = int(concurrent_games or min(int(games), 4096))
-    sp = SelfPlayEngine(model, cfg_dict, games=G, device=dev, deterministic=False, seed=seed, precision=precision)
+    # "as_shipped": the reference's search with its configured selection jitter and entropy noise (distinct leaves per mini-batch);
+    # "collapsed": one evaluated leaf per game and mini-batch (the throughput mode, exact when the jitter is neutralised)
+    sp = SelfPlayEngine(model, cfg_dict, games=G, device=dev, deterministic=False, seed=seed, precision=precision, search_mode=search_mode)
     mcfg = cfg_dict.get("model", {}) or {}
     ssl_tasks = tuple(mcfg.get("ssl_tasks", ())) if mcfg.get("self_supervised", False) else ()      # internal.py:251-256
     rec = GameRecorder(sp, ssl_tasks=ssl_tasks)
     out_dir = os.path.join(str(cfg_dict.get("data_dir", "data")), "selfplay")
     written, last_hb, t_start = 0, time.perf_counter(), time.perf_counter()
-    sp.start()
+    sp.start(games)                      # exactly `games` games are started; every one of them is played to its end (internal.py:326)
     while written < games:
         sp.begin_move()
         for _ in range(sp.batches_per_move()):
             sp.search_step()
         rec.after_search()
         sp.end_move()
-        for gd in rec.after_move():
+        sp.check_status()
+        finished = rec.after_move()
+        if not finished and sp.active_games() == 0:
+            break                            # nothing in flight any more (games lost to a too small recorder window)
+        for gd in finished:
             if written >= games:
                 break
             T = int(gd["meta_moves"][0])
