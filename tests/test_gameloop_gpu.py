@@ -103,10 +103,34 @@ def test_start_budget_plays_every_started_game_to_its_end(golden_dir):
     sp.check_status()
 
 
-def test_temperature_overflow_falls_back_to_uniform():
-    """visits ** (1 / T) overflowing float32 (T = 0.1, > ~7000 visits): the reference's probabilities become NaN and it picks a uniformly
-    random legal move (internal.py:715-731) -- oracle restatement and kernel agree on that branch."""
+def test_temperature_overflow_falls_back_to_uniform(golden_dir):
+    """visits ** (1 / T) overflowing float32 (T = 0.1, > ~7000 visits on one move): the reference's probabilities become NaN and it picks
+    a uniformly random legal move (internal.py:715-731); kernel and oracle restatement take the same branch with the same draw."""
+    from matrix0_b200.selfplay import SelfPlayEngine
     from oracle.selfplay_ref import sample_move_from_counts
-    moves = list(chess.Board().legal_moves)
-    visits = [9000] + [10] * (len(moves) - 1)
-    assert sample_move_from_counts(moves, visits, 0.1, 0.51) == int(0.51 * len(moves))
+    net = small_net(golden_dir)
+    G, sims = 2, 60000
+    cfg = {"mcts": dict(MCTS_KW, num_simulations=sims, inference_batch_size=96, playout_random_frac=0.0, dirichlet_frac=0.0),
+           "selfplay": {"num_simulations": sims, "opening_random_plies": 2, "max_game_len": 50, "temperature_start": 0.1, "temperature_end": 0.1,
+                        "temperature_moves": 0, "resign_threshold": -2.0}}
+    sp = SelfPlayEngine(net, cfg, games=G, deterministic=True, seed=4, precision="fp32")
+    sp.start()
+    sp.begin_move()
+    for _ in range(sp.batches_per_move()):
+        sp.search_step()
+    eng = sp.engine
+    eng.result(with_pi=False)
+    cnt, mv, vis = eng.res_count.cpu().numpy(), eng.res_moves.cpu().numpy().view(np.uint16), eng.res_visits.cpu().numpy()
+    u = torch.tensor([0.51, 0.07], dtype=torch.float64, device="cuda")
+    sp.set_sampling_uniforms(u)
+    sp.end_move()
+    played = sp.moves_played.cpu().numpy().view(np.uint16)
+    overflowed = 0
+    for g in range(G):
+        k = int(cnt[g])
+        v = [int(x) for x in vis[g, :k]]
+        with np.errstate(over="ignore"):
+            overflowed += int(not np.isfinite((np.array(v, dtype=np.float32) ** np.float32(10.0)).sum()))
+        idx = sample_move_from_counts(list(range(k)), v, 0.1, float(u[g]))
+        assert int(played[g]) == int(mv[g, idx]), (g, v)
+    assert overflowed > 0
