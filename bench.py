@@ -275,6 +275,7 @@ def main():
                     help="mcts.inference_batch_size: 96 = the reference's accounting (one evaluated leaf per game stands for up to 96 "
                          "simulations, SURVEY Q1); 1 = distinct-leaf mode, every simulation evaluates its own leaf (SURVEY 8d row 4, second mode)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-extras", action="store_true", help="headline record only: skip the as_shipped / encode / forward_sweep sub-records")
     ap.add_argument("--precision", default=os.environ.get("M0_BENCH_PRECISION", "fp16"), choices=["fp16", "bf16", "fp32"])
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on the first
@@ -312,6 +313,13 @@ def main():
     if args.workload == "selfplay":
         from matrix0_b200 import bench_selfplay
         out = bench_selfplay.run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ranks)
+        if world == 1 and not args.no_extras:
+            # BASELINE configs[1] beside the headline: the encode + legal-mask microbenchmark with its own roofline / e2e / cpu_baseline
+            import torch
+            torch.cuda.empty_cache()
+            enc_args = argparse.Namespace(**vars(args))
+            enc_args.steps, enc_args.warmup, enc_args.cpu_seconds = 10, 3, min(args.cpu_seconds, 5.0)
+            out["encode"] = bench_encode(enc_args, rank, world, local)
     else:
         out = bench_encode(args, rank, world, local)
     if rank == 0:

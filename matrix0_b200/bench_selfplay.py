@@ -224,9 +224,83 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
                  "terminal_sims": d["terminal_sims"], "tt_hops": d["tt_hops"],
                  "algorithmic_bytes": 24 * d["children_scanned"] + 24 * d["path_nodes"] + 44 * d["children_created"]},
     }
+    out["accounting"] = ("value counts SIMULATIONS in the reference's accounting: with the jitter neutralised every simulation of a mini-batch reaches "
+                         "the same leaf (SURVEY Q1), so one evaluated row stands for up to inference_batch_size simulations; the physical rate is "
+                         "unique_nn_evals_per_s rows/s.  `as_shipped` is the same engine with the reference's per-simulation jitter and entropy noise: "
+                         "compare its nn_rows_per_s with cpu_baseline.distinct_rows_per_s (like with like) or its sims_per_s with cpu_baseline.value")
+    if not getattr(args, "no_extras", False) and leaf_batch > 1:
+        del eng
+        sp.engine.close()
+        torch.cuda.empty_cache()
+        out["as_shipped"] = bench_as_shipped(net, cfg, G, local, D.rank_seed(4321, rank), precision, stream)
+        if world == 1:
+            out["forward_sweep"] = forward_sweep(net, precision, stream, load_peaks)
     if rank == 0:
         out["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
     return out
+
+
+def bench_as_shipped(net, cfg, G, local, seed, precision, stream, moves=2):
+    """The reference's search AS SHIPPED (selection_jitter 0.05 drawn per child per simulation, entropy noise on near-uniform priors,
+    Dirichlet noise, playout-cap randomisation): every mini-batch collects up to 96 samples per game, the DISTINCT leaves of all games are
+    evaluated in compact batches.  Timed with CUDA events over `moves` whole moves after one warm-up move."""
+    import torch
+    from matrix0_b200.selfplay import SelfPlayEngine
+    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=seed, precision=precision, search_mode="as_shipped")
+    sp.start()
+    sp.play_move()
+    torch.cuda.synchronize()
+    c0, r0, p0 = sp.counters(), sp.nn_rows, sp.nn_rows_padded
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(moves):
+        sp.play_move()
+    t1.record(stream)
+    torch.cuda.synchronize()
+    secs = t0.elapsed_time(t1) * 1e-3
+    c1 = sp.counters()
+    d = {k: c1[k] - c0[k] for k in c1}
+    sp.check_status()
+    rows = d["nn_evals"] + G * moves          # distinct leaves + the root evaluation of every move
+    out = {"mode": "as shipped: per-simulation selection jitter (mcts.py:893-897), entropy noise (:170-186), Dirichlet noise, playout-cap "
+                   "randomisation; one evaluator row per DISTINCT leaf of a mini-batch, fresh tree per move",
+           "games_per_gpu": G, "moves_timed": moves, "seconds": secs, "sims_per_s": d["sims"] / secs, "positions_per_s": d["positions_played"] / secs,
+           "nn_rows_per_s": rows / secs, "padded_rows_per_s": (sp.nn_rows_padded - p0 + G * moves) / secs,
+           "samples_per_s": d["leaf_samples"] / secs, "distinct_rows_per_sample": d["nn_evals"] / max(1, d["leaf_samples"]),
+           "rows_per_move_per_game": rows / (G * moves), "noisy_expansions_share": d["noisy_expansions"] / max(1, d["expansions"]),
+           "engine_bytes": sp.engine.bytes, "max_nodes_per_game": sp.engine.max_nodes}
+    sp.engine.close()
+    return out
+
+
+def forward_sweep(net, precision, stream, load_peaks, batches=(256, 512, 1024, 2048, 4096, 8192), warmup=3, iters=10):
+    """BASELINE configs[2]: ResNet-24 inference forward alone over a batch sweep (real encoded positions, CUDA events)."""
+    import torch
+    from matrix0_b200 import _native
+    lib = _native.lib()
+    peaks = load_peaks()
+    res = []
+    for B in batches:
+        pos = torch.empty((B, 9), dtype=torch.int64, device="cuda")
+        _native.check(lib.m0_random_playouts(pos.data_ptr(), B, 7, 80, stream.cuda_stream))
+        planes = torch.empty((B, 19, 8, 8), dtype=torch.float32, device="cuda")
+        _native.check(lib.m0_encode_planes(pos.data_ptr(), B, planes.data_ptr(), stream.cuda_stream))
+        for _ in range(warmup):
+            net.forward_planes(planes, precision)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(iters):
+            net.forward_planes(planes, precision)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        tf = FLOP_PER_POSITION * B / (ms * 1e-3) / 1e12
+        res.append({"batch": B, "ms": ms, "positions_per_s": B / (ms * 1e-3), "tflops": tf, "frac_of_burst_peak": tf / peaks["bf16_tflops"],
+                    "frac_of_sustained_peak": tf / peaks["bf16_tflops_sustained"]})
+    return {"workload": "ResNet-24 inference forward alone (BASELINE configs[2]), real encoded positions, " + precision, "dtype": precision,
+            "sweep": res}
+
 
 
 def cpu_baseline(sims: int, budget_s: float, moves_cap: int = 1):
@@ -249,21 +323,24 @@ def cpu_baseline(sims: int, budget_s: float, moves_cap: int = 1):
     b = chess.Board()
     t0 = time.perf_counter()
     done_sims = moves = 0
-    evals = 0
+    evals = rows = distinct = 0
     while moves < moves_cap or time.perf_counter() - t0 < budget_s * 0.5:
-        mc = RefMCTS(RefConfig(**{**m, "dirichlet_frac": 0.0, "enable_entropy_noise": False, "playout_random_frac": 0.0}), net, jitter_value=None)
+        mc = RefMCTS(RefConfig(**m), net, jitter_value=None)     # as shipped: random.random() jitter, entropy / Dirichlet noise, playout cap
         vc, pi, v = mc.run(b, ply=moves)
-        done_sims += sims
+        done_sims += mc._last_sims_run
         evals += mc.unique_evals
+        rows += mc.sample_rows + 1
+        distinct += mc.distinct_rows + 1
         moves += 1
         b.push(max(vc.items(), key=lambda kv: kv[1])[0])
         if b.is_game_over() or time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     return {"value": done_sims / dt, "unit": "sims/s", "cores": cores, "kind": "port",
-            "sample": f"{moves} move(s) x {sims} sims of one game from the start position in {dt:.1f}s ({evals} NN calls of <=96 rows, fp32 torch CPU); "
-                      f"positions/s = {moves / dt:.4f}",
-            "positions_per_s": moves / dt}
+            "sample": f"{moves} move(s) x ~{sims} sims of one game from the start position in {dt:.1f}s, as shipped (jitter, entropy / Dirichlet noise, "
+                      f"playout cap): {evals} NN calls, {rows} rows evaluated (one per collected sample, duplicates included) of which {distinct} "
+                      f"distinct leaves, fp32 torch CPU; positions/s = {moves / dt:.4f}",
+            "positions_per_s": moves / dt, "nn_rows_per_s": rows / dt, "distinct_rows_per_s": distinct / dt}
 
 
 def reference_arm(args):
@@ -275,5 +352,6 @@ def reference_arm(args):
                        "games_per_gpu": args.games, "sims_per_move": args.sims, "inference_batch_size": int(getattr(args, "leaf_batch", 96)),
                        "sample": "the reference's CPU path (RefMCTS + fp32 torch forward on all host cores) on ONE game of that workload, "
                                  "bounded to a few moves; games are independent, so sims/s per game is the reference's rate for any number of games"},
-            "positions_per_s": base["positions_per_s"], "cpu_baseline": base,
+            "positions_per_s": base["positions_per_s"], "nn_rows_per_s": base["nn_rows_per_s"], "distinct_rows_per_s": base["distinct_rows_per_s"],
+            "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -856,6 +856,34 @@ M0_HD bool is_insufficient_material(const Position& p) {
   return has_insufficient_material(p, 1) && has_insufficient_material(p, 0);
 }
 
+// ---- synthetic positions: seeded random playouts -----------------------------------------------------
+// Position i of a batch = plies_i = hash(seed, i) % (max_plies + 1) uniformly random legal moves from the standard start
+// position (stops early when no legal move exists or material is insufficient): azchess/utils/board.py:7-38 (random_board) as a
+// pure function of (seed, i), so that the device kernel and the host check (tests/hostcheck) produce the same positions.
+M0_HD Position start_position_std() {
+  Position p;
+  p.pawns = 0x00FF00000000FF00ull; p.knights = 0x4200000000000042ull; p.bishops = 0x2400000000000024ull;
+  p.rooks = 0x8100000000000081ull; p.queens = 0x0800000000000008ull; p.kings = 0x1000000000000010ull;
+  p.occ_w = 0x000000000000FFFFull; p.occ_b = 0xFFFF000000000000ull;
+  p.state = pack_state(1, CR_WK | CR_WQ | CR_BK | CR_BQ, EP_NONE, 0, 1);
+  return p;
+}
+M0_HD Position random_playout_position(u64 seed, int i, int max_plies) {
+  Position p = start_position_std();
+  u64 rng = mix64(seed ^ (0x9E3779B97F4A7C15ull * (u64)(i + 1)));
+  int plies = (int)(rng % (u64)(max_plies + 1));
+  Move mv[MAX_MOVES];
+  for (int k = 0; k < plies; ++k) {
+    if (is_insufficient_material(p)) break;
+    int m = generate_legal_moves(p, mv);
+    if (m == 0) break;
+    if (m > MAX_MOVES) m = MAX_MOVES;
+    rng = mix64(rng + 0x9E3779B97F4A7C15ull);
+    push_move(p, mv[(int)(rng % (u64)m)]);
+  }
+  return p;
+}
+
 // ---- board planes: azchess/encoding.py:11-46 -------------------------------------------------------
 // plane p (0..11) bitboard in python-chess orientation; value of the 7 constant planes 12..18
 M0_HD u64 piece_plane_bb(const Position& p, int plane) {

@@ -50,22 +50,7 @@ __global__ void pack_positions_kernel(const u64* __restrict__ raw, int n, u64* _
 __global__ void random_playouts_kernel(u64* __restrict__ pos, int n, u64 seed, int max_plies) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Position p;
-  p.pawns = 0x00FF00000000FF00ull; p.knights = 0x4200000000000042ull; p.bishops = 0x2400000000000024ull;
-  p.rooks = 0x8100000000000081ull; p.queens = 0x0800000000000008ull; p.kings = 0x1000000000000010ull;
-  p.occ_w = 0x000000000000FFFFull; p.occ_b = 0xFFFF000000000000ull;
-  p.state = pack_state(1, CR_WK | CR_WQ | CR_BK | CR_BQ, EP_NONE, 0, 1);
-  u64 rng = mix64(seed ^ (0x9E3779B97F4A7C15ull * (u64)(i + 1)));
-  int plies = (int)(rng % (u64)(max_plies + 1));
-  Move mv[MAX_MOVES];
-  for (int k = 0; k < plies; ++k) {
-    if (is_insufficient_material(p)) break;
-    int m = generate_legal_moves(p, mv);
-    if (m == 0) break;
-    if (m > MAX_MOVES) m = MAX_MOVES;
-    rng = mix64(rng + 0x9E3779B97F4A7C15ull);
-    push_move(p, mv[(int)(rng % (u64)m)]);
-  }
+  const Position p = random_playout_position(seed, i, max_plies);
   store_position(pos + (size_t)i * POSITION_WORDS, p);
 }
 

@@ -145,8 +145,21 @@ __device__ __forceinline__ void warp_expand(const EngineView& E, const SearchPar
     }
   } else {
     // np.any(np.isnan(logits)) or np.any(np.isinf(logits)) over the whole vector (mcts.py:147)
+    // (an exponent field of all ones; 16-byte loads, four in flight per lane: the row is 18.7 KB of streaming reads)
     bool bad = false;
-    for (int i = lane; i < POLICY_SIZE; i += 32) bad |= !isfinite(lg[i]);
+    if ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) {
+      const uint4* lg4 = reinterpret_cast<const uint4*>(lg);
+      u32 acc = 0;
+#pragma unroll 4
+      for (int i = lane; i < POLICY_SIZE / 4; i += 32) {
+        const uint4 v = __ldg(lg4 + i);
+        acc |= (u32)((v.x & 0x7F800000u) == 0x7F800000u) | (u32)((v.y & 0x7F800000u) == 0x7F800000u) |
+               (u32)((v.z & 0x7F800000u) == 0x7F800000u) | (u32)((v.w & 0x7F800000u) == 0x7F800000u);
+      }
+      bad = acc != 0;
+    } else {
+      for (int i = lane; i < POLICY_SIZE; i += 32) bad |= !isfinite(lg[i]);
+    }
     bad = __any_sync(FULL, bad);
     if (bad) {
       for (int j = lane; j < k; j += 32) s_p[j] = uniform;

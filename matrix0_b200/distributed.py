@@ -19,12 +19,30 @@ def rank_seed(seed: int, rank: int) -> int:
 
 
 def broadcast_parameters(params: Dict[str, "object"], src: int = 0) -> None:
-    """Make every rank hold rank `src`'s parameters (one broadcast per tensor, sorted by name for a fixed order)."""
+    """Make every rank hold rank `src`'s parameters: ONE broadcast of one packed buffer (the reference loads one checkpoint per phase,
+    orchestrator.py:373-388).  Tensors are flattened in name order into a float32 buffer on the source rank and copied back in place."""
+    import torch
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return
-    for name in sorted(params):
-        dist.broadcast(params[name], src=src)
+    names = sorted(params)
+    if not names:
+        return
+    ref = params[names[0]]
+    total = sum(int(params[n].numel()) for n in names)
+    buf = torch.empty((total,), dtype=torch.float32, device=ref.device)
+    if dist.get_rank() == src:
+        off = 0
+        for n in names:
+            k = int(params[n].numel())
+            buf[off:off + k].copy_(params[n].reshape(-1).to(torch.float32))
+            off += k
+    dist.broadcast(buf, src=src)
+    off = 0
+    for n in names:
+        k = int(params[n].numel())
+        params[n].copy_(buf[off:off + k].reshape(params[n].shape).to(params[n].dtype))
+        off += k
 
 
 def reduce_scalars(values: Iterable[float], op: str = "sum", device=None):

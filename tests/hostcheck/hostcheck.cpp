@@ -47,6 +47,10 @@ void hc_key(const uint64_t* pos9, uint64_t* key2) {
   Key128 k = position_key(load(pos9));
   key2[0] = k.lo; key2[1] = k.hi;
 }
+// the positions m0_random_playouts(seed, max_plies) writes, computed on the host (same function as the device kernel)
+void hc_random_playouts(uint64_t* out, int first, int n, uint64_t seed, int max_plies) {
+  for (int i = 0; i < n; ++i) store(random_playout_position(seed, first + i, max_plies), out + (size_t)i * 9);
+}
 int hc_has_legal_ep(const uint64_t* pos9) { return has_legal_ep(load(pos9)); }
 int hc_insufficient(const uint64_t* pos9) { return is_insufficient_material(load(pos9)); }
 void hc_planes(const uint64_t* pos9, float* out) {

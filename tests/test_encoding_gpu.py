@@ -154,3 +154,41 @@ def test_set_kernel_edge_positions(enc):
     assert torch.equal(m2.sum(dim=1, dtype=torch.int32), cnt)
     m3 = enc.encode_positions_device(pos, False, True, False)[1]              # mask alone
     assert torch.equal(m3, m2)
+
+
+def test_config2_full_size_against_oracle_digests(enc, golden_dir):
+    """BASELINE configs[1] as written: the 1 Mi positions of the bench (m0_random_playouts(seed 1234, <= 120 plies); 1,019,010 of them
+    distinct).  (a) the device playouts equal the host build of the same function on all 256 chunks (SHA-256 of the packed records);
+    (b) the half-warp set kernel (planes + mask, the benchmarked one) and the ordered thread-per-position kernel agree byte for byte on
+    all 1 Mi positions; (c) planes, mask, ordered move list, policy indices and counts of the first 131,072 positions hash to the digests
+    the ORACLE produced in the build container (tests/golden/make_encode_digest.py)."""
+    import hashlib
+    import json
+    import torch
+    from matrix0_b200 import _native
+    d = json.load(open(os.path.join(golden_dir, "encode_digest.json")))
+    n, chunk = d["n_total"], d["chunk"]
+    pos = torch.empty((n, 9), dtype=torch.int64, device="cuda")
+    _native.check(_native.lib().m0_random_playouts(pos.data_ptr(), n, d["seed"], d["max_plies"], _native.current_stream()), "m0_random_playouts")
+    ph = pos.cpu().numpy()
+    for c in range(n // chunk):
+        assert hashlib.sha256(ph[c * chunk:(c + 1) * chunk].tobytes()).hexdigest() == d["position_sha256"][c], c
+    assert len(np.unique(ph.view([("", ph.dtype)] * 9))) == d["distinct_positions"] >= 1_000_000
+    planes, mask, _, _, _ = enc.encode_positions_device(pos, True, True, False)            # the set kernel (the bench's kernel)
+    no = d["oracle_chunks"] * chunk
+    for lo in range(0, n, 1 << 18):                                                        # ordered kernel in slices of 256 Ki
+        hi = min(n, lo + (1 << 18))
+        p2, m2, mv, ix, cnt = enc.encode_positions_device(pos[lo:hi], True, True, True)
+        assert torch.equal(p2, planes[lo:hi]) and torch.equal(m2, mask[lo:hi]), lo
+        assert torch.equal(m2.sum(dim=1, dtype=torch.int32), cnt)
+        if lo < no:
+            k = min(hi, no) - lo
+            ar = torch.arange(256, device="cuda")[None, :] < cnt[:k, None]                 # entries past the count are unspecified
+            mvh = torch.where(ar, mv[:k], torch.zeros_like(mv[:k])).cpu().numpy().view(np.uint16)
+            ixh = torch.where(ar, ix[:k], torch.zeros_like(ix[:k])).cpu().numpy().view(np.uint16)
+            pl, mk, cn = planes[lo:lo + k].cpu().numpy(), mask[lo:lo + k].cpu().numpy(), cnt[:k].cpu().numpy()
+            for c in range(k // chunk):
+                gc = lo // chunk + c
+                s = slice(c * chunk, (c + 1) * chunk)
+                for name, arr in (("planes", pl[s]), ("mask", mk[s]), ("moves", mvh[s]), ("idx", ixh[s]), ("counts", cn[s])):
+                    assert hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest() == d["oracle_sha256"][name][gc], (name, gc)

@@ -132,3 +132,16 @@ def test_legal_set_equals_ordered_generator(hc):
                                       ctypes.byref(bad), first.ctypes.data_as(U64P))
         assert bad.value == 0, (f, [hex(int(x)) for x in first])
     assert seen > 300_000
+
+
+def test_host_playouts_match_committed_position_digests(hc, golden_dir):
+    """The host build of random_playout_position reproduces the committed digests of the first chunks (the GPU test checks all 256
+    against the device kernel)."""
+    import hashlib
+    import json
+    d = json.load(open(os.path.join(golden_dir, "encode_digest.json")))
+    n = 4 * d["chunk"]
+    out = np.zeros((n, 9), dtype=np.uint64)
+    hc.hc_random_playouts(out.ctypes.data_as(U64P), 0, n, ctypes.c_uint64(d["seed"]), d["max_plies"])
+    for c in range(4):
+        assert hashlib.sha256(out[c * d["chunk"]:(c + 1) * d["chunk"]].tobytes()).hexdigest() == d["position_sha256"][c]

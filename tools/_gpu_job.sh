@@ -1,4 +1,7 @@
 set -x
-mkdir -p gpurun_out/r2c
-python -m pytest tests/test_gameloop_gpu.py tests/test_selfplay_gpu.py tests/test_nn_gpu.py -q 2>&1 | tail -60 > gpurun_out/r2c/pytest.log
-tail -5 gpurun_out/r2c/pytest.log
+mkdir -p gpurun_out/r2d
+python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r2d/pytest.log
+tail -3 gpurun_out/r2d/pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2d/bench.json 2> gpurun_out/r2d/bench.err
+tail -c 600 gpurun_out/r2d/bench.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2d/bench_ref.json 2> gpurun_out/r2d/bench_ref.err
