@@ -95,6 +95,11 @@ typedef struct m0_search_config {
   int raw_logit_priors;    /* 1 = the reference's direct-model path (no inference backend, legal_softmax): non-root leaves are expanded by
                               Node._expand_with_legal_priors on the RAW logits of the legal moves (mcts.py:697-703, :227-256) */
   double min_child_prior;  /* drop children whose prior is below this (mcts.py:817-818); 0 = off */
+  double virtual_loss;     /* MCTSConfig.virtual_loss (mcts.py:75) */
+  int virtual_loss_on;     /* 1 = throughput mode: the in-flight marking of MCTS._select (inflight_counts, mcts.py:889-890, :922-923) is applied
+                              within every mini-batch of m0_search_select_multi, so its simulations spread over distinct leaves.  The reference
+                              ships this code but none of its callers passes inflight_counts: 0 reproduces the reference. */
+  int reserved;
 } m0_search_config;
 
 int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, int max_depth, int hist_cap, m0_engine** out);
@@ -129,7 +134,7 @@ int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double*
 /* ---- the mini-batch as shipped (selection_jitter in force, config.yaml:138): every simulation of a batch selects with its own
  * random.random() draws (mcts.py:893-897), so a batch holds up to batch_n different leaves; duplicated leaves share a network row.
  * Sequence per mini-batch: m0_search_select_multi -> m0_search_multi_encode -> evaluator -> m0_search_expand_backup_multi. */
-int m0_search_multi_enable(m0_engine* e, int samples_per_batch);
+int m0_search_multi_enable(m0_engine* e, int samples_per_batch, int virtual_loss);
 /* caller-supplied draws (parity with the reference under a seeded RNG): d_jitter float64[G][jitter_stride] = random.random() values in
  * consumption order, d_normal float64[G][normal_stride] = np.random.normal(0, 0.1) values of the entropy noise (mcts.py:181);
  * NULL = device generator.  Status bit 16 is set for a game that exhausts a stream. */

@@ -50,7 +50,7 @@ SIGNATURES = {
     "m0_search_pending": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_search_pending_counts": (c_int, [c_void_p, c_void_p, c_void_p]),
     "m0_search_result": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "m0_search_multi_enable": (c_int, [c_void_p, c_int]),
+    "m0_search_multi_enable": (c_int, [c_void_p, c_int, c_int]),
     "m0_search_set_streams": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "m0_search_select_multi": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_search_multi_encode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -86,6 +86,7 @@ class SearchConfigStruct(ctypes.Structure):
         ("enable_entropy_noise", c_int), ("value_from_white", c_int), ("cpuct_len", c_int),
         ("seed", c_uint64), ("cpuct_by_depth", ctypes.POINTER(c_double)),
         ("max_children", c_int), ("raw_logit_priors", c_int), ("min_child_prior", c_double),
+        ("virtual_loss", c_double), ("virtual_loss_on", c_int), ("reserved", c_int),
     ]
 
 

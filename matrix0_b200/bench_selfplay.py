@@ -234,19 +234,21 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
         torch.cuda.empty_cache()
         out["as_shipped"] = bench_as_shipped(net, cfg, G, local, D.rank_seed(4321, rank), precision, stream)
         if world == 1:
+            out["throughput_virtual_loss"] = bench_as_shipped(net, cfg, min(G, 512), local, D.rank_seed(999, rank), precision, stream, moves=1,
+                                                              search_mode="virtual_loss")
             out["forward_sweep"] = forward_sweep(net, precision, stream, load_peaks)
     if rank == 0:
         out["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
     return out
 
 
-def bench_as_shipped(net, cfg, G, local, seed, precision, stream, moves=2):
+def bench_as_shipped(net, cfg, G, local, seed, precision, stream, moves=2, search_mode="as_shipped"):
     """The reference's search AS SHIPPED (selection_jitter 0.05 drawn per child per simulation, entropy noise on near-uniform priors,
     Dirichlet noise, playout-cap randomisation): every mini-batch collects up to 96 samples per game, the DISTINCT leaves of all games are
     evaluated in compact batches.  Timed with CUDA events over `moves` whole moves after one warm-up move."""
     import torch
     from matrix0_b200.selfplay import SelfPlayEngine
-    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=seed, precision=precision, search_mode="as_shipped")
+    sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=seed, precision=precision, search_mode=search_mode)
     sp.start()
     sp.play_move()
     torch.cuda.synchronize()
@@ -262,8 +264,13 @@ def bench_as_shipped(net, cfg, G, local, seed, precision, stream, moves=2):
     d = {k: c1[k] - c0[k] for k in c1}
     sp.check_status()
     rows = d["nn_evals"] + G * moves          # distinct leaves + the root evaluation of every move
-    out = {"mode": "as shipped: per-simulation selection jitter (mcts.py:893-897), entropy noise (:170-186), Dirichlet noise, playout-cap "
-                   "randomisation; one evaluator row per DISTINCT leaf of a mini-batch, fresh tree per move",
+    label = ("as shipped: per-simulation selection jitter (mcts.py:893-897), entropy noise (:170-186), Dirichlet noise, playout-cap "
+             "randomisation; one evaluator row per DISTINCT leaf of a mini-batch, fresh tree per move")
+    if search_mode == "virtual_loss":
+        label = ("throughput mode: as shipped PLUS the in-flight marking of MCTS._select (virtual loss, mcts.py:889-890 / :922-923, code the "
+                 "reference ships but never activates) inside every mini-batch: the simulations of a batch spread over distinct leaves, "
+                 "(almost) every simulation evaluates its own row")
+    out = {"mode": label,
            "games_per_gpu": G, "moves_timed": moves, "seconds": secs, "sims_per_s": d["sims"] / secs, "positions_per_s": d["positions_played"] / secs,
            "nn_rows_per_s": rows / secs, "padded_rows_per_s": (sp.nn_rows_padded - p0 + G * moves) / secs,
            "samples_per_s": d["leaf_samples"] / secs, "distinct_rows_per_sample": d["nn_evals"] / max(1, d["leaf_samples"]),

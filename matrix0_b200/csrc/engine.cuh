@@ -36,6 +36,10 @@ struct SearchParams {
   int max_children;         // _prune_children, mcts.py:806-826 (0 = off)
   int raw_logit_priors;     // non-root leaves get logits[idx] / sum(logits[idx]) (_expand_with_legal_priors, mcts.py:227-256, :697-703)
   double min_child_prior;   // mcts.py:817-818 (0 = off)
+  double virtual_loss;      // mcts.py:889-890, applied per in-flight selection of an edge when virtual_loss_on
+  int virtual_loss_on;      // the reference's in-flight marking (_select's inflight_counts, :889-890 / :922-923), which no caller of the
+                            // reference passes: switched on it spreads the simulations of a mini-batch over distinct leaves
+  int pad_;
 };
 
 struct EngineView {
@@ -99,6 +103,7 @@ struct EngineView {
   int* ml_leaf_first;     // [G][ml_cap] leaf slot -> first sample that reached it
   u64* ml_leaf_pos;       // [G][ml_cap][9]
   int* ml_row_base;       // [G + 1] exclusive prefix of ml_n_leaves: compact network rows
+  u16* node_inflight;     // [G][max_nodes] in-flight selections of an edge child within the current mini-batch (virtual loss)
 };
 
 static constexpr u32 MOVE_NONE = 0xFFFFu;

@@ -146,6 +146,8 @@ int m0_engine_configure(m0_engine* e, const m0_search_config* c, void* stream) {
   p.max_children = c->max_children > 0 ? c->max_children : 0;
   p.min_child_prior = c->min_child_prior > 0.0 ? c->min_child_prior : 0.0;
   p.raw_logit_priors = c->raw_logit_priors ? 1 : 0;
+  p.virtual_loss = c->virtual_loss;
+  p.virtual_loss_on = (c->virtual_loss_on && c->virtual_loss > 0.0) ? 1 : 0;
   if (p.entropy_noise && !p.legal_softmax) {
     m0_set_error("m0_engine_configure: enable_entropy_noise with legal_softmax = false (noise over all 4672 entries, mcts.py:164-186) is not "
                  "implemented on the device; set legal_softmax = true, enable_entropy_noise = false, or deterministic = 1");
@@ -253,9 +255,14 @@ int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double*
 }
 
 // ---- the reference's mini-batch as shipped: per-simulation jitter, distinct leaves (tree_multi_kernels.cu) ---------------------
-// Allocates the per-game sample / leaf tables for mini-batches of up to `samples_per_batch` simulations (inference_batch_size).
-int m0_search_multi_enable(m0_engine* e, int samples_per_batch) {
+// Allocates the per-game sample / leaf tables for mini-batches of up to `samples_per_batch` simulations (inference_batch_size);
+// virtual_loss != 0 also allocates the per-node in-flight counters of the virtual-loss mode (m0_search_config.virtual_loss_on).
+int m0_search_multi_enable(m0_engine* e, int samples_per_batch, int virtual_loss) {
   if (!e || samples_per_batch <= 0 || samples_per_batch > 4096) { m0_set_error("m0_search_multi_enable: invalid argument"); return M0_ERR_ARG; }
+  if (virtual_loss && !e->v.node_inflight) {
+    M0_CUDA_TRY(cudaSetDevice(e->device));
+    TRY(dev_alloc(e, &e->v.node_inflight, (size_t)e->v.G * e->v.max_nodes));
+  }
   if (e->v.ml_cap >= samples_per_batch) return M0_OK;
   if (e->v.ml_cap > 0) { m0_set_error("m0_search_multi_enable: already enabled with a smaller batch (%d)", e->v.ml_cap); return M0_ERR_STATE; }
   M0_CUDA_TRY(cudaSetDevice(e->device));

@@ -17,6 +17,9 @@ struct m0_search_config {
   int max_children;              // _prune_children (mcts.py:806-826), 0 = off
   int raw_logit_priors;          // SURVEY Q3 switch: the direct-model path's _expand_with_legal_priors(logits[idx]) for non-root leaves
   double min_child_prior;        // 0 = off
+  double virtual_loss;           // MCTSConfig.virtual_loss (mcts.py:75)
+  int virtual_loss_on;           // 1 = apply the reference's in-flight marking inside a mini-batch (its own callers never do)
+  int reserved;
 };
 
 struct m0_engine {

@@ -49,6 +49,13 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
   }
   int n_samples = 0, n_leaves = 0;
   if (lane == 0) path[0] = root;
+  const bool vl = P.virtual_loss_on && E.node_inflight != nullptr && P.virtual_loss > 0.0;
+  u16* inflight = vl ? E.node_inflight + nb : nullptr;
+  if (vl) {   // inflight_counts = {} for this mini-batch
+    const int cnt = E.node_count[g];
+    for (int i = lane; i < cnt; i += 32) inflight[i] = 0;
+    __syncwarp();
+  }
   for (int sim = 0; sim < batch_n; ++sim) {
     Position pos = root_pos;
     int node = root, depth = 0;
@@ -80,6 +87,7 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
           u32 mv = E.node_mv[c] & 0xFFFFu;
           if ((mv & 63u) == ((prev_mv >> 6) & 63u) && ((mv >> 6) & 63u) == (prev_mv & 63u)) s = d_sub(s, 0.01);
         }
+        if (vl) s = d_sub(s, d_mul((double)inflight[fc + j], P.virtual_loss));                                   // mcts.py:889-890
         if (P.jitter_on) s = d_add(s, d_mul(d_sub(draw_jitter_uniform(E, P, g, jcur, j), 0.5), P.jitter));   // mcts.py:893-897
         if (s > best_s) { best_s = s; best_j = j; }
       }
@@ -113,9 +121,11 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
         pirrev[depth] = irrev ? 1 : 0;
         pkey[depth + 1] = cur_key;
         path[depth + 1] = nxt;
+        if (vl) inflight[child] += 1;   // inflight_counts[best_child] += 1 (the EDGE child, mcts.py:922-923)
       }
       depth++;
       node = nxt;
+      if (vl) __syncwarp();
     }
     __syncwarp();
     c_path += depth + 1;

@@ -87,7 +87,7 @@ class SearchEngine:
         return _native.current_stream()
 
     # ---- configuration ---------------------------------------------------------------------------
-    def configure(self, cfg, deterministic: bool, seed: int = 0, raw_logit_priors: bool = False) -> None:
+    def configure(self, cfg, deterministic: bool, seed: int = 0, raw_logit_priors: bool = False, virtual_loss: bool = False) -> None:
         """``raw_logit_priors``: SURVEY Q3 switch -- the reference's direct-model path (``MCTS(cfg, model)`` without an inference
         backend and ``legal_softmax``) expands non-root leaves from the raw legal logits (mcts.py:697-703)."""
         table = np.ascontiguousarray(cpuct_table(cfg, self.max_depth + 1))
@@ -108,6 +108,8 @@ class SearchEngine:
         s.max_children = int(getattr(cfg, "max_children", 0) or 0)
         s.min_child_prior = float(getattr(cfg, "min_child_prior", 0.0) or 0.0)
         s.raw_logit_priors = 1 if raw_logit_priors else 0
+        s.virtual_loss = float(getattr(cfg, "virtual_loss", 1.0))
+        s.virtual_loss_on = 1 if virtual_loss else 0
         _native.check(self._lib.m0_engine_configure(self._h, ctypes.byref(s), self._stream()), "m0_engine_configure")
 
     # ---- games -----------------------------------------------------------------------------------
@@ -184,9 +186,9 @@ class SearchEngine:
                                                  self.res_root_n.data_ptr(), self._stream()), "m0_search_result")
 
     # ---- the mini-batch as shipped: per-simulation jitter, distinct leaves (csrc/tree_multi_kernels.cu) -------------
-    def enable_multi(self, samples_per_batch: int) -> None:
+    def enable_multi(self, samples_per_batch: int, virtual_loss: bool = False) -> None:
         import torch
-        _native.check(self._lib.m0_search_multi_enable(self._h, int(samples_per_batch)), "m0_search_multi_enable")
+        _native.check(self._lib.m0_search_multi_enable(self._h, int(samples_per_batch), 1 if virtual_loss else 0), "m0_search_multi_enable")
         self.ml_cap = int(samples_per_batch)
         self.row_base = torch.zeros((self.G + 1,), dtype=torch.int32, device=self.device)
         self.n_samples = torch.zeros((self.G,), dtype=torch.int32, device=self.device)

@@ -101,7 +101,7 @@ class _RootView:
 class MCTS:
     def __init__(self, model_or_cfg, cfg_or_model, device: str = "cuda", inference_backend=None, num_threads: int = None,
                  *, deterministic: Optional[bool] = None, max_nodes: Optional[int] = None, seed: Optional[int] = None,
-                 direct_model_priors: Optional[bool] = None):
+                 direct_model_priors: Optional[bool] = None, virtual_loss_batches: bool = False):
         # both argument orders, mcts.py:270-277
         if isinstance(model_or_cfg, MCTSConfig):
             cfg, model = model_or_cfg, cfg_or_model
@@ -126,15 +126,18 @@ class MCTS:
             direct_model_priors = os.environ.get("MATRIX0_DIRECT_MODEL_PRIORS", "") in ("1", "true", "yes")
         # SURVEY Q3 switch: the reference WITHOUT an inference backend expands non-root leaves from raw logits (mcts.py:697-703)
         self.direct_model_priors = bool(direct_model_priors) and bool(getattr(cfg, "legal_softmax", False))
+        # throughput mode: the reference's in-flight marking (mcts.py:889-890, :922-923 -- code it ships but never calls with a dict,
+        # SURVEY Q2b) spreads the simulations of a mini-batch over distinct leaves, each with its own evaluator row
+        self.virtual_loss_batches = bool(virtual_loss_batches) and not self.deterministic
         self._max_batch = int(getattr(cfg, "inference_batch_size", None) or getattr(cfg, "simulation_batch_size", 96))
         if self._max_batch <= 0:
             self._max_batch = 96
         with torch.cuda.device(dev):
             self._engine = SearchEngine(1, max_nodes=max_nodes, device=dev.index if dev.index is not None else torch.cuda.current_device())
             self._engine.configure(cfg, self.deterministic, seed if seed is not None else random.getrandbits(63),
-                                   raw_logit_priors=self.direct_model_priors)
+                                   raw_logit_priors=self.direct_model_priors, virtual_loss=self.virtual_loss_batches)
             if not self.deterministic:
-                self._engine.enable_multi(self._max_batch)
+                self._engine.enable_multi(self._max_batch, virtual_loss=self.virtual_loss_batches)
         rows = 1 if self.deterministic else self._max_batch
         self._logits = torch.zeros((rows, POLICY_SIZE), dtype=torch.float32, device=dev)
         self._values = torch.zeros((rows,), dtype=torch.float32, device=dev)

@@ -92,11 +92,15 @@ class SelfPlayEngine:
                           when its jitter is neutralised (SURVEY Q1; ``deterministic=True`` is bit-exact), and the throughput mode;
         ``"as_shipped"``  the reference with ``selection_jitter`` in force (config.yaml:138): every simulation of a mini-batch
                           selects with its own jitter draws (mcts.py:893-897), the distinct leaves of all games are compacted into
-                          evaluator batches of ``forward_rows`` rows, samples are expanded / backed up in collection order."""
+                          evaluator batches of ``forward_rows`` rows, samples are expanded / backed up in collection order;
+        ``"virtual_loss"`` throughput mode: ``as_shipped`` plus the reference's in-flight marking (``_select``'s ``inflight_counts``,
+                          mcts.py:889-890 / :922-923 -- code the reference ships but never activates) inside every mini-batch,
+                          so the simulations of a batch spread over distinct leaves and (almost) every simulation evaluates its own row."""
         import torch
-        if search_mode not in ("collapsed", "as_shipped"):
-            raise ValueError(f"search_mode must be 'collapsed' or 'as_shipped', got {search_mode!r}")
-        self.search_mode = search_mode
+        if search_mode not in ("collapsed", "as_shipped", "virtual_loss"):
+            raise ValueError(f"search_mode must be 'collapsed', 'as_shipped' or 'virtual_loss', got {search_mode!r}")
+        self.virtual_loss = search_mode == "virtual_loss"
+        self.search_mode = search_mode = "as_shipped" if self.virtual_loss else search_mode
         self.model = model
         self.cfg_dict = cfg_dict
         self.mcfg = resolve_mcts_config(cfg_dict)
@@ -116,9 +120,9 @@ class SelfPlayEngine:
         with torch.cuda.device(self.device):
             self.engine = SearchEngine(self.G, max_nodes=max_nodes, max_depth=128,
                                        hist_cap=int(self.sp.get("max_game_len", 200)) + opening + 64, device=self.device_index)
-            self.engine.configure(self.mcfg, deterministic, seed)
+            self.engine.configure(self.mcfg, deterministic, seed, virtual_loss=self.virtual_loss)
             if search_mode == "as_shipped":
-                self.engine.enable_multi(bs)
+                self.engine.enable_multi(bs, virtual_loss=self.virtual_loss)
                 self.forward_rows = max(bs, min(int(forward_rows), self.G * bs))
                 self.forward_rows += self.forward_rows & 1
                 # evaluator batch sizes: full chunks of forward_rows rows, the tail chunk in the smallest size that holds it

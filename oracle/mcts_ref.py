@@ -52,6 +52,7 @@ class RefConfig:
         self.enable_entropy_noise = True
         self.max_children = 0
         self.min_child_prior = 0.0
+        self.virtual_loss = 1.0
         for k, v in kw.items():
             if hasattr(self, k):
                 setattr(self, k, v)
@@ -133,7 +134,7 @@ def expand(node: RefNode, board, logits: np.ndarray, legal_only: bool, allow_noi
 
 class RefMCTS:
     def __init__(self, cfg: RefConfig, backend, jitter_value: Optional[float] = 0.5, jitter_stream=None, normal_stream=None,
-                 direct_model: bool = False):
+                 direct_model: bool = False, virtual_loss: bool = False):
         """backend: object with infer_np; jitter_value: constant standing in for random.random()
         (None = call random.random() like the reference).  jitter_stream / normal_stream: 1-D arrays consumed in order
         instead of random.random() / np.random.normal(0, 0.1) (the draws a seeded reference run would make).
@@ -142,6 +143,9 @@ class RefMCTS:
         self.cfg, self.backend, self.jv = cfg, backend, jitter_value
         self.jitter_stream, self.normal_stream, self.jit_used, self.nrm_used = jitter_stream, normal_stream, 0, 0
         self.direct_model = direct_model
+        # True: _select is called with an inflight_counts dict per mini-batch (mcts.py:851, :889-890, :922-923).  The reference ships that
+        # code but _collect_leaf_position never passes the dict (:745): this is the engine's throughput mode, not reference behaviour
+        self.virtual_loss = virtual_loss
         self.min_gap = float("inf")   # smallest top-2 score gap over all selections (diagnostic for tolerance-limited parity)
         self.tt: "OrderedDict[tuple, RefNode]" = OrderedDict()
         self.nn_cache: Dict[tuple, tuple] = {}
@@ -227,7 +231,7 @@ class RefMCTS:
             b2.push(m)
             self.tt[b2._transposition_key()] = child
 
-    def _select(self, b, root: RefNode):  # mcts.py:851-925 (inflight_counts is never passed: Q1)
+    def _select(self, b, root: RefNode, inflight=None):  # mcts.py:851-925 (inflight_counts is never passed by the reference: Q1)
         cfg = self.cfg
         node, path = root, [root]
         while node.expanded:
@@ -243,6 +247,8 @@ class RefMCTS:
                     prev = path[-1].move
                     if child.move.from_square == prev.to_square and child.move.to_square == prev.from_square:
                         s -= 0.01
+                if inflight is not None and cfg.virtual_loss > 0.0:  # :889-890
+                    s -= float(inflight.get(child, 0)) * float(cfg.virtual_loss)
                 s += (self._rand() - 0.5) * (cfg.selection_jitter if cfg.selection_jitter > 0 else 0.001)
                 if s > best_s:
                     second_s, best_s, best = best_s, s, child
@@ -255,6 +261,8 @@ class RefMCTS:
             b.push(best.move)
             node = self.tt.get(b._transposition_key()) or best
             path.append(node)
+            if inflight is not None:  # :922-923
+                inflight[best] = inflight.get(best, 0) + 1
         return node, path, b
 
     # -- MCTS.run: mcts.py:318-512 -----------------------------------------------------------------
@@ -298,8 +306,9 @@ class RefMCTS:
         while done < sims:
             batch_n = min(bs, sims - done)
             samples = []
+            inflight = {} if self.virtual_loss else None
             for _ in range(batch_n):
-                node, path, lb = self._select(board.copy(), root)
+                node, path, lb = self._select(board.copy(), root, inflight)
                 if lb.is_game_over():
                     self._backprop(path, self._terminal_value(lb))
                 else:

@@ -4,6 +4,11 @@ pruning (:806-826) and the direct-model path (:697-703), fed SEEDED streams of r
 
 Run in the build container only (needs /root/reference):  python tests/golden/make_stochastic_golden.py
 Output: tests/golden/mcts_stochastic_golden.json
+        python tests/golden/make_stochastic_golden.py vl   ->  tests/golden/mcts_vl_golden.json: the same with the reference's
+        in-flight marking switched ON inside every mini-batch (the engine's throughput mode).  The reference ships that code in
+        ``MCTS._select`` (inflight_counts, mcts.py:889-890, :922-923) but ``_collect_leaf_position`` never passes the dict (:745); the
+        generator subclasses the reference ``MCTS`` and overrides ONLY ``_collect_leaf_position`` to pass one dict per mini-batch, so the
+        selection itself is still the unmodified ``_select``.
 
 Streams (the GPU test regenerates them from the seeds): jitter = ``random.Random(seed).random()`` values, normal =
 ``np.random.RandomState(seed).normal(0, 0.1, n)``; the generator patches ``random.random`` / ``np.random.normal`` of the reference
@@ -80,6 +85,7 @@ def main():
     import logging
     import torch
     logging.disable(logging.CRITICAL)
+    VL = len(sys.argv) > 1 and sys.argv[1] == "vl"
     ref = refload.load_reference("mcts")
     import chess
     from oracle.backends import HashBackend
@@ -106,6 +112,19 @@ def main():
             p, v = self.be.infer_np(x.numpy())
             return torch.from_numpy(p), torch.from_numpy(v)
 
+    class VirtualLossMCTS(ref.MCTS):
+        """Reference MCTS whose mini-batches call the UNMODIFIED _select with an inflight_counts dict (one per mini-batch)."""
+
+        def _collect_leaf_position(self, board, root, leaf_samples, append_lock):
+            if getattr(self, "_vl_list", None) is not leaf_samples:     # a new leaf_samples list = a new mini-batch (mcts.py:538)
+                self._vl_list, self._vl = leaf_samples, {}
+            node, path, leaf_board = self._select(board, root, self._vl)
+            if leaf_board.is_game_over():                                 # mcts.py:747-751
+                self._backpropagate(path, self._terminal_value(leaf_board))
+                return
+            leaf_samples.append({"board": leaf_board, "node": node, "path": list(path)})
+
+    MCTSClass = VirtualLossMCTS if VL else ref.MCTS
     rng = random.Random(99)
     boards = [(f, []) for f in FENS]
     for _ in range(14):     # positions along random playouts (with their move stacks: repetition history)
@@ -118,6 +137,14 @@ def main():
             boards.append((chess.STARTING_FEN, [m.uci() for m in b.move_stack]))
 
     plan = []
+    if VL:
+        CFGS["selfplay_vl"] = dict(CFGS["selfplay"], virtual_loss=1.0)
+        CFGS["vl_small"] = dict(CFGS["selfplay_b32"], virtual_loss=0.3, enable_entropy_noise=False)
+        for i, (fen, moves) in enumerate(boards):
+            plan.append(("selfplay_vl", ("hash", 0.0 if i % 3 == 0 else 1.0, 700 + i), 300, fen, moves))
+            if i % 2 == 1:
+                plan.append(("vl_small", ("hash", 1.0, 800 + i), 160, fen, moves))
+        boards = []
     for i, (fen, moves) in enumerate(boards):
         plan.append(("selfplay", ("hash", 0.0, 100 + i), 300, fen, moves))          # exact priors, noise on every expansion
         plan.append(("selfplay", ("hash", 0.02, 200 + i), 400, fen, moves))         # random-init-like logits
@@ -144,9 +171,9 @@ def main():
             cfg = ref.MCTSConfig(num_threads=1, enable_memory_cleanup=False, dirichlet_frac=0.0, playout_random_frac=0.0, num_simulations=sims, **kw)
             be = HashBackend(scale=backend[1], seed=backend[2])
             if cfg_name == "direct":
-                m = ref.MCTS(cfg, TorchBackendModel(be), device="cpu", inference_backend=None)
+                m = MCTSClass(cfg, TorchBackendModel(be), device="cpu", inference_backend=None)
             else:
-                m = ref.MCTS(cfg, _Model(), device="cpu", inference_backend=be)
+                m = MCTSClass(cfg, _Model(), device="cpu", inference_backend=be)
             vc, pi, v = m.run(b.copy(), ply=len(moves))
             root = m._last_root
         finally:
@@ -156,7 +183,7 @@ def main():
                "jitter_used": sj.i, "normal_used": sn.i}
         # (2) the oracle restatement on the same streams: must agree exactly; reports the smallest top-2 gap
         o = RefMCTS(RefConfig(dirichlet_frac=0.0, playout_random_frac=0.0, num_simulations=sims, **kw), HashBackend(scale=backend[1], seed=backend[2]),
-                    jitter_value=None, jitter_stream=jit, normal_stream=nrm, direct_model=(cfg_name == "direct"))
+                    jitter_value=None, jitter_stream=jit, normal_stream=nrm, direct_model=(cfg_name == "direct"), virtual_loss=VL)
         vc2, pi2, v2 = o.run(b.copy(), ply=len(moves))
         assert [[mv.uci(), n] for mv, n in vc2.items()] == exp["visits"], ("oracle != reference", ci, cfg_name)
         assert v2 == v and pi2.tobytes() == pi.tobytes() and o.jit_used == sj.i and o.nrm_used == sn.i, ("oracle != reference", ci)
@@ -172,7 +199,7 @@ def main():
         print(ci, cfg_name, backend, "visits top", max(n for _, n in exp["visits"]), "jit", sj.i, "nrm", sn.i, "gap %.2e" % o.min_gap,
               "rows", o.distinct_rows, flush=True)
     json.dump({"configs": CFGS, "n_jitter": N_JITTER, "n_normal": N_NORMAL, "min_gap": MIN_GAP, "dropped_for_near_ties": dropped,
-               "cases": cases}, open(os.path.join(HERE, "mcts_stochastic_golden.json"), "w"))
+               "virtual_loss_batches": VL, "cases": cases}, open(os.path.join(HERE, "mcts_vl_golden.json" if VL else "mcts_stochastic_golden.json"), "w"))
     print("stochastic goldens:", len(cases), "cases kept,", dropped, "dropped (top-2 gap <", MIN_GAP, ")")
 
 

@@ -12,8 +12,8 @@ from oracle.backends import HashBackend
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mcts_stochastic_golden.json")
 
 
-def load():
-    return json.load(open(GOLDEN))
+def load(name="mcts_stochastic_golden.json"):
+    return json.load(open(os.path.join(os.path.dirname(GOLDEN), name)))
 
 
 def streams(seed, n_jitter, n_normal):

@@ -36,6 +36,23 @@ def test_reference_stochastic_goldens():
     assert sum(kinds.values()) >= 60 and set(kinds) == {"selfplay", "selfplay_b32", "arena_full", "prune", "direct"}, kinds
 
 
+def test_virtual_loss_throughput_mode_goldens():
+    """Throughput mode (north_star: "PUCT selection with virtual loss"): the in-flight marking of the reference's own MCTS._select
+    (inflight_counts, mcts.py:889-890, :922-923) applied inside every mini-batch, so that the simulations of a batch spread over
+    distinct leaves (142-254 evaluator rows per 160-300 simulations in these cases).  Goldens: the UNMODIFIED _select driven with one
+    dict per mini-batch (tests/golden/make_stochastic_golden.py vl), same seeded draws; visit counts, pi, value, child Q bit-exact."""
+    d = S.load("mcts_vl_golden.json")
+    assert d["virtual_loss_batches"] and len(d["cases"]) >= 20
+    for c in d["cases"]:
+        jit, nrm = S.streams(c["seed"], c["expect"]["jitter_used"] + 8, c["expect"]["normal_used"] + 8)
+        m = make_gpu(d["configs"][c["cfg"]], S.backend_of(c), c["sims"], virtual_loss_batches=True)
+        m.set_random_streams(jit, nrm)
+        vc, pi, v = m.run(S.board_of(c), ply=c["ply"])
+        S.check(c, vc, pi, v, m._last_root, prior_rtol=0.0 if c["backend"][1] == 0.0 else 1e-6)
+        assert m._engine.counters()["nn_evals"] >= c["expect"]["distinct_rows"]          # (+ the root evaluation is counted by begin)
+        m._engine.close()
+
+
 def test_stream_exhaustion_is_reported():
     d = S.load()
     c = d["cases"][1]

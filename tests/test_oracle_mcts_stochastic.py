@@ -22,3 +22,17 @@ def test_oracle_reproduces_reference_stochastic_goldens(part):
         S.check(c, vc, pi, v, m._last_root, prior_rtol=0.0)
         assert m.jit_used == c["expect"]["jitter_used"] and m.nrm_used == c["expect"]["normal_used"]
     assert kinds
+
+
+def test_oracle_reproduces_virtual_loss_goldens():
+    """The oracle's in-flight marking == the unmodified reference _select driven with an inflight_counts dict per mini-batch."""
+    d = S.load("mcts_vl_golden.json")
+    for ci, c in enumerate(d["cases"]):
+        if ci % 7:
+            continue
+        jit, nrm = S.streams(c["seed"], max(c["expect"]["jitter_used"], 1), max(c["expect"]["normal_used"], 1))
+        m = RefMCTS(RefConfig(dirichlet_frac=0.0, playout_random_frac=0.0, num_simulations=c["sims"], **d["configs"][c["cfg"]]), S.backend_of(c),
+                    jitter_value=None, jitter_stream=jit, normal_stream=nrm, virtual_loss=True)
+        vc, pi, v = m.run(S.board_of(c), ply=c["ply"])
+        S.check(c, vc, pi, v, m._last_root, prior_rtol=0.0)
+        assert m.distinct_rows == c["expect"]["distinct_rows"]
