@@ -289,6 +289,17 @@ int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+// columns per launch slice of a wide K <= 320 GEMM: the widest divisor of n that leaves room for two accumulators in tensor memory
+// (<= 256 columns, multiple of 16 so that a 2-CTA cluster splits the W tile into whole swizzle atoms); M0_TC_SLICE overrides
+int slice_width_for(int n, int dflt) {
+  static int forced = -1;
+  if (forced < 0) forced = env_int("M0_TC_SLICE", 0);
+  if (forced > 0) return (n % forced == 0) ? forced : dflt;
+  if (!env_int("M0_TC_ACC2", 1)) return dflt;
+  for (int w = 256; w >= 64; w -= 16)
+    if (n % w == 0) return w;
+  return dflt;
+}
 // 3x3 convolutions whose output width suits the CTA-pair kernel (M0_TC_PAIR=0 keeps the single-CTA kernel)
 bool pair_ok(int n) {
   static int on = -1;
@@ -415,7 +426,15 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   p.kb_per_tap = cin / 64;
   p.conv = conv;
   p.w_row0 = w_row0;
-  p.tmem_cols = pow2_cols(N);
+  // two accumulators when they fit into the 512 columns of tensor memory (M0_TC_ACC2=0: single accumulator, for A-B comparison)
+  {
+    static int acc2 = -1;
+    if (acc2 < 0) acc2 = env_int("M0_TC_ACC2", 1);
+    const int stride = (N + 31) / 32 * 32;
+    p.acc_stages = (acc2 && 2 * stride <= 512 && !gn_gamma) ? 2 : 1;
+    p.acc_stride = stride;
+    p.tmem_cols = pow2_cols(p.acc_stages * stride);
+  }
   p.out_f32 = out_f32;
   p.out_bf16 = out_bf16;
   p.ldc = ldc;
@@ -632,7 +651,7 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
       st->heads_tc = true;
     }
     if (c.chess_features) {
-      if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, C, s)) != M0_OK) break;
+      if (c.piece_square_tables && (rc = make_weight(st, &st->pst, n->w.pst_w, C, C, env_int("M0_TC_SLICE_PROJ", 1) ? slice_width_for(C, C) : C, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->inter, n->w.inter_w, C, 9 * C, C, s)) != M0_OK) break;
     }
     // fused SE + residual epilogue of conv2 (M0_TC_FUSE_SE=0 keeps the separate SE / residual kernels)
@@ -657,8 +676,8 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
         if ((rc = make_weight(st, &st->blocks[i].se_w2, w2p, C, hp, C, s)) != M0_OK) break;
       }
       if (b.has_attention) {
-        if ((rc = make_weight(st, &st->blocks[i].qkv, b.att_qkv_w, 3 * C, C, C, s)) != M0_OK) break;
-        if ((rc = make_weight(st, &st->blocks[i].proj, b.att_proj_w, C, C, C, s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].qkv, b.att_qkv_w, 3 * C, C, slice_width_for(3 * C, C), s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->blocks[i].proj, b.att_proj_w, C, C, env_int("M0_TC_SLICE_PROJ", 1) ? slice_width_for(C, C) : C, s)) != M0_OK) break;
       }
     }
   } while (0);
@@ -759,9 +778,16 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
       if (c.se) {
         // SE excitation before conv2 runs: hidden = act(fold * sums + b1), gate = sigmoid(W2 hidden + b2)  (resnet.py:61-64)
         // first layer split over K (60 k-blocks on only B/128 tiles otherwise), partial sums reduced with the bias + activation
-        PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, st->se_part, nullptr, st->hid_pad, 0, none, ACT_NONE, 1.0f, s,
-                                   nullptr, nullptr, nullptr, -1, 1, st->se_splits, (long long)st->se_rows * st->hid_pad));
-        PROF("se_hidden", nn_se_hidden(st->se_part, st->se_splits, (long long)st->se_rows * st->hid_pad, b.se_b1, st->se_hid_h, B, c.se_hidden, st->hid_pad, act, s));
+        static int se_nosplit = -1;
+        if (se_nosplit < 0) se_nosplit = env_int("M0_SE_NOSPLIT", 0);
+        if (se_nosplit) {
+          // one launch: bias + activation in the GEMM epilogue, hidden layer written in the operand format (no split-K, no reduction kernel)
+          PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, nullptr, st->se_hid_h, st->hid_pad, 0, b.se_b1, act, 1.0f, s));
+        } else {
+          PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, st->se_part, nullptr, st->hid_pad, 0, none, ACT_NONE, 1.0f, s,
+                                     nullptr, nullptr, nullptr, -1, 1, st->se_splits, (long long)st->se_rows * st->hid_pad));
+          PROF("se_hidden", nn_se_hidden(st->se_part, st->se_splits, (long long)st->se_rows * st->hid_pad, b.se_b1, st->se_hid_h, B, c.se_hidden, st->hid_pad, act, s));
+        }
         PROF("se_fc2", launch_gemm(st, st->se_hid_mat, tb.se_w2, B, 0, 1, st->hid_pad, 0, C, st->se_gate, nullptr, C, 0, b.se_b2, ACT_SIGMOID, 1.0f, s));
       }
       // conv2 with the whole block tail in its epilogue: x += gate * conv2 ; a1 = act(GN1_{i+1}(x)) (or half(x) before attention)

@@ -190,6 +190,9 @@ struct GemmParams {
   long long split_stride;
   int n_slices;      // >= 1: the launch covers n_slices consecutive groups of N output columns (w_row0 / col0 advance by N per slice);
                      // a CTA walks the slices of one M tile back to back, so the A tile is re-read from L2, not from HBM
+  int acc_stages;    // 1 or 2 accumulators in tensor memory (2 when two of them fit in 512 columns): the MMAs of work item i + 1 then
+                     // overlap the epilogue of work item i -- the K <= 320 GEMMs are bound by their epilogues otherwise
+  int acc_stride;    // TMEM column distance between the accumulators
 };
 
 // two floats -> one 32-bit word of bf16 or fp16 (low half = first value)
@@ -228,9 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   float* s_stats = s_beta + 320;              // [4 quarters][20 groups][sum, sumsq]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + p.stages;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const int na = p.acc_stages > 1 ? 2 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cs = p.cluster;
@@ -254,8 +258,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], (uint32_t)cs);   // every CTA of the cluster must have consumed the stage
     }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 256);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 256);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -306,10 +312,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t idesc = make_idesc_bf16(BM, p.n_part, p.fp16);
     const uint32_t part_bytes = (uint32_t)(p.n_part * BK * 2);
     int stage = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    uint32_t phase = 0, it = 0;
     const uint32_t smem_base = smem_u32(smem);
-    for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters) {
-      mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the accumulator
+    for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters, ++it) {
+      const uint32_t acc = na == 2 ? (it & 1u) : 0u, acc_phase = na == 2 ? ((it >> 1) & 1u) : (it & 1u);
+      const uint32_t tmem_acc = tmem_base + acc * (uint32_t)p.acc_stride;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       for (int kb = 0; kb < kb_part; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -323,12 +331,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-              umma_bf16(tmem_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, accum);
-              umma_bf16(tmem_base + (uint32_t)p.n_part, adesc0 + 2 * k, bdesc1 + 2 * k, idesc, accum);
+              umma_bf16(tmem_acc, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, accum);
+              umma_bf16(tmem_acc + (uint32_t)p.n_part, adesc0 + 2 * k, bdesc1 + 2 * k, idesc, accum);
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage (in every CTA of the cluster) once these MMAs have read it
           if (cs > 1) umma_commit_mcast(&empty_bar[stage], mask);
@@ -337,9 +345,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       __syncwarp();
-      acc_phase ^= 1;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (bias / activation) -> smem transpose -> coalesced global stores =====
@@ -353,17 +360,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int c = epi_tid; c < p.N; c += 256) { s_gamma[c] = p.gn_gamma[c]; s_beta[c] = p.gn_beta[c]; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    uint32_t acc_phase = 0;
-    for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters) {
+    uint32_t it = 0;
+    for (int gi = cluster_id; gi < num_groups * ns * nk; gi += num_clusters, ++it) {
+      const uint32_t acc = na == 2 ? (it & 1u) : 0u, acc_phase = na == 2 ? ((it >> 1) & 1u) : (it & 1u);
       const int ks = gi % nk, gs = gi / nk;
       const int g = gs / ns, slice = gs - g * ns;
       float* const out_f32 = p.out_f32 ? p.out_f32 + (size_t)ks * p.split_stride : nullptr;
       const int w_row0 = p.w_row0 + slice * p.N, col0 = p.col0 + slice * p.N;
       const int n_store = (p.n_store - slice * p.N) < p.N ? (p.n_store - slice * p.N) : p.N;   // p.n_store counts over all slices
-      mbar_wait(tmem_full_bar, acc_phase);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int tile_row0 = (g * cs + rank) * BM + quarter * 32;
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t tmem_row = tmem_base + acc * (uint32_t)p.acc_stride + ((uint32_t)(quarter * 32) << 16);
       if (fused_gn) {
         // pass 1: per (half board = this warp, group of 16 channels) sum and sum of squares
         for (int c0 = cset * 32; c0 < p.N; c0 += 64) {
@@ -484,8 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty_bar);
-      acc_phase ^= 1;
+      mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tc_fence_before();

@@ -3,8 +3,8 @@
 // visited node, mcts.py:893-897 -- so a batch collects up to batch_n different leaves.  Nothing but terminal backups
 // (:747-751) changes the statistics during collection; after inference the samples are processed in collection order:
 // expand the leaf if it still is one (+ entropy noise, pruning, TT registration), then back the sample's own path up
-// (:654-670).  Duplicated leaves share one network row (identical positions give identical rows), distinct leaves get
-// their own; the rows of all games are compacted into one evaluator batch.
+// (:654-670).  Samples that reached the same node with the same board share one network row (identical planes give identical
+// rows), all others get their own; the rows of all games are compacted into one evaluator batch.
 //
 // One warp owns one game.  Kernels:
 //   search_select_multi_kernel        collection of one mini-batch per game (selection, terminal backups, leaf table)
@@ -137,10 +137,13 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
       c_term++;
       continue;
     }
-    // sample {board, node, path}: find / append the leaf node in the game's leaf table
+    // sample {board, node, path}: find / append the leaf in the game's leaf table.  A row is shared only by samples with the same node
+    // AND the same board: a transposition-table node can be reached with different clocks (not part of the key, but part of the
+    // planes), and the reference evaluates every sample's own board (mcts.py:571-583)
     int slot = -1;
+    const u64* lp = E.ml_leaf_pos + (size_t)g * E.ml_cap * POSITION_WORDS;
     for (int r = lane; r < n_leaves; r += 32)
-      if (leaf_node[r] == node) slot = r;
+      if (leaf_node[r] == node && lp[(size_t)r * POSITION_WORDS + 8] == pos.state) slot = r;
     for (int off = 16; off > 0; off >>= 1) slot = max(slot, __shfl_xor_sync(FULL, slot, off));
     if (slot < 0) {
       slot = n_leaves++;

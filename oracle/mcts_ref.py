@@ -151,7 +151,7 @@ class RefMCTS:
         self.nn_cache: Dict[tuple, tuple] = {}
         self.unique_evals = 0
         self.sample_rows = 0      # rows the reference evaluates (one per collected sample, duplicates included)
-        self.distinct_rows = 0    # distinct leaf nodes among them (the rows the engine evaluates)
+        self.distinct_rows = 0    # distinct (leaf node, board incl. clocks) pairs among them: the rows the engine evaluates
         self._last_root = None
         self._last_sims_run = 0
 
@@ -318,7 +318,7 @@ class RefMCTS:
                 policies, values = self.backend.infer_np(batch)
                 self.unique_evals += 1
                 self.sample_rows += len(samples)
-                self.distinct_rows += len({id(s[1]) for s in samples})
+                self.distinct_rows += len({(id(s[1]), s[0].halfmove_clock, s[0].fullmove_number, s[0].ep_square) for s in samples})
                 for (lb, node, path), pol, val in zip(samples, policies, values):
                     if not node.expanded:
                         self._expand_leaf(node, lb, pol, allow_noise)

@@ -4,6 +4,7 @@
 // matrix0_b200 (the product has no CPU path and raises when the CUDA library is missing).
 #include "../../matrix0_b200/csrc/chess_core.cuh"
 #include "../../matrix0_b200/csrc/ssl_core.cuh"
+#include "../../matrix0_b200/csrc/movegen_warp.cuh"
 #include <string.h>
 using namespace m0;
 
@@ -50,6 +51,45 @@ void hc_key(const uint64_t* pos9, uint64_t* key2) {
 // the positions m0_random_playouts(seed, max_plies) writes, computed on the host (same function as the device kernel)
 void hc_random_playouts(uint64_t* out, int first, int n, uint64_t seed, int max_plies) {
   for (int i = 0; i < n; ++i) store(random_playout_position(seed, first + i, max_plies), out + (size_t)i * 9);
+}
+// The warp-cooperative ordered generator (movegen_warp.cuh) with its 32 lanes simulated one after the other: the same per-lane
+// functions (lane_generate / lane_counts / lane_emit) and the same suffix-sum placement as the device wrapper.
+// Returns -1 when the board takes the single-lane fallback on the device.
+int hc_legal_moves_warp(const uint64_t* pos9, uint16_t* moves, int* in_check_out) {
+  Position p = load(pos9);
+  if (!warp_movegen_supported(p)) return -1;
+  const u64 ours = pos_us(p), theirs = pos_them(p), king_bb = p.kings & ours;
+  u64 danger = 0, checkers = 0;
+  for (u64 t = theirs; t; t &= t - 1) {
+    const int e = lsb(t);
+    const u64 a = attacks_from(p, e);
+    danger |= a;
+    if (a & king_bb) checkers |= sq_bb(e);
+  }
+  const LegalCtx c = make_legal_ctx(p, &checkers);
+  const bool in_check = checkers != 0;
+  LaneGen g[32];
+  LaneCounts n[32];
+  u64 rest = ours;
+  for (int lane = 0; lane < 32; ++lane) {
+    int from = -1;
+    if (rest) { from = lsb(rest); rest &= rest - 1; }
+    g[lane] = lane_generate(p, c, danger, from);
+    n[lane] = lane_counts(g[lane], in_check);
+  }
+  u32 s0[33], s1[33];
+  s0[32] = s1[32] = 0;
+  for (int lane = 31; lane >= 0; --lane) { s0[lane] = s0[lane + 1] + n[lane].w0; s1[lane] = s1[lane + 1] + n[lane].w1; }
+  int n_castle = 0, ksq = 0, cto[2] = {0, 0};
+  if (!in_check) n_castle = legal_castling(p, c, &ksq, cto, &danger);
+  const u32 tot0 = s0[0], tot1 = s1[0];
+  const int nK = (int)(tot1 >> 24), nA = (int)(tot0 & 0xFFFFu), nC = (int)(tot0 >> 16), nS = (int)(tot1 & 0xFFu), nD = (int)((tot1 >> 8) & 0xFFu),
+            nE = (int)((tot1 >> 16) & 0xFFu);
+  const int base_a = nK, base_z = base_a + nA, base_c = base_z + n_castle, base_s = base_c + nC, base_d = base_s + nS, base_e = base_d + nD;
+  for (int lane = 0; lane < 32; ++lane) lane_emit(g[lane], in_check, c.ep, moves, base_a, base_c, base_s, base_d, base_e, s0[lane + 1], s1[lane + 1]);
+  for (int i = 0; i < n_castle; ++i) { int at = base_z + i; put_move(moves, at, ksq, cto[i], 0); }
+  *in_check_out = in_check ? 1 : 0;
+  return base_e + nE;
 }
 int hc_has_legal_ep(const uint64_t* pos9) { return has_legal_ep(load(pos9)); }
 int hc_insufficient(const uint64_t* pos9) { return is_insufficient_material(load(pos9)); }

@@ -24,7 +24,8 @@ def hc():
     src = os.path.join(HC_DIR, "hostcheck.cpp")
     core = os.path.join(ROOT, "matrix0_b200", "csrc", "chess_core.cuh")
     ssl = os.path.join(ROOT, "matrix0_b200", "csrc", "ssl_core.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(ssl)):
+    mg = os.path.join(ROOT, "matrix0_b200", "csrc", "movegen_warp.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(ssl), os.path.getmtime(mg)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     return ctypes.CDLL(so)
 
@@ -145,3 +146,34 @@ def test_host_playouts_match_committed_position_digests(hc, golden_dir):
     hc.hc_random_playouts(out.ctypes.data_as(U64P), 0, n, ctypes.c_uint64(d["seed"]), d["max_plies"])
     for c in range(4):
         assert hashlib.sha256(out[c * d["chunk"]:(c + 1) * d["chunk"]].tobytes()).hexdigest() == d["position_sha256"][c]
+
+
+def test_warp_ordered_generator_matches_python_chess_order(hc, golden_dir):
+    """csrc/movegen_warp.cuh (one own piece per lane, list placed by suffix sums) with its lanes simulated on the host: the SAME ordered
+    list as the oracle's python-chess generation order -- random playouts, the constructed edge positions (checks, double checks, pins,
+    en passant, promotions, castling), and 20,000 of the bench's synthetic positions against the single-thread generator."""
+    boards = random_playout_boards(60, 200, seed=77) + [chess.Board(f) for f in WEIRD_FENS]
+    u16p = ctypes.POINTER(ctypes.c_uint16)
+    n_fallback = n_check = 0
+    for b in boards:
+        pos = pack(hc, b)
+        mv = np.zeros(512, dtype=np.uint16)
+        chk = ctypes.c_int(0)
+        n = hc.hc_legal_moves_warp(pos.ctypes.data_as(U64P), mv.ctypes.data_as(u16p), ctypes.byref(chk))
+        if n < 0:
+            n_fallback += 1
+            continue
+        exp = [c for c, _ in E.legal_moves_and_indices(b)]
+        assert n == len(exp) and mv[:n].tolist() == exp, b.fen()
+        assert bool(chk.value) == b.is_check(), b.fen()
+        n_check += b.is_check()
+    assert n_check > 20 and n_fallback < len(WEIRD_FENS)
+    N = 20000
+    pos = np.zeros((N, 9), dtype=np.uint64)
+    hc.hc_random_playouts(pos.ctypes.data_as(U64P), 0, N, ctypes.c_uint64(99), 160)
+    a, bb, idx = np.zeros(512, dtype=np.uint16), np.zeros(512, dtype=np.uint16), np.zeros(512, dtype=np.int16)
+    for i in range(N):
+        chk = ctypes.c_int(0)
+        n1 = hc.hc_legal_moves_warp(pos[i].ctypes.data_as(U64P), a.ctypes.data_as(u16p), ctypes.byref(chk))
+        n2 = hc.hc_legal_moves(pos[i].ctypes.data_as(U64P), bb.ctypes.data_as(u16p), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+        assert n1 == n2 and (a[:n1] == bb[:n1]).all(), i
