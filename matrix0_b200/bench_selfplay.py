@@ -196,6 +196,25 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     ce1 = sp.counters()
     e2e_sims = allsum(ce1["sims"] - ce0["sims"])
 
+    # tree kernels in situ: CUDA events around search_select_kernel and search_expand_backup_kernel over one more move; algorithmic bytes
+    # from the device counters of the same steps (+ the logits rows the expansion scans / gathers and the planes the selection writes)
+    while Cycle.i % per_move:
+        step()
+    ct0 = sp.counters()
+    sp.tree_events = []
+    sp.begin_move()
+    for _ in range(per_move - 1):
+        sp.search_step()
+    sp.end_move()
+    torch.cuda.synchronize()
+    evs, sp.tree_events = sp.tree_events, None
+    ct1 = sp.counters()
+    dt = {k: ct1[k] - ct0[k] for k in ct1}
+    sel_us = 1e3 * sum(e[0].elapsed_time(e[1]) for e in evs) / len(evs)
+    exp_us = 1e3 * sum(e[2].elapsed_time(e[3]) for e in evs) / len(evs)
+    tree_bytes = (24 * dt["children_scanned"] + 24 * dt["path_nodes"] + 44 * dt["children_created"]
+                  + (4 * 4672 + 72 + 19 * 64 * 4) * (dt["nn_evals"])) / len(evs)
+    tree_gbs = tree_bytes / ((sel_us + exp_us) * 1e-6) / 1e9
     out = {
         "metric": "MCTS sims/sec, batched self-play, ResNet-24 (BASELINE configs[3])", "value": sims_all / secs, "unit": "sims/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -222,7 +241,14 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
                     "launch_sites": site_ms, "sum_of_sites_ms": fwd_profiled_ms},
         "tree": {"children_scanned": d["children_scanned"], "path_nodes": d["path_nodes"], "children_created": d["children_created"],
                  "terminal_sims": d["terminal_sims"], "tt_hops": d["tt_hops"],
-                 "algorithmic_bytes": 24 * d["children_scanned"] + 24 * d["path_nodes"] + 44 * d["children_created"]},
+                 "algorithmic_bytes": 24 * d["children_scanned"] + 24 * d["path_nodes"] + 44 * d["children_created"],
+                 "roofline": {"bound": "hbm (latency-bound in practice: one warp per game, dependent pointer chasing down the tree)",
+                              "select_us_per_step": sel_us, "expand_backup_us_per_step": exp_us, "algorithmic_bytes_per_step": tree_bytes,
+                              "achieved": tree_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tree_gbs / peaks["hbm_gbs"],
+                              "share_of_step": (sel_us + exp_us) * 1e-3 / (total_ms / args.steps),
+                              "bytes": "24 B x children scanned + 24 B x path nodes + 44 B x children created + per evaluated leaf the logits row "
+                                       "(18,688 B), the leaf position (72 B) and its planes (4,864 B)",
+                              "timing": "CUDA events around the two kernels of every search step of one move, in the running loop"}},
     }
     out["accounting"] = ("value counts SIMULATIONS in the reference's accounting: with the jitter neutralised every simulation of a mini-batch reaches "
                          "the same leaf (SURVEY Q1), so one evaluated row stands for up to inference_batch_size simulations; the physical rate is "

@@ -6,6 +6,7 @@
 // start position with `opening_random_plies` uniformly random legal moves (:371-379).
 #include "engine.cuh"
 #include "selfplay.cuh"
+#include "movegen_warp.cuh"
 
 namespace m0 {
 
@@ -74,16 +75,9 @@ __device__ bool draw_heuristics(const EngineView& E, const SelfPlayState& S, int
 //   should_adjudicate_draw (heuristics disabled by default)   draw.py:31-41
 // which together equal board.is_game_over(claim_draw=True) plus stalemate.
 __device__ int game_end_reason(const EngineView& E, int g, const Position& pos, u16* s_moves, int lane) {
-  int n_moves = 0, in_check = 0;
-  if (lane == 0) {
-    u64 checkers;
-    n_moves = generate_legal_moves(pos, s_moves, &checkers);
-    in_check = checkers != 0;
-  }
-  n_moves = __shfl_sync(FULLM, n_moves, 0);
-  in_check = __shfl_sync(FULLM, in_check, 0);
+  int in_check = 0;
+  int n_moves = warp_generate_legal_moves(pos, s_moves, &in_check, lane);
   if (n_moves > MAX_MOVES) n_moves = MAX_MOVES;
-  __syncwarp();
   if (n_moves == 0) return in_check ? END_CHECKMATE : END_STALEMATE;
   if (is_insufficient_material(pos)) return END_INSUFFICIENT;
   const int hm = pos_halfmove(pos);
@@ -168,10 +162,8 @@ __device__ void start_game(const EngineView& E, const SelfPlayState& S, int g, u
   }
   __syncwarp();
   for (int k = 0; k < S.params->opening_random_plies; ++k) {
-    int n = 0;
-    if (lane == 0) n = generate_legal_moves(pos, s_moves);
-    n = __shfl_sync(FULLM, n, 0);
-    __syncwarp();
+    int chk = 0;
+    int n = warp_generate_legal_moves(pos, s_moves, &chk, lane);
     if (n == 0 || is_insufficient_material(pos)) break;  // board.is_game_over() (no repetition possible this early)
     if (n > MAX_MOVES) n = MAX_MOVES;
     int pick = 0;

@@ -3,6 +3,7 @@
 // repetition test of a leaf, the random draws, and Node._expand with entropy noise and child pruning.
 #pragma once
 #include "engine.cuh"
+#include "movegen_warp.cuh"
 
 namespace m0 {
 
@@ -96,14 +97,8 @@ __device__ __forceinline__ bool leaf_is_fivefold(const EngineView& E, int g, int
 // (_terminal_value, mcts.py:1223-1229).  depth / key: place on the search path for the repetition test.
 __device__ __forceinline__ int warp_leaf_moves(const EngineView& E, const SearchParams& P, int g, const Position& pos, int depth, const Key128& key,
                                                u16* s_moves, bool* terminal, double* terminal_value, int lane) {
-  int n_moves = 0, in_check = 0;
-  if (lane == 0) {
-    u64 checkers;
-    n_moves = generate_legal_moves(pos, s_moves, &checkers);
-    in_check = checkers != 0;
-  }
-  n_moves = __shfl_sync(FULL, n_moves, 0);
-  in_check = __shfl_sync(FULL, in_check, 0);
+  int in_check = 0;
+  int n_moves = warp_generate_legal_moves(pos, s_moves, &in_check, lane);   // one own piece per lane, python-chess order
   if (n_moves > MAX_MOVES) n_moves = MAX_MOVES;
   bool term = n_moves == 0 || is_insufficient_material(pos) || (pos_halfmove(pos) >= 150 && n_moves > 0);
   if (!term && pos_halfmove(pos) >= 8) {

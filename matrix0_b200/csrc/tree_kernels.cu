@@ -80,14 +80,8 @@ search_begin_kernel(EngineView E, float* __restrict__ planes, int* __restrict__ 
   Position pos = load_position(E.root_pos + (size_t)g * POSITION_WORDS);
   bool epl;
   Key128 key = position_key(pos, &epl);
-  int n_moves = 0, in_check = 0;
-  if (lane == 0) {
-    u64 checkers;
-    n_moves = generate_legal_moves(pos, s_moves[wib], &checkers);
-    in_check = checkers != 0;
-  }
-  n_moves = __shfl_sync(FULL, n_moves, 0);
-  in_check = __shfl_sync(FULL, in_check, 0);
+  int in_check = 0;
+  int n_moves = warp_generate_legal_moves(pos, s_moves[wib], &in_check, lane);
   if (n_moves > MAX_MOVES) n_moves = MAX_MOVES;
   // board.is_game_over(): the search path is empty, so only the game history can repeat
   if (lane == 0) {
@@ -268,14 +262,8 @@ search_select_kernel(EngineView E, int batch_cap, int* __restrict__ sims_left, f
     __syncwarp();
     c_path += depth + 1;
     // leaf: terminal? (board.is_game_over(), mcts.py:747)
-    int n_moves = 0, in_check = 0;
-    if (lane == 0) {
-      u64 checkers;
-      n_moves = generate_legal_moves(pos, s_moves[wib], &checkers);
-      in_check = checkers != 0;
-    }
-    n_moves = __shfl_sync(FULL, n_moves, 0);
-    in_check = __shfl_sync(FULL, in_check, 0);
+    int in_check = 0;
+    int n_moves = warp_generate_legal_moves(pos, s_moves[wib], &in_check, lane);
     if (n_moves > MAX_MOVES) n_moves = MAX_MOVES;
     bool terminal = n_moves == 0 || is_insufficient_material(pos) || (pos_halfmove(pos) >= 150 && n_moves > 0);
     if (!terminal && pos_halfmove(pos) >= 8) {

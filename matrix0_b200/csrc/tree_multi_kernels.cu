@@ -243,11 +243,9 @@ search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* __r
     const int node = leaf_node[r];
     if (E.node_first[nb + node] < 0) {   // `not node.is_expanded()` (mcts.py:657)
       const Position pos = load_position(E.ml_leaf_pos + ((size_t)g * E.ml_cap + r) * POSITION_WORDS);
-      int k = 0;
-      if (lane == 0) k = generate_legal_moves(pos, s_moves[wib]);
-      k = __shfl_sync(FULL, k, 0);
+      int chk = 0;
+      int k = warp_generate_legal_moves(pos, s_moves[wib], &chk, lane);
       if (k > MAX_MOVES) k = MAX_MOVES;
-      __syncwarp();
       const int wtm = pos_turn(pos);
       for (int j = lane; j < k; j += 32) s_idx[wib][j] = (u16)policy_index(s_moves[wib][j], wtm);
       __syncwarp();

@@ -165,6 +165,7 @@ class SelfPlayEngine:
         self.nn_evals = 0
         self.nn_rows = 0
         self.nn_rows_padded = 0
+        self.tree_events = None     # set to a list to collect CUDA events around the tree kernels of every search step
         self.moves = 0
         self.steps = 0
 
@@ -252,10 +253,22 @@ class SelfPlayEngine:
         eng = self.engine
         if self.search_mode == "as_shipped":
             return self._search_step_as_shipped()
+        ev = self.tree_events
+        if ev is not None:        # measurement aid (bench.py): CUDA events around the two tree kernels of this step
+            import torch
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
         _native.check(self._lib.m0_search_select_var(eng._h, int(self.mcfg.inference_batch_size), self.sims_left.data_ptr(),
                                                      eng.planes.data_ptr(), _native.current_stream()), "m0_search_select_var")
+        if ev is not None:
+            e[1].record()
         logits, values = self._forward(eng.planes)
+        if ev is not None:
+            e[2].record()
         eng.expand_backup(logits, values)
+        if ev is not None:
+            e[3].record()
+            ev.append(e)
         self.steps += 1
 
     def _search_step_as_shipped(self) -> None:
