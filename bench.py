@@ -269,7 +269,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("M0_BENCH_WORKLOAD", "auto"), choices=["auto", "encode", "selfplay"])
     ap.add_argument("--positions", type=int, default=1 << 20)
     ap.add_argument("--e2e-positions", type=int, default=1 << 16)
-    ap.add_argument("--games", type=int, default=4096)
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games PER GPU (weak scaling, the default of the driver's 1..8 GPU runs)")
+    ap.add_argument("--total-games", type=int, default=0,
+                    help="BASELINE configs[4] as written: this many games in total, split evenly over the ranks (32768 -> 16384 / 8192 / 4096 per GPU at 2 / 4 / 8)")
     ap.add_argument("--sims", type=int, default=800)
     ap.add_argument("--leaf-batch", type=int, default=96,
                     help="mcts.inference_batch_size: 96 = the reference's accounting (one evaluated leaf per game stands for up to 96 "
@@ -310,6 +312,8 @@ def main():
         return
 
     rank, world, local = dist_setup(args.gpus)
+    if args.total_games > 0:
+        args.games = args.total_games // world
     if args.workload == "selfplay":
         from matrix0_b200 import bench_selfplay
         out = bench_selfplay.run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ranks)

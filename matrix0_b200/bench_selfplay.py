@@ -218,9 +218,9 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     out = {
         "metric": "MCTS sims/sec, batched self-play, ResNet-24 (BASELINE configs[3])", "value": sims_all / secs, "unit": "sims/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+        "scaling": "strong" if int(getattr(args, "total_games", 0)) > 0 else "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
         "config": {"workload": f"batched self-play: {G} concurrent games/GPU x {args.sims} sims/move, ResNet-24 320ch/24 blocks/20 heads {precision}, random init",
-                   "games_per_gpu": G, "sims_per_move": args.sims, "inference_batch_size": leaf_batch, "steps_per_move": per_move,
+                   "games_per_gpu": G, "total_games": G * world, "sims_per_move": args.sims, "inference_batch_size": leaf_batch, "steps_per_move": per_move,
                    "mode": ("reference-exact accounting (one evaluated leaf per game and mini-batch, SURVEY Q1), fresh tree per move" if leaf_batch > 1
                             else "distinct leaves: every simulation selects, evaluates and backs up its own leaf (inference_batch_size = 1), fresh tree per move"),
                    "openings": "start position + 12 random plies (device RNG)", "l2": "per-step activations (>1 GB) exceed the 126 MB L2"},

@@ -837,7 +837,7 @@ M0_HD Key128 position_key(const Position& p, bool* ep_legal_out = nullptr) {
   Key128 k;
   k.lo = mix64(a ^ (b << 1));
   k.hi = mix64(b ^ (a >> 3) ^ 0xA0761D6478BD642Full);
-  if (k.lo == 0 && k.hi == 0) k.lo = 1;  // (0,0) is the empty-slot marker of the TT
+  if (k.lo == 0) k.lo = 1;  // (0, 0) is the empty-slot marker of the TT and its low word the claim flag of concurrent inserts
   return k;
 }
 

@@ -144,4 +144,29 @@ __device__ __forceinline__ void tt_put(const EngineView& E, int g, const Key128&
   E.status[g] |= ST_TT_OVERFLOW;
 }
 
+// The same for many lanes of the game's warp at once, each with a DIFFERENT key (the children of one node are different positions):
+// an empty slot is claimed with a compare-and-swap on its low word, so two lanes probing into the same slot cannot both take it.
+// A lane that meets a foreign low word just probes on; complete entries are all that later kernels see.
+__device__ __forceinline__ void tt_put_concurrent(const EngineView& E, int g, const Key128& k, int node) {
+  const size_t base = (size_t)g * E.tt_cap;
+  const u32 mask = (u32)E.tt_cap - 1;
+  u32 h = (u32)k.lo & mask;
+  for (int probe = 0; probe < E.tt_cap; ++probe) {
+    const u64 lo = E.tt_lo[base + h];
+    if (lo == k.lo && E.tt_hi[base + h] == k.hi) { E.tt_val[base + h] = node; return; }
+    if (lo == 0 && E.tt_hi[base + h] == 0) {
+      if (atomicAdd(&E.tt_count[g], 0) >= E.tt_cap - E.tt_cap / 8) { atomicOr(&E.status[g], ST_TT_OVERFLOW); return; }
+      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&E.tt_lo[base + h]), 0ull, (unsigned long long)k.lo);
+      if (old == 0ull) {
+        E.tt_hi[base + h] = k.hi;
+        E.tt_val[base + h] = node;
+        atomicAdd(&E.tt_count[g], 1);
+        return;
+      }
+    }
+    h = (h + 1) & mask;
+  }
+  atomicOr(&E.status[g], ST_TT_OVERFLOW);
+}
+
 }  // namespace m0

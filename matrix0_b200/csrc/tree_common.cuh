@@ -300,17 +300,17 @@ __device__ __forceinline__ void warp_expand(const EngineView& E, const SearchPar
     E.node_mv[c] = (u32)mv | ((u32)idx[src[t]] << 16);
     E.node_nchild[c] = 0;
     if (reg) {
+      // self.tt[key] = child for every child (mcts.py:1330-1346).  The children of one node are different positions, so the
+      // lanes insert concurrently; "last writer wins" only orders EQUAL keys, i.e. this expansion against earlier ones
       Position cp = pos;
       push_move(cp, mv);
-      S.key[j] = position_key(cp);
+      tt_put_concurrent(E, g, position_key(cp), first + j);
     }
   }
   __syncwarp();
   if (lane == 0) {
     E.node_first[nb + node] = first;
     E.node_nchild[nb + node] = (u16)kk;
-    if (reg)
-      for (int j = 0; j < kk; ++j) tt_put(E, g, S.key[j], first + j);  // last writer wins, child order
     atomicAdd(&E.counters[CTR_EXPANSIONS], 1ull);
     atomicAdd(&E.counters[CTR_CHILDREN_CREATED], (unsigned long long)kk);
   }

@@ -70,7 +70,7 @@ class GameRecorder:
     def after_move(self) -> List[Dict[str, np.ndarray]]:
         """Call after SelfPlayEngine.end_move(); returns the game_data dictionaries of the games that just ended."""
         now = self._ply0 + len(self._plies)          # absolute index one past the ply just played
-        out = []
+        todo = []
         for fin in self.sp.finished_games():
             slot = fin["slot"]
             first = int(self._start[slot])
@@ -78,7 +78,17 @@ class GameRecorder:
             self._start[slot] = now
             if T <= 0 or first < self._ply0:
                 continue  # the game began before the retained window (keep_plies too small): skipped, never truncated
-            out.append(self._assemble(slot, first, now, fin))
+            todo.append((slot, first, fin))
+        out, group, rows = [], [], 0
+        for item in todo:                                  # bounded device / host staging: <= 65,536 positions per encode launch
+            T = now - item[1]
+            if group and rows + T > 65536:
+                out += self._assemble_batch(group, now)
+                group, rows = [], 0
+            group.append(item)
+            rows += T
+        if group:
+            out += self._assemble_batch(group, now)
         # drop plies no live game needs any more
         lo = int(self._start.min())
         drop = max(0, min(lo - self._ply0, len(self._plies)))
@@ -89,42 +99,49 @@ class GameRecorder:
             self._ply0 += drop
         return out
 
-    def _assemble(self, slot: int, first: int, now: int, fin: Dict[str, Any]) -> Dict[str, np.ndarray]:
+    def _assemble_batch(self, todo, now: int) -> List[Dict[str, np.ndarray]]:
+        """game_data dictionaries of all games that ended this ply: ONE encode launch (planes + legal masks) and one SSL launch over the
+        concatenated positions of all of them, one D2H copy per array, then per-game views."""
         torch = self._torch
         lib = _native.lib()
-        rows = [self._plies[i - self._ply0] for i in range(first, now)]
-        T = len(rows)
-        pos = np.stack([r["pos"][slot] for r in rows])                     # [T, 9]
+        rows_of = [[self._plies[i - self._ply0] for i in range(first, now)] for _, first, _ in todo]
+        lens = [len(r) for r in rows_of]
+        pos = np.concatenate([np.stack([r["pos"][slot] for r in rows]) for (slot, _, _), rows in zip(todo, rows_of)])     # [sum T, 9]
+        N = pos.shape[0]
         dpos = torch.from_numpy(pos).to(self.sp.device)
-        planes = torch.empty((T, 19, 8, 8), dtype=torch.float32, device=self.sp.device)
-        mask = torch.empty((T, 4672), dtype=torch.uint8, device=self.sp.device)
-        _native.check(lib.m0_encode_positions(dpos.data_ptr(), T, planes.data_ptr(), mask.data_ptr(), None, None, None, _native.current_stream()),
+        planes = torch.empty((N, 19, 8, 8), dtype=torch.float32, device=self.sp.device)
+        mask = torch.empty((N, 4672), dtype=torch.uint8, device=self.sp.device)
+        _native.check(lib.m0_encode_positions(dpos.data_ptr(), N, planes.data_ptr(), mask.data_ptr(), None, None, None, _native.current_stream()),
                       "m0_encode_positions")
-        pi = np.zeros((T, 4672), dtype=np.float32)
-        turns = np.empty((T,), dtype=np.float32)
-        sims = []
-        for t, r in enumerate(rows):
-            k = int(r["count"][slot])
-            n = r["visits"][slot, :k].astype(np.float64)
-            tot = n.sum()
-            if tot > 0:
-                pi[t, r["idx"][slot, :k].astype(np.int64)] = (n / tot).astype(np.float32)   # mcts.py:840-847
-            turns[t] = 1.0 if (int(pos[t, 8]) & 1) else -1.0          # packed state word: bit 0 = side to move (White = 1)
-            sims.append(float(tot))
-        z = float(fin["result"])
-        ssl = {}
+        planes_h, mask_h = planes.cpu().numpy(), mask.cpu().numpy()
+        ssl_h = {}
         if self.ssl_tasks:
             from .encoding import ssl_targets_device
             maps = ssl_targets_device(dpos)
-            ssl = {f"ssl_{t}": maps[t].cpu().numpy() for t in self.ssl_tasks}
-        return {
-            **ssl,
-            "s": planes.cpu().numpy(), "pi": pi, "z": (z * turns).astype(np.float32), "legal_mask": mask.cpu().numpy(),
-            "meta_moves": np.array([T], dtype=np.int32), "meta_result": np.array([z], dtype=np.float32),
-            "meta_resigned": np.array([1 if fin["resigned"] else 0], dtype=np.int8), "meta_draw": np.array([1 if z == 0.0 else 0], dtype=np.int8),
-            "meta_avg_policy_entropy": np.array([fin["avg_policy_entropy"]], dtype=np.float32),
-            "meta_avg_sims": np.array([float(np.mean(sims)) if sims else 0.0], dtype=np.float32),
-        }
+            ssl_h = {t: maps[t].cpu().numpy() for t in self.ssl_tasks}
+        out, off = [], 0
+        for (slot, first, fin), rows, T in zip(todo, rows_of, lens):
+            pi = np.zeros((T, 4672), dtype=np.float32)
+            sims = np.empty((T,), dtype=np.float64)
+            for t, r in enumerate(rows):
+                k = int(r["count"][slot])
+                n = r["visits"][slot, :k].astype(np.float64)
+                tot = n.sum()
+                if tot > 0:
+                    pi[t, r["idx"][slot, :k].astype(np.int64)] = (n / tot).astype(np.float32)   # mcts.py:840-847
+                sims[t] = tot
+            turns = np.where((pos[off:off + T, 8] & 1) != 0, 1.0, -1.0).astype(np.float32)       # packed state word: bit 0 = side to move
+            z = float(fin["result"])
+            out.append({
+                **{f"ssl_{t}": ssl_h[t][off:off + T].copy() for t in ssl_h},
+                "s": planes_h[off:off + T].copy(), "pi": pi, "z": (z * turns).astype(np.float32), "legal_mask": mask_h[off:off + T].copy(),
+                "meta_moves": np.array([T], dtype=np.int32), "meta_result": np.array([z], dtype=np.float32),
+                "meta_resigned": np.array([1 if fin["resigned"] else 0], dtype=np.int8), "meta_draw": np.array([1 if z == 0.0 else 0], dtype=np.int8),
+                "meta_avg_policy_entropy": np.array([fin["avg_policy_entropy"]], dtype=np.float32),
+                "meta_avg_sims": np.array([float(sims.mean()) if T else 0.0], dtype=np.float32),
+            })
+            off += T
+        return out
 
 
 def write_game_npz(directory: str, game: Dict[str, np.ndarray], worker_id: int, game_id: int) -> str:
