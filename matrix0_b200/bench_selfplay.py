@@ -140,7 +140,7 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
     conv_ms, conv_n, site_ms = 0.0, 0, {}
     for site in ("conv1+gn", "conv2+pool", "conv2+se+res+gn", "se_apply_gn", "se_gate", "se_fc1", "se_hidden", "se_fc2", "attention_tc", "gemm_qkv", "gemm_proj",
                  "layernorm_residual_f32", "ln_res_gn", "gn_act_res", "conv_other", "gemm_pst", "planes_to_nhwc_half", "f32_to_bf16", "gemm_pol_conv",
-                 "gemm_pol_fc1", "gemm_pol_fc2", "gemm_val_conv1", "gemm_val_conv2", "gemm_val_fc1", "gemm_f32"):
+                 "gemm_pol_fc1", "gemm_pol_fc2", "gemm_val_conv1", "gemm_val_conv2", "gemm_val_fc1", "gemm_val_fc2", "gemm_val_gate", "value_tail", "gemm_f32"):
         ms, cnt = ctypes.c_double(0), ctypes.c_longlong(0)
         _native.check(lib.m0_profile_get(site.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
         if cnt.value:

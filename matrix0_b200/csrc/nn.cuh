@@ -24,8 +24,8 @@ int nn_attention_f32(const float* qkv, const float* rel_bias, float* out, int B,
 int nn_layernorm_residual_f32(const float* proj, const float* x, const float* gamma, const float* beta, float* out, int tokens, int C,
                               cudaStream_t s);
 int nn_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, cudaStream_t s);
-int nn_ln_res_gn(const float* proj, float* x, const float* ln_g, const float* ln_b, const float* gn_g, const float* gn_b, __nv_bfloat16* a_out,
-                 int B, int C, int act, cudaStream_t s);
+int nn_ln_res_gn(const void* proj, int proj_half, float* x, const float* ln_g, const float* ln_b, const float* gn_g, const float* gn_b,
+                 __nv_bfloat16* a_out, int B, int C, int act, cudaStream_t s);
 
 }  // namespace m0
 

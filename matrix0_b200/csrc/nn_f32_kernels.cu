@@ -288,7 +288,9 @@ __global__ void layernorm_residual_f32_kernel(const float* __restrict__ proj, co
 // Tensor-core path: x_new = LN(proj + x) (resnet.py:182-188) and, fused, a_out = half(act(GroupNorm_16ch(x_new))) = the bn1 +
 // activation of the next residual block (resnet.py:46-47).  One block (8 warps) per board; warp w owns tokens 8w..8w+7, lane l
 // owns channels 2l + 64j (j < C/64): proj and x are read once, the sums live in registers for both normalisations.
-template <int NJ>
+// HALF_IN: proj is the 16-bit output of the projection GEMM (the reference's proj convolution runs under autocast, resnet.py:676-677);
+// gn_g == nullptr with a_out != nullptr: a_out = half(x_new) without the GroupNorm (the operand of the head GEMMs after the last block)
+template <int NJ, bool HALF_IN>
 __global__ void __launch_bounds__(256, 2)
 ln_res_gn_kernel(const float* __restrict__ proj, float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                  const float* __restrict__ gn_g, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ a_out, int act, int fp16) {
@@ -301,7 +303,14 @@ ln_res_gn_kernel(const float* __restrict__ proj, float* __restrict__ x, const fl
   for (int t = 0; t < 8; ++t)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float2 p2 = __ldg(reinterpret_cast<const float2*>(proj + base + (size_t)t * C + 64 * j));
+      float2 p2;
+      if (HALF_IN) {
+        const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(proj) + base + (size_t)t * C + 64 * j));
+        if (fp16) p2 = __half22float2(*reinterpret_cast<const __half2*>(&h));
+        else p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h));
+      } else {
+        p2 = __ldg(reinterpret_cast<const float2*>(proj + base + (size_t)t * C + 64 * j));
+      }
       const float2 x2 = *reinterpret_cast<const float2*>(x + base + (size_t)t * C + 64 * j);
       v[t][2 * j] = p2.x + x2.x;
       v[t][2 * j + 1] = p2.y + x2.y;
@@ -349,6 +358,18 @@ ln_res_gn_kernel(const float* __restrict__ proj, float* __restrict__ x, const fl
     for (int j = 0; j < NJ; ++j) *reinterpret_cast<float2*>(x + base + (size_t)t * C + 64 * j) = make_float2(v[t][2 * j], v[t][2 * j + 1]);
   }
   if (!a_out) return;
+  if (!gn_g) {   // plain 16-bit copy of the new residual stream
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        uint32_t pk;
+        if (fp16) { __half2 h = __floats2half2_rn(v[t][2 * j], v[t][2 * j + 1]); pk = *reinterpret_cast<uint32_t*>(&h); }
+        else { __nv_bfloat162 h = __floats2bfloat162_rn(v[t][2 * j], v[t][2 * j + 1]); pk = *reinterpret_cast<uint32_t*>(&h); }
+        *reinterpret_cast<uint32_t*>(a_out + base + (size_t)t * C + 64 * j) = pk;
+      }
+    return;
+  }
   // GroupNorm over (board, 16 channels): channel 2l + 64j belongs to group 4j + l / 8 -> 8 lanes x 8 tokens x 8 warps
   const int sub = lane >> 3;
   float gm[NJ], gr[NJ];
@@ -461,17 +482,23 @@ int nn_layernorm_residual_f32(const float* proj, const float* x, const float* ga
   return m0_check_launch("layernorm_residual_f32");
 }
 // x <- LN(proj + x) in place; a_out (optional) = half(act(GroupNorm(x))) with the next block's bn1 parameters
-int nn_ln_res_gn(const float* proj, float* x, const float* ln_g, const float* ln_b, const float* gn_g, const float* gn_b, __nv_bfloat16* a_out,
-                 int B, int C, int act, cudaStream_t s) {
+int nn_ln_res_gn(const void* proj, int proj_half, float* x, const float* ln_g, const float* ln_b, const float* gn_g, const float* gn_b,
+                 __nv_bfloat16* a_out, int B, int C, int act, cudaStream_t s) {
   const int fp16 = g_half_fp16;
+  const float* p = reinterpret_cast<const float*>(proj);
+#define M0_LN_CASE(NJ)                                                                                                    \
+  if (proj_half) ln_res_gn_kernel<NJ, true><<<B, 256, 0, s>>>(p, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16);            \
+  else ln_res_gn_kernel<NJ, false><<<B, 256, 0, s>>>(p, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16);                     \
+  break;
   switch (C) {
-    case 64: ln_res_gn_kernel<1><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
-    case 128: ln_res_gn_kernel<2><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
-    case 192: ln_res_gn_kernel<3><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
-    case 256: ln_res_gn_kernel<4><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
-    case 320: ln_res_gn_kernel<5><<<B, 256, 0, s>>>(proj, x, ln_g, ln_b, gn_g, gn_b, a_out, act, fp16); break;
+    case 64: M0_LN_CASE(1)
+    case 128: M0_LN_CASE(2)
+    case 192: M0_LN_CASE(3)
+    case 256: M0_LN_CASE(4)
+    case 320: M0_LN_CASE(5)
     default: m0_set_error("ln_res_gn: unsupported channel count %d", C); return M0_ERR_ARG;
   }
+#undef M0_LN_CASE
   return m0_check_launch("ln_res_gn");
 }
 int nn_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, cudaStream_t s) {

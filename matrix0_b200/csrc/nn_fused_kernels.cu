@@ -342,6 +342,20 @@ int nn_se_hidden(const float* part, int splits, long long split_stride, const fl
   se_hidden_kernel<<<(B * hid + 255) / 256, 256, 0, s>>>(part, splits, split_stride, b1, hidden, B, hid, ld, act, nn_half_format());
   return m0_check_launch("se_hidden");
 }
+// value = tanh(value_fc3(h * gate)) (resnet.py:750-753): one warp per board, h = value_fc2 output, gate = sigmoid(value_gate(h))
+__global__ void value_tail_kernel(const float* __restrict__ gate, const float* __restrict__ h, const float* __restrict__ w3, const float* __restrict__ b3,
+                                  float* __restrict__ values, int B, int C) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(w3[c], h[(size_t)b * C + c] * gate[(size_t)b * C + c], acc);
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, off);
+  if (lane == 0) values[b] = tanhf(acc + b3[0]);
+}
+int nn_value_tail(const float* gate, const float* h, const float* w3, const float* b3, float* values, int B, int C, cudaStream_t s) {
+  value_tail_kernel<<<(B + 7) / 8, 256, 0, s>>>(gate, h, w3, b3, values, B, C);
+  return m0_check_launch("value_tail");
+}
 int nn_planes_to_nhwc_half(const float* planes, __nv_bfloat16* out, int B, int P, cudaStream_t s) {
   const size_t total = (size_t)B * 64 * 64;
   planes_to_nhwc_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, out, B, P, nn_half_format());

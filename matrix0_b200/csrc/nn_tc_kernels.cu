@@ -27,6 +27,7 @@ int nn_se_hidden(const float* part, int splits, long long split_stride, const fl
 int nn_gn_act_res(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride, float* out,
                   __nv_bfloat16* out_half, int B, int C, int act, cudaStream_t s);
 int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half, int B, int C, int heads, float mix, cudaStream_t s);
+int nn_value_tail(const float* gate, const float* h, const float* w3, const float* b3, float* values, int B, int C, cudaStream_t s);
 int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float* w2t, const float* b2, float* gate, int B, int C, int hid, int act,
                cudaStream_t s);
 }  // namespace m0
@@ -196,10 +197,12 @@ struct TcState {
   __nv_bfloat16* qkv_h = nullptr;   // [cap][64][3C] half (attention input)
   // heads on tensor cores
   bool heads_tc = false;
-  TcWeight pol_conv, pol_fc1, pol_fc2, val_conv1, val_conv2, val_fc1;
+  TcWeight pol_conv, pol_fc1, pol_fc2, val_conv1, val_conv2, val_fc1, val_fc2, val_gate;
+  bool val_tail_tc = false;      // value_fc2 and value_gate on tensor cores as well (C % 64 == 0)
   int pol_rank_pad = 0;
   __nv_bfloat16 *ph_h = nullptr, *pf_h = nullptr, *vh_h = nullptr;   // [cap][4096], [cap][rank_pad], [cap][64][128]
-  CUtensorMap ph_mat, pf_mat, vh_conv_mat, vh_fc_mat;
+  __nv_bfloat16 *vf1_h = nullptr, *vf2_h = nullptr;                  // [cap][2C], [cap][C]: operands of value_fc2 / value_gate
+  CUtensorMap ph_mat, pf_mat, vh_conv_mat, vh_fc_mat, vf1_mat, vf2_mat;
   CUtensorMap planes_conv;
   TcWeight stem;
   // bf16 activation buffers [cap][64][C] and their maps
@@ -523,6 +526,9 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
   if (st->ph_h) cudaFree(st->ph_h);
   if (st->pf_h) cudaFree(st->pf_h);
   if (st->vh_h) cudaFree(st->vh_h);
+  if (st->vf1_h) cudaFree(st->vf1_h);
+  if (st->vf2_h) cudaFree(st->vf2_h);
+  st->vf1_h = st->vf2_h = nullptr;
   if (st->prims) cudaFree(st->prims);
   if (st->se_hid_h) cudaFree(st->se_hid_h);
   if (st->se_part) cudaFree(st->se_part);
@@ -548,6 +554,12 @@ int tc_reserve(m0_net* n, TcState* st, int B) {
     TRY(make_map_2d(&st->pf_mat, st->pf_h, (uint64_t)need, rp, 128));
     TRY(make_map_2d(&st->vh_conv_mat, st->vh_h, (uint64_t)need * 64, 128, 128));
     TRY(make_map_2d(&st->vh_fc_mat, st->vh_h, (uint64_t)need, 8192, 128));
+    if (st->val_tail_tc) {
+      M0_CUDA_TRY(cudaMalloc((void**)&st->vf1_h, (size_t)need * 2 * C * 2));
+      M0_CUDA_TRY(cudaMalloc((void**)&st->vf2_h, (size_t)need * C * 2));
+      TRY(make_map_2d(&st->vf1_mat, st->vf1_h, (uint64_t)need, 2 * C, 128));
+      TRY(make_map_2d(&st->vf2_mat, st->vf2_h, (uint64_t)need, C, 128));
+    }
   }
   if (st->se_fused && n->cfg.se) {
     // rows are padded to whole 128-row GEMM tiles; the padding columns of the hidden layer stay zero
@@ -648,6 +660,11 @@ int tc_net_prepare(::m0_net* n, cudaStream_t s) {
       if ((rc = make_weight(st, &st->val_conv1, n->w.val_conv1_w, 128, C, 128, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->val_conv2, n->w.val_conv2_w, 128, 128, 128, s)) != M0_OK) break;
       if ((rc = make_weight(st, &st->val_fc1, n->w.val_fc1_w, 2 * C, 8192, C, s)) != M0_OK) break;
+      if (C % 64 == 0 && env_int("M0_TC_VALUE_TAIL", 1)) {
+        if ((rc = make_weight(st, &st->val_fc2, n->w.val_fc2_w, C, 2 * C, slice_width_for(C, C), s)) != M0_OK) break;
+        if ((rc = make_weight(st, &st->val_gate, n->w.val_gate_w, C, C, slice_width_for(C, C), s)) != M0_OK) break;
+        st->val_tail_tc = true;
+      }
       st->heads_tc = true;
     }
     if (c.chess_features) {
@@ -707,6 +724,8 @@ void tc_net_release(::m0_net* n) {
     if (st->ph_h) cudaFree(st->ph_h);
     if (st->pf_h) cudaFree(st->pf_h);
     if (st->vh_h) cudaFree(st->vh_h);
+    if (st->vf1_h) cudaFree(st->vf1_h);
+    if (st->vf2_h) cudaFree(st->vf2_h);
     if (st->prims) cudaFree(st->prims);
     if (st->se_hid_h) cudaFree(st->se_hid_h);
     if (st->se_part) cudaFree(st->se_part);
@@ -757,6 +776,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   // a1 = act(GN1(x)) of the first block; later blocks get it from the fused SE / residual kernel of their predecessor
   if (c.blocks > 0) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[0].gn1_w, w.blocks[0].gn1_b, st->a1, B, C, act, s));
   int att_seen = 0;
+  bool heads_input_ready = false;   // a1 already holds half(x) of the final residual stream
   const int stride = c.infer_attention_stride > 1 ? c.infer_attention_stride : 1;
   for (int i = 0; i < c.blocks; ++i) {
     const m0_block_weights& b = w.blocks[i];
@@ -824,11 +844,18 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
         PROF("attention_f32", nn_attention_f32(n->qkv, rb, n->t1, B, C, c.attention_heads, c.attention_unmasked_mix, s));
         PROF("f32_to_bf16", nn_f32_to_bf16(n->t1, st->a2, (size_t)M * C, s));
       }
-      PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, n->t2, nullptr, C, s, &st->t2f_out));
-      // x = LN(proj + x) and, in the same pass, a1 = act(GN1_{i+1}(x)) for the next block
-      if (C % 64 == 0 && C <= 320) {
-        PROF("ln_res_gn", nn_ln_res_gn(n->t2, n->x, b.att_ln_w, b.att_ln_b, last ? nullptr : w.blocks[i + 1].gn1_w, last ? nullptr : w.blocks[i + 1].gn1_b,
-                                       last ? nullptr : st->a1, B, C, act, s));
+      // the projection leaves the GEMM in the 16-bit operand format, as under the reference's autocast (M0_TC_PROJ_F32=1: fp32 hand-off)
+      static int proj_f32 = -1;
+      if (proj_f32 < 0) proj_f32 = env_int("M0_TC_PROJ_F32", 0);
+      const bool fused_ln = C % 64 == 0 && C <= 320;
+      const bool proj_half = fused_ln && !proj_f32;
+      if (proj_half) PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, nullptr, reinterpret_cast<__nv_bfloat16*>(n->t2), C, s, &st->t2h_out));
+      else PROF("gemm_proj", gemm_rows64(st, st->a2_mat, tb.proj, B, C, n->t2, nullptr, C, s, &st->t2f_out));
+      // x = LN(proj + x) and, in the same pass, a1 = act(GN1_{i+1}(x)) for the next block (after the last block: a1 = half(x) for the heads)
+      if (fused_ln) {
+        heads_input_ready = last && st->heads_tc;
+        PROF("ln_res_gn", nn_ln_res_gn(n->t2, proj_half ? 1 : 0, n->x, b.att_ln_w, b.att_ln_b, last ? nullptr : w.blocks[i + 1].gn1_w,
+                                       last ? nullptr : w.blocks[i + 1].gn1_b, (last && !st->heads_tc) ? nullptr : st->a1, B, C, act, s));
       } else {
         PROF("layernorm_residual_f32", nn_layernorm_residual_f32(n->t2, n->x, b.att_ln_w, b.att_ln_b, n->x, M, C, s));
         if (!last) PROF("se_apply_gn", nn_se_apply_gn(nullptr, nullptr, n->x, w.blocks[i + 1].gn1_w, w.blocks[i + 1].gn1_b, st->a1, B, C, act, s));
@@ -838,7 +865,7 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   if (!st->heads_tc) return net_forward_heads_f32(n, B, logits, values, s);
   // ---- heads (resnet.py:697-753) on tensor cores; the three small value layers after fc1 stay in fp32 ----
   const int vact = c.value_activation, r = c.policy_factor_rank, rp = st->pol_rank_pad;
-  PROF("f32_to_bf16", nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
+  if (!heads_input_ready) PROF("f32_to_bf16", nn_f32_to_bf16(n->x, st->a1, (size_t)M * C, s));
   // policy: conv1x1 C->64, GN, act, fc1 + ReLU, fc2 * logit scale
   PROF("gemm_pol_conv", launch_gemm(st, st->a1_mat, st->pol_conv, M, 0, 1, C, 0, 64, n->t1, nullptr, 64, 0, none, ACT_NONE, 1.0f, s));
   PROF("gn_act_res", nn_gn_act_res(n->t1, w.pol_gn_w, w.pol_gn_b, nullptr, 0, nullptr, st->ph_h, B, 64, act, s));
@@ -851,11 +878,23 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
   PROF("gn_act_res", nn_gn_act_res(n->vh1, w.val_gn1_w, w.val_gn1_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
   PROF("gemm_val_conv2", launch_gemm(st, st->vh_conv_mat, st->val_conv2, M, 0, 1, 128, 0, 128, n->vh1, nullptr, 128, 0, none, ACT_NONE, 1.0f, s));
   PROF("gn_act_res", nn_gn_act_res(n->vh1, w.val_gn2_w, w.val_gn2_b, nullptr, 0, nullptr, st->vh_h, B, 128, act, s));
-  PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, 0, C, n->vf1, nullptr, 2 * C, 0, w.val_fc1_b, vact, 1.0f, s, nullptr, nullptr,
-                                   nullptr, -1, 2));
-  PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
-  PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf2, w.val_gate_w, w.val_gate_b, n->vf2, n->vg, B, C, C, C, C, 0, ACT_SIGMOID, 1.0f, s));
-  PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vg, w.val_fc3_w, w.val_fc3_b, nullptr, values, B, 1, C, C, 1, 0, ACT_TANH, 1.0f, s));
+  if (st->val_tail_tc) {
+    // fc1 (+ activation) -> 16-bit, fc2 (+ activation) and the gate's linear layer + sigmoid on tensor cores (resnet.py:747-752);
+    // value = tanh(fc3(fc2_out * gate)) in one small reduction kernel
+    PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, 0, C, nullptr, st->vf1_h, 2 * C, 0, w.val_fc1_b, vact, 1.0f, s, nullptr,
+                                     nullptr, nullptr, -1, 2));
+    PROF("gemm_val_fc2", launch_gemm(st, st->vf1_mat, st->val_fc2, B, 0, 1, 2 * C, 0, st->val_fc2.n_launch, n->vf2, st->vf2_h, C, 0, w.val_fc2_b, vact, 1.0f, s,
+                                     nullptr, nullptr, nullptr, -1, C / st->val_fc2.n_launch));
+    PROF("gemm_val_gate", launch_gemm(st, st->vf2_mat, st->val_gate, B, 0, 1, C, 0, st->val_gate.n_launch, n->vg, nullptr, C, 0, w.val_gate_b, ACT_SIGMOID, 1.0f,
+                                      s, nullptr, nullptr, nullptr, -1, C / st->val_gate.n_launch));
+    PROF("value_tail", nn_value_tail(n->vg, n->vf2, w.val_fc3_w, w.val_fc3_b, values, B, C, s));
+  } else {
+    PROF("gemm_val_fc1", launch_gemm(st, st->vh_fc_mat, st->val_fc1, B, 0, 1, 8192, 0, C, n->vf1, nullptr, 2 * C, 0, w.val_fc1_b, vact, 1.0f, s, nullptr, nullptr,
+                                     nullptr, -1, 2));
+    PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf1, w.val_fc2_w, w.val_fc2_b, nullptr, n->vf2, B, C, 2 * C, 2 * C, C, 0, vact, 1.0f, s));
+    PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vf2, w.val_gate_w, w.val_gate_b, n->vf2, n->vg, B, C, C, C, C, 0, ACT_SIGMOID, 1.0f, s));
+    PROF("gemm_f32", nn_gemm_f32(A_DIRECT, n->vg, w.val_fc3_w, w.val_fc3_b, nullptr, values, B, 1, C, C, 1, 0, ACT_TANH, 1.0f, s));
+  }
   if (TcProfiler::get().enabled()) TcProfiler::get().collect();
   return M0_OK;
 }

@@ -129,22 +129,33 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
     }
     __syncwarp();
     c_path += depth + 1;
-    bool terminal;
-    double tv;
-    warp_leaf_moves(E, P, g, pos, depth, cur_key, s_moves[wib], &terminal, &tv, lane);
-    if (terminal) {
-      warp_backup(E, g, depth + 1, py_clip_unit(tv), 1, lane);   // mcts.py:747-751: immediately, visible to the rest of the batch
-      c_term++;
-      continue;
-    }
-    // sample {board, node, path}: find / append the leaf in the game's leaf table.  A row is shared only by samples with the same node
-    // AND the same board: a transposition-table node can be reached with different clocks (not part of the key, but part of the
-    // planes), and the reference evaluates every sample's own board (mcts.py:571-583)
+    // Is this leaf already in the game's leaf table (same node, same board)?  Then an earlier simulation of this mini-batch found it
+    // alive -- legal moves exist, material and the 75-move clock are properties of the board -- and only the repetition test, which
+    // looks at THIS path, has to be repeated.  Otherwise generate the moves and test the position (board.is_game_over(), mcts.py:747).
     int slot = -1;
     const u64* lp = E.ml_leaf_pos + (size_t)g * E.ml_cap * POSITION_WORDS;
     for (int r = lane; r < n_leaves; r += 32)
       if (leaf_node[r] == node && lp[(size_t)r * POSITION_WORDS + 8] == pos.state) slot = r;
     for (int off = 16; off > 0; off >>= 1) slot = max(slot, __shfl_xor_sync(FULL, slot, off));
+    bool terminal = false;
+    double tv = P.draw_penalty;
+    if (slot >= 0) {
+      if (pos_halfmove(pos) >= 8) {
+        int rep = 0;
+        if (lane == 0) rep = leaf_is_fivefold(E, g, depth, cur_key) ? 1 : 0;
+        terminal = __shfl_sync(FULL, rep, 0) != 0;
+      }
+    } else {
+      warp_leaf_moves(E, P, g, pos, depth, cur_key, s_moves[wib], &terminal, &tv, lane);
+    }
+    if (terminal) {
+      warp_backup(E, g, depth + 1, py_clip_unit(tv), 1, lane);   // mcts.py:747-751: immediately, visible to the rest of the batch
+      c_term++;
+      continue;
+    }
+    // sample {board, node, path}.  A row is shared only by samples with the same node AND the same board: a transposition-table node
+    // can be reached with different clocks (not part of the key, but part of the planes), and the reference evaluates every sample's
+    // own board (mcts.py:571-583)
     if (slot < 0) {
       slot = n_leaves++;
       if (lane == 0) {

@@ -86,7 +86,7 @@ def resolve_mcts_config(cfg_dict: Dict[str, Any]) -> MCTSConfig:
 class SelfPlayEngine:
     def __init__(self, model, cfg_dict: Dict[str, Any], games: int = 4096, device: Optional[int] = None, deterministic: bool = False,
                  seed: int = 1234, precision: Optional[str] = None, max_nodes: Optional[int] = None, cuda_graph: bool = True,
-                 search_mode: str = "collapsed", forward_rows: int = 4096):
+                 search_mode: str = "collapsed", forward_rows: Optional[int] = None):
         """``search_mode``:
         ``"collapsed"``   one selection per game and mini-batch, backed up with the multiplicity of the batch: exactly the reference
                           when its jitter is neutralised (SURVEY Q1; ``deterministic=True`` is bit-exact), and the throughput mode;
@@ -123,6 +123,10 @@ class SelfPlayEngine:
             self.engine.configure(self.mcfg, deterministic, seed, virtual_loss=self.virtual_loss)
             if search_mode == "as_shipped":
                 self.engine.enable_multi(bs, virtual_loss=self.virtual_loss)
+                if forward_rows is None:
+                    # as shipped a mini-batch holds ~1.1 distinct leaves per game (entropy noise makes the priors peaked): one evaluator
+                    # call of G + G/8 rows takes them all in the common case; the virtual-loss mode fills whole 4096-row calls
+                    forward_rows = 4096 if self.virtual_loss else min(8192, (self.G + max(256, self.G // 8) + 127) // 128 * 128)
                 self.forward_rows = max(bs, min(int(forward_rows), self.G * bs))
                 self.forward_rows += self.forward_rows & 1
                 # evaluator batch sizes: full chunks of forward_rows rows, the tail chunk in the smallest size that holds it
