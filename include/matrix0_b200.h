@@ -144,10 +144,12 @@ int m0_search_set_streams(m0_engine* e, const double* d_jitter, long long jitter
 int m0_search_select_multi(m0_engine* e, int batch_n, int32_t* d_sims_left, int32_t* d_row_base, int32_t* d_n_samples, void* stream);
 /* encode_board of the collected leaves of games [g0, g1) into d_planes float32[rows][19][8][8]; mode 0 compact rows (row_base[g] + slot
  * - row0), 1 dense per leaf ((g - g0) * samples_per_batch + slot), 2 one row per sample in collection order */
-int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, float* d_planes, void* stream);
+int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, float* d_planes, int row_cap, void* stream);
 /* expansion (+ entropy noise, pruning, TT registration) and backup of the samples of games [g0, g1) in collection order (mcts.py:654-670) */
+/* row_cap > 0 (compact rows): games whose rows end beyond row0 + row_cap are skipped by m0_search_multi_encode AND by this call and keep
+ * their samples, so an evaluator batch of row_cap rows can be launched before the host has read the row numbering */
 int m0_search_expand_backup_multi(m0_engine* e, int g0, int g1, const float* d_logits, int logits_stride, const float* d_values, int row0,
-                                  int per_sample, void* stream);
+                                  int per_sample, int row_cap, void* stream);
 int m0_engine_counters(m0_engine* e, unsigned long long* h_out16); /* host buffer; synchronises */
 int m0_engine_status(m0_engine* e, int32_t* d_status_out, int32_t* d_node_count_out, void* stream);
 

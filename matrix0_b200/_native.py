@@ -53,8 +53,8 @@ SIGNATURES = {
     "m0_search_multi_enable": (c_int, [c_void_p, c_int, c_int]),
     "m0_search_set_streams": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "m0_search_select_multi": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "m0_search_multi_encode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "m0_search_expand_backup_multi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "m0_search_multi_encode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "m0_search_expand_backup_multi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "m0_engine_counters": (c_int, [c_void_p, c_void_p]),
     "m0_engine_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "m0_search_select_var": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

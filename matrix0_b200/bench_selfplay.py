@@ -138,7 +138,7 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
         net.forward_planes(planes, precision)
     torch.cuda.synchronize()
     conv_ms, conv_n, site_ms = 0.0, 0, {}
-    for site in ("conv1+gn", "conv2+pool", "conv2+se+res+gn", "se_apply_gn", "se_gate", "se_fc1", "se_hidden", "se_fc2", "attention_tc", "gemm_qkv", "gemm_proj",
+    for site in ("conv1+gn", "conv2+pool", "conv2+se+res+gn", "se_apply_gn", "se_gate", "se_fc1", "se_hidden", "se_fc2", "se_tail", "attention_tc", "gemm_qkv", "gemm_proj",
                  "layernorm_residual_f32", "ln_res_gn", "gn_act_res", "conv_other", "gemm_pst", "planes_to_nhwc_half", "f32_to_bf16", "gemm_pol_conv",
                  "gemm_pol_fc1", "gemm_pol_fc2", "gemm_val_conv1", "gemm_val_conv2", "gemm_val_fc1", "gemm_val_fc2", "gemm_val_gate", "value_tail", "gemm_f32"):
         ms, cnt = ctypes.c_double(0), ctypes.c_longlong(0)
@@ -275,6 +275,7 @@ def bench_as_shipped(net, cfg, G, local, seed, precision, stream, moves=2, searc
     import torch
     from matrix0_b200.selfplay import SelfPlayEngine
     sp = SelfPlayEngine(net, cfg, games=G, device=local, deterministic=False, seed=seed, precision=precision, search_mode=search_mode)
+    sp.warm_up_forward()
     sp.start()
     sp.play_move()
     torch.cuda.synchronize()

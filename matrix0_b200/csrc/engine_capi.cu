@@ -18,9 +18,9 @@ __global__ void search_add_dirichlet_kernel(EngineView E, const double* noise, c
 // kernels (tree_multi_kernels.cu)
 __global__ void search_select_multi_kernel(EngineView E, int batch_cap, int* sims_left);
 __global__ void multi_scan_kernel(EngineView E);
-__global__ void multi_encode_kernel(EngineView E, int g0, int g1, int row0, int mode, float* planes);
+__global__ void multi_encode_kernel(EngineView E, int g0, int g1, int row0, int mode, float* planes, int row_cap);
 __global__ void search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* logits, int logits_stride, const float* values,
-                                                  int row0, int per_sample);
+                                                  int row0, int per_sample, int row_cap);
 }  // namespace m0
 
 using namespace m0;
@@ -313,13 +313,15 @@ int m0_search_select_multi(m0_engine* e, int batch_n, int32_t* d_sims_left, int3
   return M0_OK;
 }
 
+// row_cap > 0 (compact rows only): games whose rows do not end within row_cap rows of row0 are skipped by BOTH calls and keep their
+// samples -- the host can launch an evaluator batch for "as many leading games as fit" before it has read the row numbering.
 // encode_board of the collected leaves of games [g0, g1) (mcts.py:571-583).  mode 0: compact rows, row = row_base[g] + slot - row0;
 // mode 1: dense per leaf, row = (g - g0) * samples_per_batch + slot; mode 2: one row per SAMPLE in collection order (duplicates
 // repeated, as the reference's batch tensor holds them), row = (g - g0) * samples_per_batch + sample.
-int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, float* d_planes, void* stream) {
+int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, float* d_planes, int row_cap, void* stream) {
   if (!e || !d_planes || g0 < 0 || g1 > e->v.G || g0 >= g1 || e->v.ml_cap <= 0 || mode < 0 || mode > 2) { m0_set_error("m0_search_multi_encode: invalid argument"); return M0_ERR_ARG; }
   const long long warps = (long long)(g1 - g0) * e->v.ml_cap;
-  multi_encode_kernel<<<(unsigned)((warps + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, g0, g1, row0, mode, d_planes);
+  multi_encode_kernel<<<(unsigned)((warps + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(e->v, g0, g1, row0, mode, d_planes, mode == 0 ? row_cap : 0);
   return m0_check_launch("m0_search_multi_encode");
 }
 
@@ -327,13 +329,13 @@ int m0_search_multi_encode(m0_engine* e, int g0, int g1, int row0, int mode, flo
 // (mcts.py:654-670).  per_sample = 0: d_logits / d_values rows are the compact rows starting at row0 (one row per distinct leaf);
 // per_sample = 1: one row per sample, game g's rows start at (g - g0) * samples_per_batch (mode 2 of m0_search_multi_encode).
 int m0_search_expand_backup_multi(m0_engine* e, int g0, int g1, const float* d_logits, int logits_stride, const float* d_values, int row0,
-                                  int per_sample, void* stream) {
+                                  int per_sample, int row_cap, void* stream) {
   if (!e || !d_logits || !d_values || logits_stride < POLICY_SIZE || g0 < 0 || g1 > e->v.G || g0 >= g1 || e->v.ml_cap <= 0) {
     m0_set_error("m0_search_expand_backup_multi: invalid argument");
     return M0_ERR_ARG;
   }
   search_expand_backup_multi_kernel<<<(g1 - g0 + TREE_WARPS - 1) / TREE_WARPS, TREE_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      e->v, g0, g1, d_logits, logits_stride, d_values, row0, per_sample);
+      e->v, g0, g1, d_logits, logits_stride, d_values, row0, per_sample, per_sample ? 0 : row_cap);
   return m0_check_launch("m0_search_expand_backup_multi");
 }
 

@@ -342,6 +342,45 @@ int nn_se_hidden(const float* part, int splits, long long split_stride, const fl
   se_hidden_kernel<<<(B * hid + 255) / 256, 256, 0, s>>>(part, splits, split_stride, b1, hidden, B, hid, ld, act, nn_half_format());
   return m0_check_launch("se_hidden");
 }
+// The tail of the SE excitation in one launch (resnet.py:62-64): hidden = act(sum of the split-K partial sums of the first layer + b1),
+// gate = sigmoid(W2 hidden + b2).  Eight boards per block; the hidden vectors live in shared memory, thread = output channel, W2 is read
+// transposed ([hid][C]: coalesced across the threads, L1 / L2 resident: 102 KB).  The two tiny tensor-core launches it replaces
+// (reduction kernel + a [B x 128] x [128 x 320] GEMM) cost 9 + 25 us of mostly fixed overhead per block.
+static constexpr int SE_TAIL_BOARDS = 8;
+__global__ void se_tail_kernel(const float* __restrict__ part, int splits, long long split_stride, int ld, const float* __restrict__ b1,
+                               const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ gate, int B, int C, int hid, int act) {
+  extern __shared__ float s_hid[];   // [SE_TAIL_BOARDS][hid]
+  const int b0 = blockIdx.x * SE_TAIL_BOARDS;
+  const int nb = min(SE_TAIL_BOARDS, B - b0);
+  for (int i = threadIdx.x; i < nb * hid; i += blockDim.x) {
+    const int b = i / hid, u = i - b * hid;
+    float a = b1[u];
+    for (int ks = 0; ks < splits; ++ks) a += part[(size_t)ks * split_stride + (size_t)(b0 + b) * ld + u];
+    s_hid[b * hid + u] = fk_act(a, act);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[SE_TAIL_BOARDS];
+#pragma unroll
+    for (int b = 0; b < SE_TAIL_BOARDS; ++b) acc[b] = 0.f;
+    for (int u = 0; u < hid; ++u) {
+      const float w = __ldg(w2t + (size_t)u * C + c);
+#pragma unroll
+      for (int b = 0; b < SE_TAIL_BOARDS; ++b) acc[b] = fmaf(w, s_hid[b * hid + u], acc[b]);
+    }
+    const float bias = b2[c];
+#pragma unroll
+    for (int b = 0; b < SE_TAIL_BOARDS; ++b)
+      if (b < nb) gate[(size_t)(b0 + b) * C + c] = __fdividef(1.0f, 1.0f + __expf(-(acc[b] + bias)));
+  }
+}
+int nn_se_tail(const float* part, int splits, long long split_stride, int ld, const float* b1, const float* w2t, const float* b2, float* gate, int B,
+               int C, int hid, int act, cudaStream_t s) {
+  const int threads = C >= 512 ? 512 : ((C + 31) / 32 * 32);
+  se_tail_kernel<<<(B + SE_TAIL_BOARDS - 1) / SE_TAIL_BOARDS, threads, (size_t)SE_TAIL_BOARDS * hid * sizeof(float), s>>>(
+      part, splits, split_stride, ld, b1, w2t, b2, gate, B, C, hid, act);
+  return m0_check_launch("se_tail");
+}
 // value = tanh(value_fc3(h * gate)) (resnet.py:750-753): one warp per board, h = value_fc2 output, gate = sigmoid(value_gate(h))
 __global__ void value_tail_kernel(const float* __restrict__ gate, const float* __restrict__ h, const float* __restrict__ w3, const float* __restrict__ b3,
                                   float* __restrict__ values, int B, int C) {

@@ -27,6 +27,8 @@ int nn_se_hidden(const float* part, int splits, long long split_stride, const fl
 int nn_gn_act_res(const float* x, const float* gamma, const float* beta, const float* residual, long long residual_bstride, float* out,
                   __nv_bfloat16* out_half, int B, int C, int act, cudaStream_t s);
 int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half, int B, int C, int heads, float mix, cudaStream_t s);
+int nn_se_tail(const float* part, int splits, long long split_stride, int ld, const float* b1, const float* w2t, const float* b2, float* gate, int B,
+               int C, int hid, int act, cudaStream_t s);
 int nn_value_tail(const float* gate, const float* h, const float* w3, const float* b3, float* values, int B, int C, cudaStream_t s);
 int nn_se_gate(const float* pool, const float* w1t, const float* b1, const float* w2t, const float* b2, float* gate, int B, int C, int hid, int act,
                cudaStream_t s);
@@ -806,9 +808,18 @@ int tc_net_forward(::m0_net* n, const float* planes, int B, float* logits, float
         } else {
           PROF("se_fc1", launch_gemm(st, st->prims_mat, tb.se_fold, B, 0, 1, 12 * C, 0, c.se_hidden, st->se_part, nullptr, st->hid_pad, 0, none, ACT_NONE, 1.0f, s,
                                      nullptr, nullptr, nullptr, -1, 1, st->se_splits, (long long)st->se_rows * st->hid_pad));
+          static int se_tail = -1;
+          if (se_tail < 0) se_tail = env_int("M0_SE_TAIL", 1);
+          if (se_tail) {
+            // reduction of the partial sums + bias + activation + second SE layer + sigmoid in one small SIMT launch
+            PROF("se_tail", nn_se_tail(st->se_part, st->se_splits, (long long)st->se_rows * st->hid_pad, st->hid_pad, b.se_b1, st->se_w2t[i], b.se_b2,
+                                       st->se_gate, B, C, c.se_hidden, act, s));
+            goto se_done;
+          }
           PROF("se_hidden", nn_se_hidden(st->se_part, st->se_splits, (long long)st->se_rows * st->hid_pad, b.se_b1, st->se_hid_h, B, c.se_hidden, st->hid_pad, act, s));
         }
         PROF("se_fc2", launch_gemm(st, st->se_hid_mat, tb.se_w2, B, 0, 1, st->hid_pad, 0, C, st->se_gate, nullptr, C, 0, b.se_b2, ACT_SIGMOID, 1.0f, s));
+      se_done:;
       }
       // conv2 with the whole block tail in its epilogue: x += gate * conv2 ; a1 = act(GN1_{i+1}(x)) (or half(x) before attention)
       ConvFusion f2;

@@ -215,11 +215,12 @@ __global__ void __launch_bounds__(1024) multi_scan_kernel(EngineView E) {
 // encode_board of the collected leaves of games [g0, g1): one warp per (game, slot).  mode 0: compact rows, row = row_base[g] + leaf slot
 // - row0; mode 1: dense per leaf, row = (g - g0) * ml_cap + leaf slot; mode 2: one row per SAMPLE, row = (g - g0) * ml_cap + sample
 __global__ void __launch_bounds__(TREE_THREADS)
-multi_encode_kernel(EngineView E, int g0, int g1, int row0, int mode, float* __restrict__ planes) {
+multi_encode_kernel(EngineView E, int g0, int g1, int row0, int mode, float* __restrict__ planes, int row_cap) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
   const int g = g0 + (int)(w / E.ml_cap), r = (int)(w % E.ml_cap);
   if (g >= g1 || r >= (mode == 2 ? E.ml_n_samples[g] : E.ml_n_leaves[g])) return;
+  if (row_cap > 0 && E.ml_row_base[g + 1] - row0 > row_cap) return;   // this game's rows do not fit the evaluator batch: a later chunk
   const int leaf = mode == 2 ? E.ml_smp_leaf[(size_t)g * E.ml_cap + r] : r;
   const Position pos = load_position(E.ml_leaf_pos + ((size_t)g * E.ml_cap + leaf) * POSITION_WORDS);
   const size_t row = mode == 0 ? (size_t)(E.ml_row_base[g] + r - row0) : (size_t)(g - g0) * E.ml_cap + r;
@@ -233,7 +234,7 @@ multi_encode_kernel(EngineView E, int g0, int g1, int row0, int mode, float* __r
 //                 (sample, policy, value) does with an arbitrary backend).
 __global__ void __launch_bounds__(TREE_THREADS)
 search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* __restrict__ logits, int logits_stride, const float* __restrict__ values,
-                                  int row0, int per_sample) {
+                                  int row0, int per_sample, int row_cap) {
   __shared__ ExpandSmem s_x[TREE_WARPS];
   __shared__ u16 s_moves[TREE_WARPS][MAX_MOVES];
   __shared__ u16 s_idx[TREE_WARPS][MAX_MOVES];
@@ -242,6 +243,7 @@ search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* __r
   if (g >= g1 || !E.active[g]) return;
   const int n_samples = E.ml_n_samples[g];
   if (n_samples <= 0) return;
+  if (row_cap > 0 && E.ml_row_base[g + 1] - row0 > row_cap) return;   // not part of this evaluator batch (samples stay pending)
   const SearchParams& P = *E.params;
   const size_t nb = (size_t)g * E.max_nodes;
   const int* smp_leaf = E.ml_smp_leaf + (size_t)g * E.ml_cap;

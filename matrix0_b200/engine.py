@@ -207,15 +207,16 @@ class SearchEngine:
         _native.check(self._lib.m0_search_select_multi(self._h, int(batch_n), _native.ptr(sims_left), self.row_base.data_ptr(),
                                                        self.n_samples.data_ptr(), self._stream()), "m0_search_select_multi")
 
-    def multi_encode(self, g0: int, g1: int, row0: int, mode: int, planes) -> None:
-        _native.check(self._lib.m0_search_multi_encode(self._h, int(g0), int(g1), int(row0), int(mode), planes.data_ptr(), self._stream()),
-                      "m0_search_multi_encode")
+    def multi_encode(self, g0: int, g1: int, row0: int, mode: int, planes, row_cap: int = 0) -> None:
+        _native.check(self._lib.m0_search_multi_encode(self._h, int(g0), int(g1), int(row0), int(mode), planes.data_ptr(), int(row_cap),
+                                                       self._stream()), "m0_search_multi_encode")
 
-    def expand_backup_multi(self, g0: int, g1: int, logits, values, row0: int, per_sample: bool) -> None:
+    def expand_backup_multi(self, g0: int, g1: int, logits, values, row0: int, per_sample: bool, row_cap: int = 0) -> None:
         assert logits.dtype.is_floating_point and logits.element_size() == 4 and logits.is_contiguous()
         assert values.element_size() == 4 and values.is_contiguous()
         _native.check(self._lib.m0_search_expand_backup_multi(self._h, int(g0), int(g1), logits.data_ptr(), logits.shape[1], values.data_ptr(),
-                                                              int(row0), 1 if per_sample else 0, self._stream()), "m0_search_expand_backup_multi")
+                                                              int(row0), 1 if per_sample else 0, int(row_cap), self._stream()),
+                      "m0_search_expand_backup_multi")
 
     def counters(self) -> dict:
         buf = (ctypes.c_uint64 * 16)()

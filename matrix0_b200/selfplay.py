@@ -126,7 +126,9 @@ class SelfPlayEngine:
                 if forward_rows is None:
                     # as shipped a mini-batch holds ~1.1 distinct leaves per game (entropy noise makes the priors peaked): one evaluator
                     # call of G + G/8 rows takes them all in the common case; the virtual-loss mode fills whole 4096-row calls
-                    forward_rows = 4096 if self.virtual_loss else min(8192, (self.G + max(256, self.G // 8) + 127) // 128 * 128)
+                    # (measured 1.19 rows per game and mini-batch); sized in whole rounds of the convolution kernel: 74 CTA pairs x 4 boards
+                    rnd = 4 * max(1, torch.cuda.get_device_properties(self.device).multi_processor_count // 2)
+                    forward_rows = 4096 if self.virtual_loss else min(8192, max(rnd, -(-int(1.2 * self.G) // rnd) * rnd))
                 self.forward_rows = max(bs, min(int(forward_rows), self.G * bs))
                 self.forward_rows += self.forward_rows & 1
                 # evaluator batch sizes: full chunks of forward_rows rows, the tail chunk in the smallest size that holds it
@@ -275,15 +277,32 @@ class SelfPlayEngine:
             ev.append(e)
         self.steps += 1
 
+    def warm_up_forward(self) -> None:
+        """Capture the evaluator graphs of every batch size this engine uses (one-off cost of ~1 s per size, otherwise paid inside the
+        first move that needs the size)."""
+        if self.search_mode != "as_shipped":
+            return
+        for size in sorted(self.forward_sizes, reverse=True):
+            self._forward(self.ml_planes[:size])
+        self.nn_evals = self.nn_rows = 0
+
     def _search_step_as_shipped(self) -> None:
         """mcts.py:535-740 with jitter in force: collect batch_n samples per game, evaluate the distinct leaves of all games in
         compact batches (a chunk = a run of consecutive games whose rows fit ``forward_rows``), then expand / back up per game in
         collection order.  One small D2H read (the row numbering) per mini-batch sizes the evaluator calls."""
         eng = self.engine
         eng.select_multi(int(self.mcfg.inference_batch_size), self.sims_left)
-        rb = eng.row_base.cpu().numpy()
         G, cap = self.G, self.forward_rows
-        g0 = 0
+        # first evaluator batch WITHOUT waiting for the row numbering: the kernels take as many leading games as fit into `cap` rows
+        # (device-side gate on row_base), so the host's read below overlaps the forward instead of idling the GPU
+        planes = self.ml_planes[:cap]
+        eng.multi_encode(0, G, 0, 0, planes, row_cap=cap)
+        logits, values = self._forward(planes)
+        eng.expand_backup_multi(0, G, logits, values, 0, per_sample=False, row_cap=cap)
+        rb = eng.row_base.cpu().numpy()
+        g0 = max(int(np.searchsorted(rb, cap, side="right")) - 1, 0)        # games [0, g0) were in that batch
+        self.nn_rows += int(rb[g0]) - cap
+        self.nn_rows_padded += cap
         while g0 < G:
             g1 = int(np.searchsorted(rb, rb[g0] + cap, side="right")) - 1   # largest g1 with rb[g1] - rb[g0] <= cap
             g1 = min(max(g1, g0 + 1), G)

@@ -31,6 +31,7 @@ def main():
     net = PolicyValueNet.from_config(cfg["model"], device="cuda:0", precision="fp16", seed=0)
     sp = SelfPlayEngine(net, cfg, games=a.games, device=0, deterministic=False, seed=1234, precision="fp16", search_mode=a.mode)
     rec = GameRecorder(sp, ssl_tasks=("piece", "threat", "pin", "fork", "control"))
+    sp.warm_up_forward()
     sp.start()
 
     def move():
