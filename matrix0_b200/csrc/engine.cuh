@@ -104,6 +104,7 @@ struct EngineView {
   u64* ml_leaf_pos;       // [G][ml_cap][9]
   int* ml_row_base;       // [G + 1] exclusive prefix of ml_n_leaves: compact network rows
   u16* node_inflight;     // [G][max_nodes] in-flight selections of an edge child within the current mini-batch (virtual loss)
+  double* full_scratch;   // [G][4672] entropy noise over the FULL policy vector (legal_softmax = false, mcts.py:164-186); else NULL
 };
 
 static constexpr u32 MOVE_NONE = 0xFFFFu;

@@ -148,10 +148,9 @@ int m0_engine_configure(m0_engine* e, const m0_search_config* c, void* stream) {
   p.raw_logit_priors = c->raw_logit_priors ? 1 : 0;
   p.virtual_loss = c->virtual_loss;
   p.virtual_loss_on = (c->virtual_loss_on && c->virtual_loss > 0.0) ? 1 : 0;
-  if (p.entropy_noise && !p.legal_softmax) {
-    m0_set_error("m0_engine_configure: enable_entropy_noise with legal_softmax = false (noise over all 4672 entries, mcts.py:164-186) is not "
-                 "implemented on the device; set legal_softmax = true, enable_entropy_noise = false, or deterministic = 1");
-    return M0_ERR_ARG;
+  if (p.entropy_noise && !p.legal_softmax && !e->v.full_scratch) {
+    // noise over all 4672 entries of the full softmax (mcts.py:164-186): one float64 row of scratch per game
+    TRY(dev_alloc(e, &e->v.full_scratch, (size_t)e->v.G * POLICY_SIZE, false));
   }
   cudaStream_t s = (cudaStream_t)stream;
   M0_CUDA_TRY(cudaMemcpyAsync(e->d_params, &p, sizeof(p), cudaMemcpyHostToDevice, s));

@@ -349,24 +349,30 @@ int nn_se_hidden(const float* part, int splits, long long split_stride, const fl
 static constexpr int SE_TAIL_BOARDS = 8;
 __global__ void se_tail_kernel(const float* __restrict__ part, int splits, long long split_stride, int ld, const float* __restrict__ b1,
                                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ gate, int B, int C, int hid, int act) {
-  extern __shared__ float s_hid[];   // [SE_TAIL_BOARDS][hid]
+  extern __shared__ __align__(16) float s_hid[];   // [hid][SE_TAIL_BOARDS]: the eight boards' values of one hidden unit are two 16-byte reads
   const int b0 = blockIdx.x * SE_TAIL_BOARDS;
   const int nb = min(SE_TAIL_BOARDS, B - b0);
-  for (int i = threadIdx.x; i < nb * hid; i += blockDim.x) {
+  for (int i = threadIdx.x; i < SE_TAIL_BOARDS * hid; i += blockDim.x) {
     const int b = i / hid, u = i - b * hid;
-    float a = b1[u];
-    for (int ks = 0; ks < splits; ++ks) a += part[(size_t)ks * split_stride + (size_t)(b0 + b) * ld + u];
-    s_hid[b * hid + u] = fk_act(a, act);
+    float a = 0.f;
+    if (b < nb) {
+      a = b1[u];
+      for (int ks = 0; ks < splits; ++ks) a += part[(size_t)ks * split_stride + (size_t)(b0 + b) * ld + u];
+      a = fk_act(a, act);
+    }
+    s_hid[u * SE_TAIL_BOARDS + b] = a;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc[SE_TAIL_BOARDS];
 #pragma unroll
     for (int b = 0; b < SE_TAIL_BOARDS; ++b) acc[b] = 0.f;
+#pragma unroll 4
     for (int u = 0; u < hid; ++u) {
       const float w = __ldg(w2t + (size_t)u * C + c);
-#pragma unroll
-      for (int b = 0; b < SE_TAIL_BOARDS; ++b) acc[b] = fmaf(w, s_hid[b * hid + u], acc[b]);
+      const float4 h0 = *reinterpret_cast<const float4*>(s_hid + u * SE_TAIL_BOARDS), h1 = *reinterpret_cast<const float4*>(s_hid + u * SE_TAIL_BOARDS + 4);
+      acc[0] = fmaf(w, h0.x, acc[0]); acc[1] = fmaf(w, h0.y, acc[1]); acc[2] = fmaf(w, h0.z, acc[2]); acc[3] = fmaf(w, h0.w, acc[3]);
+      acc[4] = fmaf(w, h1.x, acc[4]); acc[5] = fmaf(w, h1.y, acc[5]); acc[6] = fmaf(w, h1.z, acc[6]); acc[7] = fmaf(w, h1.w, acc[7]);
     }
     const float bias = b2[c];
 #pragma unroll

@@ -77,6 +77,8 @@ template <>
 M0_HD float np_pairwise_sum_rec<0>(const float* a, int n) { return np_pairwise_block_f32(a, n); }
 // valid for n <= 1024 (three halvings); legal-move lists have n <= 256
 M0_HD float np_pairwise_sum_f32(const float* a, int n) { return np_pairwise_sum_rec<3>(a, n); }
+// valid for n <= 8192 (six halvings): the whole 4672-entry policy vector
+M0_HD float np_pairwise_sum_f32_big(const float* a, int n) { return np_pairwise_sum_rec<6>(a, n); }
 
 // the same reduction for float64 arrays (DOUBLE_pairwise_sum): `dist.sum()` at azchess/mcts.py:184 after the float64 noise was added
 M0_HD double np_pairwise_block_f64(const double* a, int n) {
@@ -105,6 +107,7 @@ M0_HD double np_pairwise_sum_rec_f64(const double* a, int n) {
 template <>
 M0_HD double np_pairwise_sum_rec_f64<0>(const double* a, int n) { return np_pairwise_block_f64(a, n); }
 M0_HD double np_pairwise_sum_f64(const double* a, int n) { return np_pairwise_sum_rec_f64<3>(a, n); }
+M0_HD double np_pairwise_sum_f64_big(const double* a, int n) { return np_pairwise_sum_rec_f64<6>(a, n); }
 
 // azchess/mcts.py:948: v = max(-1.0, min(1.0, float(value)))  with Python's min/max NaN behaviour
 M0_HD double py_clip_unit(double x) {

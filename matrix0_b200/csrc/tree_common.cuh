@@ -181,6 +181,44 @@ __device__ __forceinline__ void warp_expand(const EngineView& E, const SearchPar
       __syncwarp();
       for (int j = lane; j < k; j += 32) s_p[j] = f_div(s_p[j], sum);   // dist (legal_only) / dist[idx] (full softmax)
       __syncwarp();
+      if (P.entropy_noise && !P.legal_softmax && E.full_scratch) {
+        // mcts.py:164-186 on the FULL distribution: entropy over all 4672 entries against log(k), N(0, 0.1) on every entry, floor,
+        // renormalise over all 4672; the priors are then read at the legal indices.  Scratch: one float64 row per game in global memory.
+        double* d = E.full_scratch + (size_t)g * POLICY_SIZE;
+        float* t = reinterpret_cast<float*>(d);
+        for (int i = lane; i < POLICY_SIZE; i += 32) {
+          const float pi = f_div(expf(f_sub(lg[i], mx)), sum);
+          t[i] = f_mul(pi, logf(f_add(pi, 1e-8f)));
+        }
+        __syncwarp();
+        int noisy = 0;
+        if (lane == 0) {
+          const float ent = -np_pairwise_sum_f32_big(t, POLICY_SIZE);
+          const double hmax = log((double)(k > 1 ? k : 1));
+          noisy = d_div((double)ent, hmax > 1e-9 ? hmax : 1e-9) > 0.9 ? 1 : 0;
+        }
+        noisy = __shfl_sync(FULL, noisy, 0);
+        __syncwarp();
+        if (noisy) {
+          const unsigned long long cur = E.nrm_cursor[g];
+          if (E.nrm_stream && cur + (unsigned long long)POLICY_SIZE > (unsigned long long)E.nrm_stride && lane == 0) E.status[g] |= ST_STREAM_EXHAUSTED;
+          for (int i = POLICY_SIZE - 1 - lane; i >= 0; i -= 32) {   // descending: the float32 terms in the low half of the row are dead by now
+            const float pi = f_div(expf(f_sub(lg[i], mx)), sum);
+            const double x = d_add((double)pi, draw_noise_normal(E, P, g, cur, i));
+            d[i] = x > 1e-8 ? x : (x != x ? x : 1e-8);
+          }
+          __syncwarp();
+          double tot = 0.0;
+          if (lane == 0) {
+            tot = np_pairwise_sum_f64_big(d, POLICY_SIZE);
+            E.nrm_cursor[g] = cur + (unsigned long long)POLICY_SIZE;
+            atomicAdd(&E.counters[CTR_NOISY_EXPANSIONS], 1ull);
+          }
+          tot = __shfl_sync(FULL, tot, 0);
+          for (int j = lane; j < k; j += 32) s_p[j] = (float)d_div(d[idx[j]], tot);
+          __syncwarp();
+        }
+      }
       if (P.entropy_noise && P.legal_softmax) {
         // mcts.py:170-186 on the active (legal-only) distribution: H = -sum(dist * log(dist + 1e-8)) in float32,
         // ratio = H / max(1e-9, log(k)) in float64; above 0.9: dist + N(0, 0.1) in float64, floor 1e-8, renormalise

@@ -367,6 +367,7 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
     # "as_shipped": the reference's search with its configured selection jitter and entropy noise (distinct leaves per mini-batch);
     # "collapsed": one evaluated leaf per game and mini-batch (the throughput mode, exact when the jitter is neutralised)
     sp = SelfPlayEngine(model, cfg_dict, games=G, device=dev, deterministic=False, seed=seed, precision=precision, search_mode=search_mode)
+    sp.warm_up_forward()
     mcfg = cfg_dict.get("model", {}) or {}
     ssl_tasks = tuple(mcfg.get("ssl_tasks", ())) if mcfg.get("self_supervised", False) else ()      # internal.py:251-256
     rec = GameRecorder(sp, ssl_tasks=ssl_tasks)

@@ -33,7 +33,7 @@ from oracle import refload  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MIN_GAP = 2e-6
-N_JITTER, N_NORMAL = 600_000, 120_000
+N_JITTER, N_NORMAL = 600_000, 600_000
 
 CFGS = {
     # config.yaml as self-play resolves it ("effective configuration")
@@ -48,6 +48,9 @@ CFGS = {
     "prune": dict(cpuct_c_base=19652.0, cpuct_c_init=1.25, fpu_reduction=0.2, legal_softmax=True, selection_jitter=0.02,
                   inference_batch_size=24, no_instant_backtrack=False, draw_penalty=-0.3, enable_entropy_noise=True,
                   max_children=7, min_child_prior=0.012),
+    # MCTSConfig's own defaults: full-policy softmax WITH entropy noise -- N(0, 0.1) on all 4672 entries (mcts.py:164-186)
+    "default_full": dict(cpuct=2.5, fpu_reduction=0.15, draw_penalty=-0.1, legal_softmax=False, selection_jitter=0.01, inference_batch_size=16,
+                         enable_entropy_noise=True),
     # the reference without an inference backend: raw-logit priors below the root
     "direct": dict(cpuct=2.0, fpu_reduction=0.1, legal_softmax=True, selection_jitter=0.05, inference_batch_size=48, enable_entropy_noise=True),
 }
@@ -155,6 +158,10 @@ def main():
             plan.append(("prune", ("hash", 1.0, 500 + i), 150, fen, moves))
         if i % 4 == 1:
             plan.append(("direct", ("hash", 1.0, 600 + i), 150, fen, moves))
+    if not VL:   # appended last so that the seeds of the earlier cases stay what they were
+        for i in (0, 2, 5, 9, 13):
+            fen, moves = boards[i]
+            plan.append(("default_full", ("hash", 0.02 if i % 2 else 1.0, 900 + i), 96, fen, moves))
     cases, dropped = [], 0
     for ci, (cfg_name, backend, sims, fen, moves) in enumerate(plan):
         kw = dict(CFGS[cfg_name])

@@ -33,7 +33,7 @@ def test_reference_stochastic_goldens():
         S.check(c, vc, pi, v, m._last_root, prior_rtol=0.0 if c["backend"][1] == 0.0 else 1e-6)
         kinds[c["cfg"]] = kinds.get(c["cfg"], 0) + 1
         m._engine.close()
-    assert sum(kinds.values()) >= 60 and set(kinds) == {"selfplay", "selfplay_b32", "arena_full", "prune", "direct"}, kinds
+    assert sum(kinds.values()) >= 70 and set(kinds) == {"selfplay", "selfplay_b32", "arena_full", "prune", "direct", "default_full"}, kinds
 
 
 def test_virtual_loss_throughput_mode_goldens():
