@@ -347,7 +347,8 @@ int nn_se_hidden(const float* part, int splits, long long split_stride, const fl
 // transposed ([hid][C]: coalesced across the threads, L1 / L2 resident: 102 KB).  The two tiny tensor-core launches it replaces
 // (reduction kernel + a [B x 128] x [128 x 320] GEMM) cost 9 + 25 us of mostly fixed overhead per block.
 static constexpr int SE_TAIL_BOARDS = 8;
-__global__ void se_tail_kernel(const float* __restrict__ part, int splits, long long split_stride, int ld, const float* __restrict__ b1,
+__global__ void __launch_bounds__(320, 4)   // 4 blocks of 320 threads per SM: the 512 blocks of a 4096-board batch are one wave on 148 SMs
+se_tail_kernel(const float* __restrict__ part, int splits, long long split_stride, int ld, const float* __restrict__ b1,
                                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ gate, int B, int C, int hid, int act) {
   extern __shared__ __align__(16) float s_hid[];   // [hid][SE_TAIL_BOARDS]: the eight boards' values of one hidden unit are two 16-byte reads
   const int b0 = blockIdx.x * SE_TAIL_BOARDS;
@@ -367,12 +368,18 @@ __global__ void se_tail_kernel(const float* __restrict__ part, int splits, long 
     float acc[SE_TAIL_BOARDS];
 #pragma unroll
     for (int b = 0; b < SE_TAIL_BOARDS; ++b) acc[b] = 0.f;
-#pragma unroll 4
-    for (int u = 0; u < hid; ++u) {
-      const float w = __ldg(w2t + (size_t)u * C + c);
-      const float4 h0 = *reinterpret_cast<const float4*>(s_hid + u * SE_TAIL_BOARDS), h1 = *reinterpret_cast<const float4*>(s_hid + u * SE_TAIL_BOARDS + 4);
-      acc[0] = fmaf(w, h0.x, acc[0]); acc[1] = fmaf(w, h0.y, acc[1]); acc[2] = fmaf(w, h0.z, acc[2]); acc[3] = fmaf(w, h0.w, acc[3]);
-      acc[4] = fmaf(w, h1.x, acc[4]); acc[5] = fmaf(w, h1.y, acc[5]); acc[6] = fmaf(w, h1.z, acc[6]); acc[7] = fmaf(w, h1.w, acc[7]);
+    for (int u0 = 0; u0 < hid; u0 += 16) {     // sixteen weight loads in flight per thread, then the arithmetic
+      float w[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) w[k] = (u0 + k < hid) ? __ldg(w2t + (size_t)(u0 + k) * C + c) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (u0 + k >= hid) break;
+        const float4 h0 = *reinterpret_cast<const float4*>(s_hid + (u0 + k) * SE_TAIL_BOARDS);
+        const float4 h1 = *reinterpret_cast<const float4*>(s_hid + (u0 + k) * SE_TAIL_BOARDS + 4);
+        acc[0] = fmaf(w[k], h0.x, acc[0]); acc[1] = fmaf(w[k], h0.y, acc[1]); acc[2] = fmaf(w[k], h0.z, acc[2]); acc[3] = fmaf(w[k], h0.w, acc[3]);
+        acc[4] = fmaf(w[k], h1.x, acc[4]); acc[5] = fmaf(w[k], h1.y, acc[5]); acc[6] = fmaf(w[k], h1.z, acc[6]); acc[7] = fmaf(w[k], h1.w, acc[7]);
+      }
     }
     const float bias = b2[c];
 #pragma unroll
@@ -382,7 +389,7 @@ __global__ void se_tail_kernel(const float* __restrict__ part, int splits, long 
 }
 int nn_se_tail(const float* part, int splits, long long split_stride, int ld, const float* b1, const float* w2t, const float* b2, float* gate, int B,
                int C, int hid, int act, cudaStream_t s) {
-  const int threads = C >= 512 ? 512 : ((C + 31) / 32 * 32);
+  const int threads = C >= 320 ? 320 : ((C + 31) / 32 * 32);
   se_tail_kernel<<<(B + SE_TAIL_BOARDS - 1) / SE_TAIL_BOARDS, threads, (size_t)SE_TAIL_BOARDS * hid * sizeof(float), s>>>(
       part, splits, split_stride, ld, b1, w2t, b2, gate, B, C, hid, act);
   return m0_check_launch("se_tail");

@@ -256,3 +256,31 @@ def test_arena_two_evaluators_route_rows_and_score(golden_dir):
         sp.play_move()
         fin += sp.finished_games()
     assert sorted((f["moves"], f["reason"]) for f in fin[:G]) == sorted((r["moves"], r["reason"]) for r in res["games"])
+
+
+def test_reloading_weights_invalidates_the_captured_forward_graph(golden_dir):
+    """load_state_dict while a SelfPlayEngine holds a captured CUDA graph of the evaluator: the next step must run on the NEW weights
+    (the graph cache is keyed by the evaluator's workspace / weight epoch), not replay launches that point at freed buffers."""
+    from matrix0_b200.model import PolicyValueNet, parameter_shapes
+    from matrix0_b200.selfplay import SelfPlayEngine
+    from oracle import nn_ref
+    g, cfg, sd = load_case(golden_dir, "small")
+    net = PolicyValueNet(cfg, device="cuda", precision="fp16")
+    net.load_state_dict(sd, strict=True)
+    G = 32
+    c = {"mcts": dict(MCTS_KW, num_simulations=32, inference_batch_size=16), "selfplay": {"num_simulations": 32, "opening_random_plies": 4}}
+    sp = SelfPlayEngine(net, c, games=G, deterministic=False, seed=3, precision="fp16")
+    assert sp.cuda_graph
+    sp.start()
+    sp.play_move()
+    assert sp.graph_replays > 0
+    planes = sp.engine.planes
+    lg_old, v_old = [t.clone() for t in sp._forward(planes)]
+    sd2 = nn_ref.make_state_dict(parameter_shapes(cfg), seed=7)
+    net.load_state_dict(sd2, strict=True)
+    lg_new, v_new = [t.clone() for t in sp._forward(planes)]                 # through the engine's graph path
+    lg_ref, v_ref = net.forward_planes(planes, "fp16")                        # eager, same weights
+    assert torch.equal(lg_new, lg_ref) and torch.equal(v_new, v_ref)
+    assert not torch.equal(lg_new, lg_old)
+    sp.play_move()                                                            # and self-play continues on the new weights
+    sp.check_status()
