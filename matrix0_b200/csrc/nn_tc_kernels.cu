@@ -920,6 +920,12 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
     m0_set_error("m0_tc_conv: invalid argument (boards even, cin %% 64 == 0, n %% 16 == 0, n <= 320, taps in {1, 9})");
     return M0_ERR_ARG;
   }
+  // the operands of this entry point are bf16 by contract, whatever 16-bit format the last forward of the process selected
+  struct FormatGuard {
+    int saved;
+    FormatGuard() : saved(nn_half_format()) { nn_set_half_format(0); }
+    ~FormatGuard() { nn_set_half_format(saved); }
+  } format_guard;
   static TcState st;
   int dev = 0;
   cudaGetDevice(&dev);

@@ -15,9 +15,21 @@
 
 namespace m0 {
 
+// Most simulations of a mini-batch repeat the path of the one before them (nothing but terminal backups changes the tree during
+// collection): the move made at each depth, the position it leads to, its key and the transposition-table hop are remembered per
+// depth and reused while the path prefix stays the same -- only the PUCT scan with its fresh jitter draws is repeated.
+static constexpr int WALK_CACHE_DEPTH = 12;
+struct WalkCache {
+  u64 pos[WALK_CACHE_DEPTH][POSITION_WORDS];
+  Key128 key[WALK_CACHE_DEPTH];
+  int child[WALK_CACHE_DEPTH], nxt[WALK_CACHE_DEPTH];
+  u8 epl[WALK_CACHE_DEPTH], irrev[WALK_CACHE_DEPTH];
+};
+
 __global__ void __launch_bounds__(TREE_THREADS)
 search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_left) {
   __shared__ u16 s_moves[TREE_WARPS][MAX_MOVES];
+  __shared__ WalkCache s_cache[TREE_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * TREE_WARPS + wib;
   if (g >= E.G) return;
@@ -56,11 +68,14 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
     for (int i = lane; i < cnt; i += 32) inflight[i] = 0;
     __syncwarp();
   }
+  WalkCache& wc = s_cache[wib];
+  int cached = 0;   // depths 0 .. cached-1 of the cache describe the previous walk
   for (int sim = 0; sim < batch_n; ++sim) {
     Position pos = root_pos;
     int node = root, depth = 0;
     bool cur_epl = root_epl;
     Key128 cur_key = E.root_key[g];
+    bool same_prefix = true;
     while (true) {
       const int fc = E.node_first[nb + node];
       if (fc < 0) break;
@@ -106,22 +121,45 @@ search_select_multi_kernel(EngineView E, int batch_cap, int* __restrict__ sims_l
       }
       if (best_j < 0) best_j = 0;  // "Fallback: selected first child" (mcts.py:911-914)
       const int child = fc + best_j;
-      const Move mv = (Move)(E.node_mv[nb + child] & 0xFFFFu);
-      PushInfo info = push_move(pos, mv);
-      const bool irrev = info.zeroing || info.reduced_castling || cur_epl;
-      bool epl;
-      cur_key = position_key(pos, &epl);
-      cur_epl = epl;
-      int hop = 0;
-      if (lane == 0) hop = tt_get(E, g, cur_key);
-      hop = __shfl_sync(FULL, hop, 0);
-      const int nxt = hop >= 0 ? hop : child;  // node = self._tt_get(key) or best_child (mcts.py:919)
-      if (hop >= 0 && hop != child) c_hops++;
-      if (lane == 0) {
-        pirrev[depth] = irrev ? 1 : 0;
-        pkey[depth + 1] = cur_key;
-        path[depth + 1] = nxt;
-        if (vl) inflight[child] += 1;   // inflight_counts[best_child] += 1 (the EDGE child, mcts.py:922-923)
+      int nxt;
+      if (same_prefix && depth < cached && wc.child[depth] == child) {
+        // the same move as in the previous walk, from the same position: position, key, hop and the path entries are already there
+        pos = load_position(wc.pos[depth]);
+        cur_key = wc.key[depth];
+        cur_epl = wc.epl[depth] != 0;
+        nxt = wc.nxt[depth];
+        if (nxt != child) c_hops++;
+        if (vl && lane == 0) inflight[child] += 1;
+      } else {
+        same_prefix = false;
+        const Move mv = (Move)(E.node_mv[nb + child] & 0xFFFFu);
+        PushInfo info = push_move(pos, mv);
+        const bool irrev = info.zeroing || info.reduced_castling || cur_epl;
+        bool epl;
+        cur_key = position_key(pos, &epl);
+        cur_epl = epl;
+        int hop = 0;
+        if (lane == 0) hop = tt_get(E, g, cur_key);
+        hop = __shfl_sync(FULL, hop, 0);
+        nxt = hop >= 0 ? hop : child;  // node = self._tt_get(key) or best_child (mcts.py:919)
+        if (hop >= 0 && hop != child) c_hops++;
+        __syncwarp();
+        if (lane == 0) {
+          pirrev[depth] = irrev ? 1 : 0;
+          pkey[depth + 1] = cur_key;
+          path[depth + 1] = nxt;
+          if (vl) inflight[child] += 1;   // inflight_counts[best_child] += 1 (the EDGE child, mcts.py:922-923)
+          if (depth < WALK_CACHE_DEPTH) {
+            store_position(wc.pos[depth], pos);
+            wc.key[depth] = cur_key;
+            wc.child[depth] = child;
+            wc.nxt[depth] = nxt;
+            wc.epl[depth] = epl ? 1 : 0;
+            wc.irrev[depth] = irrev ? 1 : 0;
+          }
+        }
+        cached = depth < WALK_CACHE_DEPTH ? depth + 1 : WALK_CACHE_DEPTH;   // deeper entries belong to another path now
+        __syncwarp();
       }
       depth++;
       node = nxt;
@@ -251,7 +289,7 @@ search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* __r
   const int* leaf_node = E.ml_leaf_node + (size_t)g * E.ml_cap;
   const int* leaf_first = E.ml_leaf_first + (size_t)g * E.ml_cap;
   const long long base = per_sample ? (long long)(g - g0) * E.ml_cap : (long long)E.ml_row_base[g] - row0;
-  for (int s = 0; s < n_samples; ++s) {
+  for (int s = 0; s < n_samples;) {
     const int r = smp_leaf[s];
     const int node = leaf_node[r];
     if (E.node_first[nb + node] < 0) {   // `not node.is_expanded()` (mcts.py:657)
@@ -265,9 +303,25 @@ search_expand_backup_multi_kernel(EngineView E, int g0, int g1, const float* __r
       const long long lrow = base + (per_sample ? leaf_first[r] : r);
       if (k > 0) warp_expand(E, P, g, node, pos, s_moves[wib], s_idx[wib], k, logits + (size_t)lrow * logits_stride, true, false, s_x[wib], lane);
     }
+    // Consecutive samples with the same leaf row and the same path (the common case: a mini-batch mostly repeats one path) back the same
+    // value up the same nodes: `run` sequential backups collapse into one pass that performs the same `run` additions per node in the same
+    // order (backup_repeated), since nothing else touches those nodes in between.  Rows per sample may carry different values: no grouping.
+    const int len = smp_len[s];
+    const int* ps = E.ml_smp_path + ((size_t)g * E.ml_cap + s) * E.max_depth;
+    int run = 1;
+    if (!per_sample) {
+      while (s + run < n_samples && smp_leaf[s + run] == r && smp_len[s + run] == len) {
+        const int* pn = E.ml_smp_path + ((size_t)g * E.ml_cap + s + run) * E.max_depth;
+        bool diff = false;
+        for (int i = lane; i < len; i += 32) diff |= ps[i] != pn[i];
+        if (__any_sync(FULL, diff)) break;
+        ++run;
+      }
+    }
     float vf = values[base + (per_sample ? s : r)];
     vf = fminf(fmaxf(vf, -1.0f), 1.0f);   // float(np.clip(value, -1, 1)), mcts.py:668
-    warp_backup_path(E, g, E.ml_smp_path + ((size_t)g * E.ml_cap + s) * E.max_depth, smp_len[s], py_clip_unit((double)vf), 1, lane);
+    warp_backup_path(E, g, ps, len, py_clip_unit((double)vf), run, lane);
+    s += run;
   }
   if (lane == 0) {
     E.ml_n_samples[g] = 0;
