@@ -259,6 +259,7 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
         sp.engine.close()
         torch.cuda.empty_cache()
         out["as_shipped"] = bench_as_shipped(net, cfg, G, local, D.rank_seed(4321, rank), precision, stream)
+        out["as_shipped"]["scope"] = "per GPU (rank 0's engine; every rank runs the same leg on its own games)"
         if world == 1:
             out["throughput_virtual_loss"] = bench_as_shipped(net, cfg, min(G, 512), local, D.rank_seed(999, rank), precision, stream, moves=1,
                                                               search_mode="virtual_loss")
