@@ -264,6 +264,8 @@ def run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ra
             out["throughput_virtual_loss"] = bench_as_shipped(net, cfg, min(G, 512), local, D.rank_seed(999, rank), precision, stream, moves=1,
                                                               search_mode="virtual_loss")
             out["forward_sweep"] = forward_sweep(net, precision, stream, load_peaks)
+            if precision != "bf16":   # BASELINE configs[2] names bf16: the same sweep with bf16 operands (same tensor-core rate)
+                out["forward_sweep_bf16"] = forward_sweep(net, "bf16", stream, load_peaks, iters=5)
     if rank == 0:
         out["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
     return out
