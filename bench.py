@@ -291,7 +291,7 @@ def main():
 
     if args.workload == "auto":
         try:
-            from matrix0_b200 import bench_selfplay  # noqa: F401
+            import bench_selfplay  # noqa: F401
             args.workload = "selfplay"
         except ImportError:
             args.workload = "encode"
@@ -304,7 +304,7 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         if args.workload == "selfplay":
-            from matrix0_b200 import bench_selfplay
+            import bench_selfplay
             out = bench_selfplay.reference_arm(args)
         else:
             out = reference_encode(args)
@@ -315,7 +315,7 @@ def main():
     if args.total_games > 0:
         args.games = args.total_games // world
     if args.workload == "selfplay":
-        from matrix0_b200 import bench_selfplay
+        import bench_selfplay
         out = bench_selfplay.run(args, rank, world, local, ClockSampler, load_peaks, barrier, max_over_ranks)
         if world == 1 and not args.no_extras:
             # BASELINE configs[1] beside the headline: the encode + legal-mask microbenchmark with its own roofline / e2e / cpu_baseline

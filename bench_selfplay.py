@@ -1,4 +1,4 @@
-"""bench.py workload "selfplay" (BASELINE configs[3] / [4]): batched self-play, G concurrent games x
+"""Helper module of bench.py (not part of the product package: its CPU legs run the oracle).  Workload "selfplay" (BASELINE configs[3] / [4]): batched self-play, G concurrent games x
 `sims` simulations per move, ResNet-24 (320 channels, 24 blocks, 20 heads), one process per GPU.
 
 A step = one search step over all games of the rank: select -> encode -> NN forward -> expand -> backup
@@ -37,7 +37,7 @@ def reference_cfg(sims: int, leaf_batch: int = 96):
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
     capture (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py); None when no capture is committed."""
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             return float(json.load(f)["conv_pair_kernel"]["dram_bytes_per_launch"])

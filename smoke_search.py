@@ -1,4 +1,4 @@
-"""smoke(): one tiny closed-loop invocation of the hot path on cuda:0 checked against the oracle:
+"""Helper module of __graft_entry__.smoke() (not part of the product package: it checks against the oracle).  smoke(): one tiny closed-loop invocation of the hot path on cuda:0 checked against the oracle:
 a small random-weight evaluator, four games, one 96-simulation search, visit counts == oracle."""
 from __future__ import annotations
 

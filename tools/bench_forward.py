@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from matrix0_b200 import _native  # noqa: E402
-from matrix0_b200.bench_selfplay import FLOP_PER_POSITION, reference_cfg  # noqa: E402
+from bench_selfplay import FLOP_PER_POSITION, reference_cfg  # noqa: E402
 from matrix0_b200.model import PolicyValueNet  # noqa: E402
 
 

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--precision", default="fp16")
     args = ap.parse_args()
     from matrix0_b200 import inference as m0inf
-    from matrix0_b200.bench_selfplay import reference_cfg
+    from bench_selfplay import reference_cfg
     cfg = reference_cfg(800)["model"]                      # the R24 of BASELINE configs[3]
     res = [m0inf.setup_shared_memory_for_worker(i, 19, 4672, args.rows) for i in range(args.workers)]
     stop, ready = threading.Event(), threading.Event()

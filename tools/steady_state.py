@@ -11,7 +11,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from matrix0_b200.bench_selfplay import reference_cfg  # noqa: E402
+from bench_selfplay import reference_cfg  # noqa: E402
 from matrix0_b200.model import PolicyValueNet  # noqa: E402
 from matrix0_b200.records import GameRecorder  # noqa: E402
 from matrix0_b200.selfplay import SelfPlayEngine  # noqa: E402
