@@ -82,3 +82,36 @@ def test_api_surface():
     m.reset()
     assert m.get_memory_usage()["simulations_run"] == 0
     m.shutdown()
+
+
+def test_root_children_follow_python_chess_order_on_edge_positions():
+    """The warp-cooperative ordered move generator inside the tree kernels (csrc/movegen_warp.cuh; its lanes are simulated on the host
+    by tests/test_hostcheck.py): root children of constructed edge positions -- kingless boards and several kings take the single-lane
+    fallback, checks / double checks / pins / en passant / promotions / castling the one-piece-per-lane path -- and of 600 playout
+    positions come out in list(board.legal_moves) order."""
+    import torch
+    from matrix0_b200.engine import SearchEngine
+    from matrix0_b200.mcts import MCTSConfig
+    from conftest import random_playout_boards
+    from oracle.encoding_ref import legal_moves_and_indices
+    from test_hostcheck import WEIRD_FENS
+    boards = [chess.Board(f) for f in WEIRD_FENS] + random_playout_boards(12, 160, seed=5)[:600]
+    G = len(boards)
+    eng = SearchEngine(G, max_nodes=512, tt_capacity=1024, max_depth=16, hist_cap=4)
+    eng.configure(MCTSConfig(num_simulations=1, legal_softmax=True, enable_entropy_noise=False), deterministic=True)
+    eng.set_boards(boards, with_history=False)
+    eng.begin()
+    info = eng.info.cpu().numpy()
+    eng.expand_backup(torch.zeros((G, 4672), dtype=torch.float32, device="cuda"), torch.zeros((G,), dtype=torch.float32, device="cuda"))
+    eng.result(with_pi=False)
+    cnt, mv = eng.res_count.cpu().numpy(), eng.res_moves.cpu().numpy().view(np.uint16)
+    checked = 0
+    for g, b in enumerate(boards):
+        exp = [c for c, _ in legal_moves_and_indices(b)]
+        if info[g] & 1:                      # terminal root: nothing expanded
+            assert b.is_game_over() or not exp, b.fen()
+            continue
+        assert [int(x) for x in mv[g, :int(cnt[g])]] == exp[:256], b.fen()
+        checked += 1
+    assert checked > 500
+    eng.close()
