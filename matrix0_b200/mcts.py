@@ -141,7 +141,8 @@ class MCTS:
         rows = 1 if self.deterministic else self._max_batch
         self._logits = torch.zeros((rows, POLICY_SIZE), dtype=torch.float32, device=dev)
         self._values = torch.zeros((rows,), dtype=torch.float32, device=dev)
-        self._sample_planes = None if self.deterministic else torch.zeros((rows, 19, 8, 8), dtype=torch.float32, device=dev)
+        # (an even number of rows: the tensor-core evaluator works on pairs of boards)
+        self._sample_planes = None if self.deterministic else torch.zeros((rows + (rows & 1), 19, 8, 8), dtype=torch.float32, device=dev)
         self._nn_cache: Dict[Tuple[int, int], float] = {}
         self.simulations_run = 0
         self._last_sims_run = 0
