@@ -69,6 +69,12 @@ class GameRecorder:
 
     def after_move(self) -> List[Dict[str, np.ndarray]]:
         """Call after SelfPlayEngine.end_move(); returns the game_data dictionaries of the games that just ended."""
+        return list(self.iter_after_move())
+
+    def iter_after_move(self):
+        """after_move() as a generator: the finished games come one at a time and are assembled in groups of <= 65,536 positions, so a ply
+        on which thousands of games end (all slots reaching max_game_len together) never holds more than one group's arrays
+        (~2 GB of planes / masks / pi) on the host.  Exhaust it before the next after_search()."""
         now = self._ply0 + len(self._plies)          # absolute index one past the ply just played
         todo = []
         for fin in self.sp.finished_games():
@@ -79,16 +85,16 @@ class GameRecorder:
             if T <= 0 or first < self._ply0:
                 continue  # the game began before the retained window (keep_plies too small): skipped, never truncated
             todo.append((slot, first, fin))
-        out, group, rows = [], [], 0
+        group, rows = [], 0
         for item in todo:                                  # bounded device / host staging: <= 65,536 positions per encode launch
             T = now - item[1]
             if group and rows + T > 65536:
-                out += self._assemble_batch(group, now)
+                yield from self._assemble_batch(group, now)
                 group, rows = [], 0
             group.append(item)
             rows += T
         if group:
-            out += self._assemble_batch(group, now)
+            yield from self._assemble_batch(group, now)
         # drop plies no live game needs any more
         lo = int(self._start.min())
         drop = max(0, min(lo - self._ply0, len(self._plies)))
@@ -97,7 +103,6 @@ class GameRecorder:
         if drop:
             del self._plies[:drop]
             self._ply0 += drop
-        return out
 
     def _assemble_batch(self, todo, now: int) -> List[Dict[str, np.ndarray]]:
         """game_data dictionaries of all games that ended this ply: ONE encode launch (planes + legal masks) and one SSL launch over the

@@ -381,12 +381,11 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
         rec.after_search()
         sp.end_move()
         sp.check_status()
-        finished = rec.after_move()
-        if not finished and sp.active_games() == 0:
-            break                            # nothing in flight any more (games lost to a too small recorder window)
-        for gd in finished:
+        n_fin = 0
+        for gd in rec.iter_after_move():     # assembled in bounded groups: a ply on which every slot ends does not stage all games at once
+            n_fin += 1
             if written >= games:
-                break
+                continue
             T = int(gd["meta_moves"][0])
             path = (data_manager.add_selfplay_data(gd, worker_id=proc_id, game_id=written) if data_manager is not None
                     else write_game_npz(out_dir, gd, proc_id, written))
@@ -398,6 +397,8 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
                        "avg_policy_entropy": float(gd["meta_avg_policy_entropy"][0]), "avg_ms_per_move": secs * 1000.0 / max(1, T),
                        "avg_sims": float(gd["meta_avg_sims"][0])})
             written += 1
+        if n_fin == 0 and sp.active_games() == 0:
+            break                            # nothing in flight any more (games lost to a too small recorder window)
         if q is not None and time.perf_counter() - last_hb >= 2.0:
             q.put({"type": "heartbeat", "proc": proc_id, "game": written, "moves": sp.moves, "avg_sims": float(sp.mcfg.num_simulations),
                    "resigned": False, "avg_policy_entropy": 0.0})
