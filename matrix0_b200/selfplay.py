@@ -341,6 +341,9 @@ class SelfPlayEngine:
         return self.engine.counters()
 
 
+LAST_WORKER_STATS: Dict[str, Any] = {}    # where the last selfplay_worker call of this process spent its time (tools/worker_throughput.py)
+
+
 def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[str], games: int, q=None, shared_memory_resource=None,
                     device: Optional[int] = None, concurrent_games: Optional[int] = None, precision: str = "fp16", data_manager=None,
                     search_mode: str = "as_shipped") -> int:
@@ -372,35 +375,93 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
     ssl_tasks = tuple(mcfg.get("ssl_tasks", ())) if mcfg.get("self_supervised", False) else ()      # internal.py:251-256
     rec = GameRecorder(sp, ssl_tasks=ssl_tasks)
     out_dir = os.path.join(str(cfg_dict.get("data_dir", "data")), "selfplay")
-    written, last_hb, t_start = 0, time.perf_counter(), time.perf_counter()
-    sp.start(games)                      # exactly `games` games are started; every one of them is played to its end (internal.py:326)
-    while written < games:
-        sp.begin_move()
-        for _ in range(sp.batches_per_move()):
-            sp.search_step()
-        rec.after_search()
-        sp.end_move()
-        sp.check_status()
-        n_fin = 0
-        for gd in rec.iter_after_move():     # assembled in bounded groups: a ply on which every slot ends does not stage all games at once
-            n_fin += 1
-            if written >= games:
-                continue
-            T = int(gd["meta_moves"][0])
-            path = (data_manager.add_selfplay_data(gd, worker_id=proc_id, game_id=written) if data_manager is not None
-                    else write_game_npz(out_dir, gd, proc_id, written))
-            secs = time.perf_counter() - t_start
+    # The shards are compressed (np.savez_compressed, ~60 ms per 200-ply game) by a small pool of writer threads (zlib releases the GIL)
+    # while the GPU searches on; at most `writer_queue_games` finished games wait in host memory, and the "game" messages keep game order.
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+    n_writers = int((cfg_dict.get("selfplay", {}) or {}).get("writer_threads", min(12, max(1, (os.cpu_count() or 2) - 2))))
+    pool = ThreadPoolExecutor(max_workers=max(1, n_writers), thread_name_prefix="m0-npz")
+    pending, max_pending = collections.deque(), int((cfg_dict.get("selfplay", {}) or {}).get("writer_queue_games", 1024))   # ~6 MB per 200-ply game
+    npz_level = (cfg_dict.get("selfplay", {}) or {}).get("npz_compresslevel", None)   # None: np.savez_compressed, byte-for-byte the reference's writer
+    submitted, written, last_hb, t_start = 0, 0, time.perf_counter(), time.perf_counter()
+
+    def save(gd, game_id):
+        if data_manager is not None:
+            return data_manager.add_selfplay_data(gd, worker_id=proc_id, game_id=game_id)
+        return write_game_npz(out_dir, gd, proc_id, game_id, compresslevel=npz_level)
+
+    stats = LAST_WORKER_STATS
+    stats.clear()
+    stats.update(seconds_search=0.0, seconds_record_assembly=0.0, seconds_waiting_for_writers=0.0, writer_threads=n_writers)
+
+    def drain(everything: bool) -> None:
+        nonlocal written
+        while pending and (everything or len(pending) > max_pending or pending[0][0].done()):
+            fut, meta = pending.popleft()
+            try:
+                tw = time.perf_counter()
+                path = fut.result()
+                stats["seconds_waiting_for_writers"] += time.perf_counter() - tw
+            except Exception:                 # a failed save does not stop the worker (internal.py:652-656)
+                path = None
+            if path is not None:
+                written += 1
             if q is not None:
-                z = float(gd["meta_result"][0])
-                q.put({"type": "game", "proc": proc_id, "file": path, "moves": T, "result": z, "secs": secs,
-                       "resigned": bool(gd["meta_resigned"][0]), "resigner": None, "draw": bool(z == 0.0),
-                       "avg_policy_entropy": float(gd["meta_avg_policy_entropy"][0]), "avg_ms_per_move": secs * 1000.0 / max(1, T),
-                       "avg_sims": float(gd["meta_avg_sims"][0])})
-            written += 1
-        if n_fin == 0 and sp.active_games() == 0:
-            break                            # nothing in flight any more (games lost to a too small recorder window)
-        if q is not None and time.perf_counter() - last_hb >= 2.0:
-            q.put({"type": "heartbeat", "proc": proc_id, "game": written, "moves": sp.moves, "avg_sims": float(sp.mcfg.num_simulations),
-                   "resigned": False, "avg_policy_entropy": 0.0})
-            last_hb = time.perf_counter()
+                q.put(dict(meta, file=path))
+
+    def handle(gd) -> None:
+        nonlocal submitted
+        if submitted >= games:
+            return
+        T = int(gd["meta_moves"][0])
+        z = float(gd["meta_result"][0])
+        secs = time.perf_counter() - t_start
+        meta = {"type": "game", "proc": proc_id, "file": None, "moves": T, "result": z, "secs": secs,
+                "resigned": bool(gd["meta_resigned"][0]), "resigner": None, "draw": bool(z == 0.0),
+                "avg_policy_entropy": float(gd["meta_avg_policy_entropy"][0]), "avg_ms_per_move": secs * 1000.0 / max(1, T),
+                "avg_sims": float(gd["meta_avg_sims"][0])}
+        pending.append((pool.submit(save, gd, submitted), meta))
+        submitted += 1
+        drain(False)
+
+    def handle_all(games_iter) -> None:
+        it = iter(games_iter)
+        while True:
+            ta = time.perf_counter()
+            gd = next(it, None)              # the recorder waits for a group's device-to-host copies inside next()
+            stats["seconds_record_assembly"] += time.perf_counter() - ta
+            if gd is None:
+                return
+            handle(gd)
+
+    sp.start(games)                      # exactly `games` games are started; every one of them is played to its end (internal.py:326)
+    try:
+        while submitted < games:
+            ts = time.perf_counter()
+            sp.begin_move()
+            for _ in range(sp.batches_per_move()):
+                sp.search_step()
+            rec.after_search()
+            sp.end_move()
+            sp.check_status()
+            stats["seconds_search"] += time.perf_counter() - ts
+            # the records of the games that ended on this ply are assembled and copied on a side stream under the next ply's search
+            # and come out of the next call; groups are bounded, so a ply on which every slot ends does not stage all games at once
+            # while the shard writers are busy the finished games wait in the recorder's device ring (up to max_game_len plies) instead
+            # of blocking the search on the writer queue
+            drain(False)
+            room = max(0, max_pending - len(pending) - rec.pending_games())
+            handle_all(rec.iter_after_move(defer=True, max_games=room))
+            drain(False)
+            if sp.active_games() == 0:
+                break                            # every started game is over (games that ended inside their opening plies leave no shard)
+            if q is not None and time.perf_counter() - last_hb >= 2.0:
+                q.put({"type": "heartbeat", "proc": proc_id, "game": submitted, "moves": sp.moves, "avg_sims": float(sp.mcfg.num_simulations),
+                       "resigned": False, "avg_policy_entropy": 0.0})
+                last_hb = time.perf_counter()
+        handle_all(rec.flush())
+    finally:
+        drain(True)
+        pool.shutdown(wait=True)
+        stats["seconds_play_and_write"] = time.perf_counter() - t_start
     return written

@@ -93,7 +93,8 @@ def test_device_game_loop_invariants(golden_dir):
     assert int(st.abs().sum()) == 0 and int(nc.max()) <= 4096
 
 
-def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path):
+@pytest.mark.parametrize("how", ["at_once", "deferred", "deferred_budget"])
+def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path, how):
     """Finished games come out as the reference's game_data dictionaries (internal.py:626-651): every recorded state replays
     through the oracle (python-chess restatement + the reference encoder's restatement) -- s and legal_mask bit-exact, pi the
     normalised visit counts on legal indices only, z = result x side to move, consecutive states one legal move apart."""
@@ -116,7 +117,18 @@ def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path):
             sp.search_step()
         rec.after_search()
         sp.end_move()
-        games += rec.after_move()
+        # defer: the records are assembled / copied on the recorder's side stream under the next ply's search and come out one call later
+        # "deferred_budget": at most 3 games are started per ply, the others wait in the device ring (oldest first, started anyway before
+        # their rows would be overwritten)
+        if how == "at_once":
+            games += rec.after_move()
+            assert rec.pending_games() == 0 and rec.backlog_games() == 0
+        else:
+            games += list(rec.iter_after_move(defer=True, max_games=3 if how == "deferred_budget" else None))
+    waited = rec.backlog_games()
+    games += list(rec.flush())
+    assert rec.pending_games() == 0 and rec.backlog_games() == 0
+    assert how != "deferred_budget" or waited > 0
     assert len(games) >= G                      # max_game_len 10: every slot finished at least one game
     checked = 0
     for gd in games[:20]:

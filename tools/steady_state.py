@@ -40,7 +40,7 @@ def main():
             sp.search_step()
         rec.after_search()
         sp.end_move()
-        return rec.after_move()
+        return list(rec.iter_after_move(defer=True))     # assembled / copied on a side stream under the next ply's search
 
     move()
     torch.cuda.synchronize()
@@ -61,8 +61,8 @@ def main():
     out = {"mode": a.mode, "games": a.games, "moves": a.moves, "seconds": dt, "sims_per_s": d["sims"] / dt, "positions_per_s": d["positions_played"] / dt,
            "nn_rows_per_s": (d["nn_evals"] + a.games * a.moves) / dt, "seconds_per_move": per_move, "games_finished_and_assembled": games,
            "plies_in_finished_games": plies, "max_game_len": a.max_game_len,
-           "includes": "GameRecorder.after_search (positions, policy indices, visit counts D2H every ply), after_move (finished games -> s / pi / z / "
-                       "legal_mask / ssl_* arrays via the encode and SSL kernels), slot restarts with 12 random opening plies"}
+           "includes": "GameRecorder.after_search (positions, policy indices, visit counts into the device ring every ply), iter_after_move (finished games -> s / pi / z / "
+                       "legal_mask / ssl_* arrays assembled on the device, one D2H per array and group), slot restarts with 12 random opening plies"}
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
     print(json.dumps(out))
