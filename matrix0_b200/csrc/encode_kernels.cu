@@ -303,11 +303,17 @@ int m0_encode_positions(const uint64_t* d_pos, int n, float* d_planes, uint8_t* 
       static bool tab_ready[64] = {};
       int dev = 0;
       M0_CUDA_TRY(cudaGetDevice(&dev));
-      if (dev < 0 || dev >= 64 || !tab_ready[dev]) {       // stream-ordered before the first use on this device
+      if (dev < 0 || dev >= 64 || !tab_ready[dev]) {       // built once per device, before the first use on ANY stream:
         build_move_index_tab_kernel<<<16, 256, 0, (cudaStream_t)stream>>>();
         int rc = m0_check_launch("build_move_index_tab_kernel");
         if (rc != 0) return rc;
-        if (dev >= 0 && dev < 64) tab_ready[dev] = true;
+        // later calls may come on other streams (the game recorder encodes on its side stream), so the one-time build is waited for
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+        if (cap == cudaStreamCaptureStatusNone) {
+          M0_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+          if (dev >= 0 && dev < 64) tab_ready[dev] = true;
+        }
       }
     }
     int blocks = (n + ENCW_POS_PER_BLOCK - 1) / ENCW_POS_PER_BLOCK;

@@ -111,7 +111,9 @@ class GameRecorder:
                 continue  # (a ring shorter than the game: skipped, never truncated)
             self._backlog.append((slot, first, T, fin))
         yield from self._deliver_all()               # groups launched on earlier plies: their copies ran under this ply's search
-        yield from self._launch_backlog(float("inf") if max_games is None else int(max_games))
+        # deferred: never wait for a copy here -- at most MAX_INFLIGHT groups are started per call (a ply on which every slot ends is
+        # spread over the following plies), except for games whose ring rows are about to be overwritten
+        yield from self._launch_backlog(float("inf") if max_games is None else int(max_games), wait=not defer)
         if not defer:
             yield from self._deliver_all()
 
@@ -133,21 +135,29 @@ class GameRecorder:
         while self._inflight:
             yield from self._deliver(self._inflight.popleft())
 
-    def _launch_backlog(self, budget):
+    def _launch_backlog(self, budget, wait: bool = True):
         """Start the assembly of backlog games, oldest first, in groups of <= GROUP_ROWS positions: ``budget`` games, plus every game whose
-        oldest ring row is about to be overwritten.  Hands out the oldest group in flight whenever MAX_INFLIGHT are."""
+        oldest ring row is about to be overwritten.  When MAX_INFLIGHT groups are in flight: ``wait`` hands out the oldest to make
+        room, otherwise the rest of the backlog stays for the next call."""
         now, K = self._now, self.keep_plies
+        # the ring row of ply `first` is rewritten by the after_search of ply first + K: everything up to the last backlog entry that
+        # close to it is started now, whatever the budget says (the backlog is ordered by the END of the games, not by their start)
+        force = 0
+        for i, item in enumerate(self._backlog):
+            if item[1] + K - now <= 2:
+                force = i + 1
         synced = False
         while self._backlog:
             group, rows = [], 0
+            full = not wait and len(self._inflight) >= self.MAX_INFLIGHT
             while self._backlog and (not group or rows + self._backlog[0][2] <= GROUP_ROWS):
-                expiring = self._backlog[0][1] + K - now <= 2     # ring row of ply `first` is rewritten by the after_search of ply first + K
-                if budget <= 0 and not expiring:
+                if (budget <= 0 or full) and force <= 0:
                     break
                 item = self._backlog.popleft()
                 group.append(item)
                 rows += item[2]
                 budget -= 1
+                force -= 1
             if not group:
                 return
             if not synced:

@@ -93,7 +93,7 @@ def test_device_game_loop_invariants(golden_dir):
     assert int(st.abs().sum()) == 0 and int(nc.max()) <= 4096
 
 
-@pytest.mark.parametrize("how", ["at_once", "deferred", "deferred_budget"])
+@pytest.mark.parametrize("how", ["at_once", "deferred", "deferred_budget", "deferred_forced"])
 def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path, how):
     """Finished games come out as the reference's game_data dictionaries (internal.py:626-651): every recorded state replays
     through the oracle (python-chess restatement + the reference encoder's restatement) -- s and legal_mask bit-exact, pi the
@@ -111,7 +111,7 @@ def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path, ho
     rec = GameRecorder(sp, ssl_tasks=("piece", "threat", "pin", "fork", "control"))
     sp.start()
     games = []
-    for _ in range(12):
+    for _ in range(40 if how == "deferred_forced" else 12):
         sp.begin_move()
         for _ in range(sp.batches_per_move()):
             sp.search_step()
@@ -123,12 +123,17 @@ def test_recorder_game_records_match_reference_contract(golden_dir, tmp_path, ho
         if how == "at_once":
             games += rec.after_move()
             assert rec.pending_games() == 0 and rec.backlog_games() == 0
+        elif how == "deferred_forced":
+            # no budget at all: every game waits in the ring (2 * max_game_len + 3 plies) until its oldest row is about to be overwritten
+            games += list(rec.iter_after_move(defer=True, max_games=0))
         else:
             games += list(rec.iter_after_move(defer=True, max_games=3 if how == "deferred_budget" else None))
     waited = rec.backlog_games()
     games += list(rec.flush())
     assert rec.pending_games() == 0 and rec.backlog_games() == 0
-    assert how != "deferred_budget" or waited > 0
+    assert how not in ("deferred_budget", "deferred_forced") or waited > 0
+    if how == "deferred_forced":
+        assert len(games) - waited >= G         # the games of the first generation were handed out by the forced path alone
     assert len(games) >= G                      # max_game_len 10: every slot finished at least one game
     checked = 0
     for gd in games[:20]:
