@@ -18,6 +18,7 @@ games; the per-game arrays are views of it.  ``ssl_{task}`` arrays (internal.py:
 from __future__ import annotations
 
 import os
+import time
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -44,7 +45,7 @@ class GameRecorder:
     next ply is searched, and are handed out by the next call (or by ``flush()``); ``after_move()`` / ``defer=False`` hand them out at once.
     """
 
-    MAX_INFLIGHT = 3     # groups whose device-to-host copies may be in flight before the oldest is handed out (pinned host memory bound)
+    MAX_INFLIGHT = 2     # groups whose device-to-host copies may be in flight before the oldest is handed out (pinned host memory bound)
 
     def __init__(self, sp, keep_plies: Optional[int] = None, ssl_tasks=()):
         import collections
@@ -69,6 +70,7 @@ class GameRecorder:
         self._inflight = collections.deque()                # groups launched on the side stream, oldest first
         self._backlog = collections.deque()                 # finished games (slot, first ply, plies, engine record) not launched yet
         self._ring_read = None                              # event: the side stream has read the ring rows of every launched group
+        self.timing = collections.Counter()                 # host seconds by phase (tools/worker_throughput.py reports them)
 
     def after_search(self) -> None:
         """Call after the last search step of a ply and before SelfPlayEngine.end_move()."""
@@ -100,7 +102,10 @@ class GameRecorder:
         calls, oldest first -- a caller whose shard writers are busy keeps the GPU searching instead of blocking on them.
         Exhaust the generator before the next after_search()."""
         now = self._now                              # one past the ply just played
-        for fin in self.sp.finished_games():
+        t0 = time.perf_counter()
+        finished = self.sp.finished_games()
+        self.timing["finished_games"] += time.perf_counter() - t0
+        for fin in finished:
             slot = fin["slot"]
             first = int(self._start[slot])
             self._start[slot] = now
@@ -168,7 +173,9 @@ class GameRecorder:
                 synced = True
             while len(self._inflight) >= self.MAX_INFLIGHT:
                 yield from self._deliver(self._inflight.popleft())
+            t0 = time.perf_counter()
             self._inflight.append(self._launch(group))
+            self.timing["launch"] += time.perf_counter() - t0
 
     def _launch(self, todo) -> Dict[str, Any]:
         """Queue the assembly of a group of finished games on the side stream: their rows gathered from the ring, ONE encode launch
@@ -184,8 +191,14 @@ class GameRecorder:
         within = np.arange(N, dtype=np.int64) - np.repeat(offs[:-1], lens)
         ply = (np.repeat(np.array([first for _, first, _, _ in todo], dtype=np.int64), lens) + within) % K
         slot = np.repeat(np.array([s for s, _, _, _ in todo], dtype=np.int64), lens)
+        # (page-locked staging: a pageable host-to-device copy would block this thread until the side stream has finished the groups
+        # queued before this one)
+        h_index = torch.empty((2, N), dtype=torch.int64, pin_memory=True)
+        h_index[0].copy_(torch.from_numpy(ply))
+        h_index[1].copy_(torch.from_numpy(slot))
         with torch.cuda.stream(self._side):
-            d_ply, d_slot = torch.from_numpy(ply).to(dev), torch.from_numpy(slot).to(dev)
+            d_index = h_index.to(dev, non_blocking=True)
+            d_ply, d_slot = d_index[0], d_index[1]
             dpos = self._pos[d_ply, d_slot].contiguous()                        # [N, 9]
             idx = (self._idx[d_ply, d_slot].to(torch.int64) & 0xFFFF)            # [N, 256] policy indices (uint16 stored as int16)
             vis = self._vis[d_ply, d_slot]
@@ -218,7 +231,9 @@ class GameRecorder:
             for t in srcs:
                 offsets.append(total)
                 total += (t.numel() * t.element_size() + 255) & ~255
+            t0 = time.perf_counter()
             block = torch.empty((total,), dtype=torch.uint8, pin_memory=True)
+            self.timing["launch_pinned_block"] += time.perf_counter() - t0
             views = []
             for t, off in zip(srcs, offsets):
                 h = block[off:off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
@@ -231,7 +246,10 @@ class GameRecorder:
 
     def _deliver(self, grp) -> List[Dict[str, np.ndarray]]:
         """The game_data dictionaries of a launched group; the per-game arrays are views of the group's host arrays."""
+        t0 = time.perf_counter()
         grp["done"].synchronize()
+        self.timing["deliver_wait_for_copy"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
         planes_h, mask_h, pi_h, turns_h, tot_h = [h.numpy() for h in grp["hosts"]]
         ssl_h = {t: h.numpy() for t, h in grp["ssl"].items()}
         offs = grp["offs"]
@@ -247,6 +265,7 @@ class GameRecorder:
                 "meta_avg_policy_entropy": np.array([fin["avg_policy_entropy"]], dtype=np.float32),
                 "meta_avg_sims": np.array([float(tot_h[a:b].mean()) if T else 0.0], dtype=np.float32),
             })
+        self.timing["deliver_build_dicts"] += time.perf_counter() - t0
         return out
 
 

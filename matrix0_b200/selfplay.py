@@ -381,7 +381,8 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
     from concurrent.futures import ThreadPoolExecutor
     n_writers = int((cfg_dict.get("selfplay", {}) or {}).get("writer_threads", min(12, max(1, (os.cpu_count() or 2) - 2))))
     pool = ThreadPoolExecutor(max_workers=max(1, n_writers), thread_name_prefix="m0-npz")
-    pending, max_pending = collections.deque(), int((cfg_dict.get("selfplay", {}) or {}).get("writer_queue_games", 1024))   # ~6 MB per 200-ply game
+    # ~6.5 MB per 200-ply game, and every 160 of them keep one 1 GiB page-locked block of the recorder alive (0.45 s to allocate the first time)
+    pending, max_pending = collections.deque(), int((cfg_dict.get("selfplay", {}) or {}).get("writer_queue_games", 32 * max(1, n_writers)))
     npz_level = (cfg_dict.get("selfplay", {}) or {}).get("npz_compresslevel", None)   # None: np.savez_compressed, byte-for-byte the reference's writer
     submitted, written, last_hb, t_start = 0, 0, time.perf_counter(), time.perf_counter()
 
@@ -464,4 +465,5 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
         drain(True)
         pool.shutdown(wait=True)
         stats["seconds_play_and_write"] = time.perf_counter() - t_start
+        stats["recorder_seconds_by_phase"] = dict(rec.timing)
     return written
