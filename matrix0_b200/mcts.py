@@ -175,13 +175,17 @@ class MCTS:
             self._logits.copy_(torch.from_numpy(np.ascontiguousarray(policies[:1, :POLICY_SIZE])), non_blocking=False)
             self._values.copy_(torch.from_numpy(values[:1].copy()), non_blocking=False)
         elif hasattr(self.model, "forward_planes"):
-            logits, values = self.model.forward_planes(eng.planes)
+            logits, values = self._native_forward(eng.planes)
             self._logits.copy_(logits.reshape(1, -1)[:, :POLICY_SIZE].float())
             self._values.copy_(values.reshape(-1)[:1].float())
         else:
             raise RuntimeError("MCTS needs an inference_backend with infer_np() or a native evaluator with forward_planes(); "
                                "matrix0_b200 has no PyTorch/CPU fallback evaluator")
         eng.expand_backup(self._logits, self._values)
+
+    def _native_forward(self, planes):
+        fwd = getattr(self.model, "forward_planes_graphed", None)
+        return fwd(planes) if fwd is not None else self.model.forward_planes(planes)
 
     def set_random_streams(self, jitter=None, normal=None) -> None:
         """Caller-supplied draws for the stochastic search (parity testing): ``jitter`` = the values ``random.random()`` would
@@ -220,7 +224,10 @@ class MCTS:
         elif hasattr(self.model, "forward_planes"):
             rows = int(eng.row_base[1])
             eng.multi_encode(0, 1, 0, 0, self._sample_planes)
-            logits, values = self.model.forward_planes(self._sample_planes[:rows + (rows & 1)])
+            # the whole (fixed) sample buffer: one cached CUDA graph serves every mini-batch, and a forward of <= 96 rows costs the same
+            # as one of 2 (a single round of every kernel); rows past `rows` hold planes of earlier batches and are ignored
+            half = getattr(self.model, "precision", "fp32") != "fp32"      # (the fp32 SIMT path runs eagerly, on the live rows only)
+            logits, values = self._native_forward(self._sample_planes if half else self._sample_planes[:rows + (rows & 1)])
             self._logits[:rows].copy_(logits[:rows, :POLICY_SIZE].float())
             self._values[:rows].copy_(values.reshape(-1)[:rows].float())
             eng.expand_backup_multi(0, 1, self._logits, self._values, 0, per_sample=False)

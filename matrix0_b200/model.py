@@ -365,6 +365,7 @@ class PolicyValueNet:
         # workspaces: bump the workspace epoch that is part of its cache key
         self._ws_epoch = getattr(self, "_ws_epoch", 0) + 1
         self._max_batch = 0
+        self.__dict__.pop("_fwd_graphs", None)
         if self._handle is not None:
             _native.load_library().m0_net_destroy(self._handle)
             self._handle = None
@@ -499,6 +500,28 @@ class PolicyValueNet:
             with torch.cuda.graph(graph):
                 logits, values = self.forward_planes(planes, precision)
         return graph, logits, values
+
+    def forward_planes_graphed(self, planes, precision: Optional[str] = None):
+        """``forward_planes`` through a cached CUDA graph per (planes buffer, batch, precision): for callers that evaluate the SAME
+        device buffer again and again with small batches (the drop-in ``MCTS`` object: ten evaluator calls of <= 96 rows per move),
+        where an eager forward is bound by its ~230 kernel launches.  The outputs are the graph's static tensors (overwritten by the
+        next replay).  fp32 (the SIMT path) runs eagerly."""
+        prec = precision or self.precision
+        if prec == "fp32":
+            return self.forward_planes(planes, precision)
+        cache = self.__dict__.setdefault("_fwd_graphs", {})
+        key = (planes.data_ptr(), int(planes.shape[0]), prec, self.ws_epoch)
+        if key not in cache:
+            graph, logits, values = self.capture_forward(planes, precision)     # (its warm-up passes may grow the workspaces)
+            for k in [k for k in cache if k[3] != self.ws_epoch]:               # captures of older weights / workspaces are stale
+                del cache[k]
+            while len(cache) >= 8:
+                del cache[next(iter(cache))]
+            key = (planes.data_ptr(), int(planes.shape[0]), prec, self.ws_epoch)
+            cache[key] = (graph, logits, values)
+        graph, logits, values = cache[key]
+        graph.replay()
+        return logits, values
 
     @property
     def ws_epoch(self) -> int:

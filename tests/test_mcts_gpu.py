@@ -115,3 +115,47 @@ def test_root_children_follow_python_chess_order_on_edge_positions():
         checked += 1
     assert checked > 500
     eng.close()
+
+
+def test_configs0_single_game_through_the_dropin_search_object(tmp_path):
+    """BASELINE configs[0] on the GPU: ONE game from the start position, 800 simulations per move, ResNet-24 random init, searched by
+    `MCTS(cfg, model, device="cuda").run(board)` move after move -- the call `selfplay_worker` / `arena.py` / `cli_play.py` of the reference
+    make (one board per call, host dictionaries back).  The latency case: ten evaluator calls of <= 96 rows per move and nothing to batch
+    across games.  The numbers go to gpurun_out/single_game.json (copied to profiles/); the assertion is only a floor well above the
+    reference's CPU rate on the same configuration (65 ... 450 sims/s, `bench.py --impl reference`)."""
+    import json
+    import os
+    import time
+    import torch
+    from bench_selfplay import reference_cfg
+    from matrix0_b200.mcts import MCTS, MCTSConfig
+    from matrix0_b200.model import PolicyValueNet
+    cfg = reference_cfg(800)
+    net = PolicyValueNet.from_config(cfg["model"], device="cuda:0", precision="fp16", seed=0)
+    out = {"workload": "BASELINE configs[0]: one game from the start position, 800 sims/move, ResNet-24 fp16 random init, MCTS.run per move"}
+    for name, det in (("as_shipped", False), ("deterministic", True)):
+        mcts = MCTS(MCTSConfig.from_dict(cfg["mcts"]), net, device="cuda", deterministic=det, seed=1234)
+        board = chess.Board()
+        for _ in range(2):                      # warm-up: workspaces, first launches, the evaluator's CUDA graphs
+            mcts.reset()
+            mcts.run(board, ply=0)
+        per_move, sims = [], 0
+        for ply in range(8):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            mcts.reset()                        # a fresh tree per move: the only working reading of the reference (DESIGN.md Q12 -- with
+            visits, pi, v = mcts.run(board, ply=ply)   # a persistent object its second move raises "zero visits", and so does ours)
+            torch.cuda.synchronize()
+            per_move.append((time.perf_counter() - t) * 1e3)
+            sims += int(mcts._last_sims_run)
+            assert visits and abs(float(pi.sum()) - 1.0) < 1e-4 and -1.0 <= v <= 1.0
+            board.push(max(visits.items(), key=lambda kv: kv[1])[0])
+        total = sum(per_move) * 1e-3
+        out[name] = {"moves": len(per_move), "ms_per_move": per_move, "ms_per_move_median": sorted(per_move)[len(per_move) // 2], "sims": sims,
+                     "sims_per_s": sims / total, "positions_per_s": len(per_move) / total}
+        mcts.shutdown()
+        assert sims / total > 2000.0, out[name]
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(root, exist_ok=True)
+    with open(os.path.join(root, "single_game.json"), "w") as f:
+        json.dump(out, f, indent=1)
