@@ -156,3 +156,39 @@ def test_refinit_bf16_gate_on_the_legal_policy(golden_dir):
     a, al, dv = _refinit_agreement(golden_dir, "bf16")
     print(f"refinit gate bf16: top-1 {a:.4f} legal top-1 {al:.4f} max|dv| {dv:.2e}")
     assert al >= 0.99 and dv <= 2e-2 and a >= 0.98, (a, al, dv)
+
+
+_ATT_AB_SCRIPT = r"""
+import hashlib, sys, torch
+sys.path.insert(0, sys.argv[1])
+from matrix0_b200.model import NetConfig, PolicyValueNet
+cfg = NetConfig(channels=64, blocks=6, attention_heads=4, policy_factor_rank=32, norm="group", activation="silu",
+                value_activation="leaky_relu", preact=True, infer_attention_stride=1, ssl_tasks=["piece"])
+for prec in ("fp16", "bf16"):
+    net = PolicyValueNet(cfg, device="cuda", precision=prec, seed=11)
+    for n in (1, 37, 257, 1031):                      # ragged: partial warps, partial blocks, several blocks
+        x = (torch.rand(n, 19, 8, 8, generator=torch.Generator().manual_seed(n)) > 0.8).float()
+        p, v = net.forward(x)
+        print(prec, n, hashlib.sha256(p.float().cpu().numpy().tobytes() + v.float().cpu().numpy().tobytes()).hexdigest())
+"""
+
+
+def test_attention_staged_kernel_is_bit_identical_to_direct_loads():
+    """The shipped attention kernel stages q / k / v through shared memory with cp.async one board ahead
+    (csrc/nn_attention_tc.cu: attention_tc_staged_kernel); M0_ATT_STAGED=0 selects the direct-global-load kernel the round-2 parity
+    numbers were first measured with.  Same fragments, same arithmetic: every logit and value must be BIT-identical, for ragged
+    batch sizes, both 16-bit operand formats, and the launcher's own boards-per-warp choice as well as 1 and 8 forced."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("direct", {"M0_ATT_STAGED": "0"}), ("staged", {"M0_ATT_STAGED": "1"}),
+                     ("staged1", {"M0_ATT_STAGED": "1", "M0_ATT_BOARDS": "1"}), ("staged8", {"M0_ATT_STAGED": "1", "M0_ATT_BOARDS": "8"})):
+        r = subprocess.run([sys.executable, "-c", _ATT_AB_SCRIPT, root], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = r.stdout.strip().splitlines()
+    assert len(outs["direct"]) == 8
+    assert outs["staged"] == outs["direct"]
+    assert outs["staged1"] == outs["direct"]
+    assert outs["staged8"] == outs["direct"]
