@@ -342,11 +342,15 @@ int nn_attention_tc(const void* qkv_half, const float* rel_bias, void* out_half,
   }
   if (staged) {
     const int smem = 2 * 64 * BIAS_LD * (int)sizeof(float) + 8 * ATT_STAGE_BYTES;
-    static const cudaError_t attr = [smem] {
+    static unsigned long long granted = 0;   // bit d: device d's kernels have the shared-memory grant (it is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((granted >> dev) & 1ull)) {
       cudaError_t e = cudaFuncSetAttribute(attention_tc_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      return e != cudaSuccess ? e : cudaFuncSetAttribute(attention_tc_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    }();
-    if (attr != cudaSuccess) { m0_set_error("attention_tc: cannot reserve %d bytes of shared memory (%s)", smem, cudaGetErrorString(attr)); return M0_ERR_CUDA; }
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) { m0_set_error("attention_tc: cannot reserve %d bytes of shared memory (%s)", smem, cudaGetErrorString(e)); return M0_ERR_CUDA; }
+      if (dev < 64) granted |= 1ull << dev;
+    }
     dim3 grid(heads, (B + 8 * bpw - 1) / (8 * bpw));
     if (nn_half_format()) attention_tc_staged_kernel<true><<<grid, 256, smem, s>>>((const uint16_t*)qkv_half, rel_bias, (uint16_t*)out_half, B, C, mix, bpw);
     else attention_tc_staged_kernel<false><<<grid, 256, smem, s>>>((const uint16_t*)qkv_half, rel_bias, (uint16_t*)out_half, B, C, mix, bpw);

@@ -181,6 +181,10 @@ struct TcBlock {
 struct TcState {
   int sm_count = 148;
   int max_smem = 0;
+  // dynamic shared memory already granted to the kernels ON THIS STATE'S DEVICE (cudaFuncSetAttribute is per device: a process-wide
+  // record would leave the kernels of a second device at the 48 KB default)
+  size_t smem_pair[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  size_t smem_gemm = 0;
   TcWeight pst, inter;
   std::vector<TcBlock> blocks;
   // SE: pooled half-board sums [cap][2][C], hidden [cap][hid], gate [cap][C]; W1 duplicated over the two halves and scaled by 1/64
@@ -358,10 +362,9 @@ int launch_conv_pair(TcState* st, const CUtensorMap& a_map, const TcWeight& w, i
                 : fz == 1 ? (nch <= 1 ? tc::conv_pair_kernel<1, 1> : nch <= 3 ? tc::conv_pair_kernel<3, 1> : tc::conv_pair_kernel<4, 1>)
                           : (nch <= 1 ? tc::conv_pair_kernel<1, 0> : nch <= 3 ? tc::conv_pair_kernel<3, 0> : tc::conv_pair_kernel<4, 0>);
   const int kidx = (nch <= 1 ? 0 : nch <= 3 ? 1 : 2) + 3 * fz;
-  static size_t configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (smem > configured[kidx]) {
+  if (smem > st->smem_pair[kidx]) {
     M0_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[kidx] = smem;
+    st->smem_pair[kidx] = smem;
   }
   const int tiles = (boards + 3) / 4;
   int clusters = st->sm_count / 2;
@@ -464,10 +467,9 @@ int launch_gemm(TcState* st, const CUtensorMap& a_map, const TcWeight& w, int M,
   if (stages < 2) { m0_set_error("tensor-core GEMM: tile does not fit in shared memory (N=%d)", N); return M0_ERR_ARG; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + tc::EPI_STAGE_BYTES + 1024 + 256;
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > st->smem_gemm) {
     M0_CUDA_TRY(cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    st->smem_gemm = smem;
   }
   const int tiles = (M + tc::BM - 1) / tc::BM;
   const int cs = w.cluster;
@@ -927,8 +929,14 @@ extern "C" int m0_tc_conv(const uint16_t* d_act_bf16, const uint16_t* d_w_bf16, 
     ~FormatGuard() { nn_set_half_format(saved); }
   } format_guard;
   static TcState st;
+  static int st_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
+  if (dev != st_dev) {   // shared-memory grants are per device
+    for (size_t& v : st.smem_pair) v = 0;
+    st.smem_gemm = 0;
+    st_dev = dev;
+  }
   cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&st.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   TcWeight w;

@@ -192,3 +192,24 @@ def test_attention_staged_kernel_is_bit_identical_to_direct_loads():
     assert outs["staged"] == outs["direct"]
     assert outs["staged1"] == outs["direct"]
     assert outs["staged8"] == outs["direct"]
+
+
+def test_two_devices_in_one_process_give_identical_outputs():
+    """One process, evaluators on cuda:0 and cuda:1 (an arena or an evaluation server per device inside one orchestrator process):
+    the opt-in shared-memory grants of the tensor-core kernels are per DEVICE state, so the second device must get its own
+    (a process-wide record would leave its kernels at the 48 KB default).  Same weights, same input ->
+    the same bits on both devices; skipped on a single-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from matrix0_b200.model import NetConfig, PolicyValueNet
+    cfg = NetConfig(channels=64, blocks=6, attention_heads=4, policy_factor_rank=32, norm="group", activation="silu",
+                    value_activation="leaky_relu", preact=True, infer_attention_stride=1, ssl_tasks=["piece"])
+    x = (torch.rand(300, 19, 8, 8, generator=torch.Generator().manual_seed(2)) > 0.8).float()
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        net = PolicyValueNet(cfg, device=dev, precision="fp16", seed=21)
+        p, v = net.forward(x)
+        assert p.device == torch.device(dev)
+        outs.append((p.float().cpu(), v.float().cpu()))
+    for p, v in outs[1:]:
+        assert torch.equal(p, outs[0][0]) and torch.equal(v, outs[0][1])
