@@ -130,3 +130,30 @@ def ptr(t) -> int:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_own_device(cls):
+    """Class decorator: every plain method defined by ``cls`` (no generators, properties or static / class methods) runs with
+    ``self.device`` as the current CUDA device.  The library launches on the caller's current device and stream, so an object that
+    lives on cuda:1 must not depend on the caller having selected cuda:1 -- the reference's workers pick their device by process
+    index (internal.py:120-130) and an orchestrator process may hold objects on several devices."""
+    import functools
+    import inspect
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def run(self, *a, **kw):
+            dev = getattr(self, "device", None)
+            if dev is None:                              # still inside __init__, before the device is known
+                return fn(self, *a, **kw)
+            import torch
+            with torch.cuda.device(dev):
+                return fn(self, *a, **kw)
+        return run
+
+    for name, fn in list(vars(cls).items()):
+        if name in ("__init__", "__del__", "close") or (name.startswith("__") and name.endswith("__")):
+            continue
+        if inspect.isfunction(fn) and not inspect.isgeneratorfunction(fn):
+            setattr(cls, name, wrap(fn))
+    return cls

@@ -18,6 +18,7 @@ from . import _native
 from .selfplay import SelfPlayEngine
 
 
+@_native.on_own_device
 class _TwoEvaluatorGames(SelfPlayEngine):
     def __init__(self, model_a, model_b, *args, **kw):
         super().__init__(model_a, *args, **kw)

@@ -93,7 +93,8 @@ int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, 
     m0_set_error("m0_engine_create: invalid argument");
     return M0_ERR_ARG;
   }
-  M0_CUDA_TRY(cudaSetDevice(device));
+  m0::DeviceGuard device_guard(device);
+  M0_CUDA_TRY(device_guard.err);
   m0_engine* e = new (std::nothrow) m0_engine();
   if (!e) { m0_set_error("m0_engine_create: out of host memory"); return M0_ERR_ARG; }
   e->device = device;
@@ -117,7 +118,7 @@ int m0_engine_create(int device, int max_games, int max_nodes, int tt_capacity, 
 
 int m0_engine_destroy(m0_engine* e) {
   if (!e) return M0_OK;
-  cudaSetDevice(e->device);
+  m0::DeviceGuard device_guard(e->device);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return M0_OK;
@@ -127,7 +128,8 @@ long long m0_engine_bytes(const m0_engine* e) { return e ? (long long)e->bytes :
 
 int m0_engine_configure(m0_engine* e, const m0_search_config* c, void* stream) {
   if (!e || !c || c->cpuct_len <= 0 || !c->cpuct_by_depth) { m0_set_error("m0_engine_configure: invalid argument"); return M0_ERR_ARG; }
-  M0_CUDA_TRY(cudaSetDevice(e->device));
+  m0::DeviceGuard device_guard(e->device);
+  M0_CUDA_TRY(device_guard.err);
   SearchParams p;
   memset(&p, 0, sizeof(p));
   p.fpu_reduction = c->fpu_reduction;
@@ -259,12 +261,14 @@ int m0_search_result(m0_engine* e, uint16_t* d_moves, int32_t* d_visits, double*
 int m0_search_multi_enable(m0_engine* e, int samples_per_batch, int virtual_loss) {
   if (!e || samples_per_batch <= 0 || samples_per_batch > 4096) { m0_set_error("m0_search_multi_enable: invalid argument"); return M0_ERR_ARG; }
   if (virtual_loss && !e->v.node_inflight) {
-    M0_CUDA_TRY(cudaSetDevice(e->device));
+    m0::DeviceGuard device_guard(e->device);
+    M0_CUDA_TRY(device_guard.err);
     TRY(dev_alloc(e, &e->v.node_inflight, (size_t)e->v.G * e->v.max_nodes));
   }
   if (e->v.ml_cap >= samples_per_batch) return M0_OK;
   if (e->v.ml_cap > 0) { m0_set_error("m0_search_multi_enable: already enabled with a smaller batch (%d)", e->v.ml_cap); return M0_ERR_STATE; }
-  M0_CUDA_TRY(cudaSetDevice(e->device));
+  m0::DeviceGuard device_guard(e->device);
+  M0_CUDA_TRY(device_guard.err);
   EngineView& v = e->v;
   const size_t G = v.G, S = G * (size_t)samples_per_batch;
   TRY(dev_alloc(e, &v.ml_n_samples, G));

@@ -27,6 +27,24 @@ int m0_check_cuda(cudaError_t e, const char* what);
 
 namespace m0 {
 
+// Entry points that own device memory (engine / network handles) run on THEIR device and leave the caller's current device as they
+// found it: the host side is PyTorch, which tracks the current device itself (a handle destroyed by the garbage collector inside a
+// `with torch.cuda.device(1)` block must not move the thread to device 0 behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 M0_HD Position load_position(const u64* w) {
   Position p;
   p.pawns = w[0]; p.knights = w[1]; p.bishops = w[2]; p.rooks = w[3]; p.queens = w[4]; p.kings = w[5];

@@ -126,7 +126,8 @@ int m0_net_create(int device, const m0_net_config* cfg, const m0_net_weights* we
     m0_set_error("m0_net_create: unsupported configuration (blocks=%d channels=%d policy=%d)", cfg->blocks, cfg->channels, cfg->policy_size);
     return M0_ERR_ARG;
   }
-  M0_CUDA_TRY(cudaSetDevice(device));
+  m0::DeviceGuard device_guard(device);
+  M0_CUDA_TRY(device_guard.err);
   m0_net* n = new (std::nothrow) m0_net();
   if (!n) { m0_set_error("m0_net_create: out of host memory"); return M0_ERR_ARG; }
   memset(n, 0, sizeof(*n));
@@ -139,7 +140,7 @@ int m0_net_create(int device, const m0_net_config* cfg, const m0_net_weights* we
 
 int m0_net_destroy(m0_net* n) {
   if (!n) return M0_OK;
-  cudaSetDevice(n->device);
+  m0::DeviceGuard device_guard(n->device);
   ws_free(n);
   tc_net_release(n);
   delete n;

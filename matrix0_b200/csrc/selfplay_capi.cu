@@ -67,7 +67,8 @@ extern "C" {
 // selfplay_worker configuration (internal.py:269-381): temperatures, resign rule, game length, opening plies
 int m0_selfplay_configure(m0_engine* e, const m0_selfplay_config* c, void* stream) {
   if (!e || !c) { m0_set_error("m0_selfplay_configure: invalid argument"); return M0_ERR_ARG; }
-  M0_CUDA_TRY(cudaSetDevice(e->device));
+  m0::DeviceGuard device_guard(e->device);
+  M0_CUDA_TRY(device_guard.err);
   TRY(sp_ensure(e));
   SelfPlayParams p;
   memset(&p, 0, sizeof(p));

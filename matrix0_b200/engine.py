@@ -39,6 +39,7 @@ def cpuct_table(cfg, length: int) -> np.ndarray:
     return out
 
 
+@_native.on_own_device
 class SearchEngine:
     def __init__(self, max_games: int, max_nodes: int = 65536, tt_capacity: int = 0, max_depth: int = 256,
                  hist_cap: int = 1024, device: Optional[int] = None):

@@ -83,6 +83,7 @@ def resolve_mcts_config(cfg_dict: Dict[str, Any]) -> MCTSConfig:
     return MCTSConfig.from_dict(m)
 
 
+@_native.on_own_device
 class SelfPlayEngine:
     def __init__(self, model, cfg_dict: Dict[str, Any], games: int = 4096, device: Optional[int] = None, deterministic: bool = False,
                  seed: int = 1234, precision: Optional[str] = None, max_nodes: Optional[int] = None, cuda_graph: bool = True,
@@ -357,9 +358,16 @@ def selfplay_worker(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[
     default writes ``{cfg.data_dir or 'data'}/selfplay/selfplay_w{proc}_g{game}_{ms}.npz`` with ``records.write_game_npz``.
     Returns the number of games written."""
     import torch
+    dev = int(device if device is not None else (proc_id % max(1, torch.cuda.device_count())))
+    with torch.cuda.device(dev):          # everything below (recorder streams, events, page-locked copies) belongs to this device
+        return _selfplay_worker_on_device(proc_id, cfg_dict, ckpt_path, games, q, dev, concurrent_games, precision, data_manager, search_mode)
+
+
+def _selfplay_worker_on_device(proc_id: int, cfg_dict: Dict[str, Any], ckpt_path: Optional[str], games: int, q, dev: int,
+                               concurrent_games: Optional[int], precision: str, data_manager, search_mode: str) -> int:
+    import torch
     from .model import PolicyValueNet
     from .records import GameRecorder, write_game_npz
-    dev = int(device if device is not None else (proc_id % max(1, torch.cuda.device_count())))
     seed = int(cfg_dict.get("seed", 1234)) + int(proc_id)     # internal.py:111-113 seeds by worker
     model = PolicyValueNet.from_config(cfg_dict.get("model", {}), device=f"cuda:{dev}", precision=precision, seed=seed)
     if ckpt_path:

@@ -301,3 +301,54 @@ def test_reloading_weights_invalidates_the_captured_forward_graph(golden_dir):
     assert not torch.equal(lg_new, lg_old)
     sp.play_move()                                                            # and self-play continues on the new weights
     sp.check_status()
+
+
+def test_search_on_a_second_device_of_the_same_process(golden_dir, tmp_path):
+    """Engines on cuda:0 and cuda:1 in ONE process, driven WITHOUT the caller selecting the device (the engine's methods run on their
+    own device, `_native.on_own_device`), the first engine being destroyed while the second is in use (a handle's destructor must
+    leave the thread's current device alone, `DeviceGuard` in csrc/m0_common.cuh): the same deterministic search gives the same visit
+    counts on both devices, and `selfplay_worker(proc_id=1, ...)` -- the reference picks the device from the worker index -- writes
+    its shards from cuda:1.  Skipped on a single-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import gc
+    import queue
+    from matrix0_b200.model import PolicyValueNet
+    from matrix0_b200.selfplay import SelfPlayEngine, selfplay_worker
+    g, cfg_net, sd = load_case(golden_dir, "small")
+    boards = random_playout_boards(4, 60, seed=5)[::7][:16]
+    sims = 200
+    cfg = {"mcts": dict(MCTS_KW, num_simulations=sims), "selfplay": {"num_simulations": sims, "opening_random_plies": 0}}
+    res = []
+    assert torch.cuda.current_device() == 0
+    for dev in (0, 1, 0):
+        net = PolicyValueNet(cfg_net, device=f"cuda:{dev}", precision="fp32")
+        net.load_state_dict(sd, strict=True)
+        sp = SelfPlayEngine(net, cfg, games=len(boards), device=dev, deterministic=True, seed=1, precision="fp32", max_nodes=8192)
+        gc.collect()                                     # the previous iteration's engine and network die here
+        assert torch.cuda.current_device() == 0
+        sp.engine.set_boards(boards)
+        sp.begin_move()
+        for _ in range(sp.batches_per_move()):
+            sp.search_step()
+        sp.engine.result(with_pi=True)
+        st, _ = sp.engine.status()
+        assert int(st.abs().sum()) == 0
+        assert sp.engine.res_visits.device.index == dev and torch.cuda.current_device() == 0
+        res.append((sp.engine.res_count.cpu().numpy(), sp.engine.res_moves.cpu().numpy(), sp.engine.res_visits.cpu().numpy(),
+                    sp.engine.res_pi.cpu().numpy()))
+    assert int(res[0][2].sum()) == len(boards) * sims
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert a.tobytes() == b.tobytes()
+    # the worker entry on the second device
+    ckpt = tmp_path / "ckpt.pt"
+    torch.save({"model": sd}, ckpt)
+    wcfg = {"model": {k: getattr(cfg_net, k) for k in cfg_net.__dataclass_fields__}, "data_dir": str(tmp_path / "data"), "seed": 3,
+            "mcts": dict(MCTS_KW, num_simulations=32, inference_batch_size=16),
+            "selfplay": {"num_simulations": 32, "opening_random_plies": 4, "max_game_len": 8, "temperature_start": 1.0, "temperature_end": 0.3,
+                         "temperature_moves": 40, "resign_threshold": -0.85, "min_resign_plies": 50}}
+    q = queue.Queue()
+    assert selfplay_worker(1, wcfg, str(ckpt), games=6, q=q, concurrent_games=4, precision="fp32") == 6
+    assert torch.cuda.current_device() == 0
+    assert len(sorted((tmp_path / "data" / "selfplay").glob("selfplay_w1_g*.npz"))) == 6
