@@ -10,6 +10,13 @@
  * on the `stream` argument (a cudaStream_t passed as void*).  There is no CPU implementation
  * behind any entry point.
  *
+ * Devices: a handle (m0_engine, m0_net) lives on the device passed to its *_create.  The entry
+ * points that allocate or free (create / destroy / configure / multi_enable) switch to that
+ * device themselves and restore the caller's current device before they return; every other
+ * entry point launches on the CALLER'S current device and `stream`, which must be the handle's
+ * (cudaSetDevice(handle's device) or torch.cuda.device(...) around the call).  Handles of several
+ * devices may coexist in one process.
+ *
  * Each entry point cites the reference interface it replaces (paths relative to the reference).
  */
 #ifndef MATRIX0_B200_H
