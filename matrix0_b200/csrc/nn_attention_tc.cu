@@ -14,6 +14,11 @@
 //   * V fragments come from 32-bit loads + movmatrix.trans instead of 16-bit gathers.
 // Blocks are ordered head-fastest so that the 20 heads of a board (one 1920-byte row of qkv per token) are read
 // by co-scheduled blocks while the lines are still in L2.
+//
+// Two kernels share the arithmetic (attend_head): attention_tc_staged_kernel (the default) brings the next board's q / k / v
+// slice into a per-warp shared-memory buffer with cp.async while the current board is computed; attention_tc_kernel loads the
+// fragments straight from global memory at the top of every board (M0_ATT_STAGED=0, kept for A/B).  Their outputs are
+// bit-identical (tests/test_nn_gpu.py::test_attention_staged_kernel_is_bit_identical_to_direct_loads).
 #include "nn.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
@@ -59,7 +64,7 @@ __device__ __forceinline__ bool attn_mask_tc(int i, int j) {  // resnet.py:105-1
 }
 
 static constexpr int BIAS_LD = 72;          // padded row stride of the staged tables (floats)
-static constexpr int ATT_BOARDS_PER_WARP = 4;
+static constexpr int ATT_BOARDS_PER_WARP = 4;    // direct-load kernel; the staged kernel takes 1..8 as an argument
 static constexpr float LOG2E = 1.4426950408889634f;
 
 // One (board, head): the four 16-row tiles of S = Q K^T, the two softmaxes and O = P V from register-resident fragments
