@@ -1,7 +1,7 @@
 """Agreement of the reduced-precision evaluator paths with the fp32 path on real encoded positions."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np, torch
 from oracle import chess_shim  # noqa
 from oracle.encoding_ref import encode_board, get_legal_actions
@@ -9,7 +9,7 @@ from conftest import random_playout_boards
 from test_oracle_nn import load_case
 from matrix0_b200.model import PolicyValueNet
 
-g, cfg, sd = load_case(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden"), "r24")
+g, cfg, sd = load_case(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden"), "r24")
 N = int(os.environ.get("M0_PROBE_POSITIONS", "512"))
 boards = random_playout_boards(max(20, N // 20), 120, seed=31)[::3][:N]
 x = torch.from_numpy(np.stack([encode_board(b) for b in boards]))

@@ -1,11 +1,11 @@
 """Reduced-precision evaluator paths vs the unmodified reference's fp32 outputs on the REFERENCE'S OWN random init
 (tests/golden/refinit_golden.npz): top-1 agreement, value error, and the logit error against this repo's fp32 CUDA path.
-    python tools/refinit_probe.py [fp16 bf16 ...]  ->  one JSON line per precision"""
+    python tests/probes/refinit_probe.py [fp16 bf16 ...]  ->  one JSON line per precision"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

@@ -9,14 +9,14 @@ replaced by an emulation of what a 16-bit tensor-core kernel would compute, ever
 Both are scored like tests/test_nn_gpu.py::test_refinit_fp16_gate: top-1 agreement with the unmodified reference's fp32 outputs on the
 reference's own random init (tests/golden/refinit_golden.npz), all logits and legal moves only, and max |delta value|.
 
-    python tools/winograd_precision_probe.py [--positions 2304] [--formats fp16,bf16]  ->  one JSON line per (format, mode)
+    python tests/probes/winograd_precision_probe.py [--positions 2304] [--formats fp16,bf16]  ->  one JSON line per (format, mode)
 """
 import argparse
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
