@@ -20,13 +20,17 @@ U64P = ctypes.POINTER(ctypes.c_uint64)
 
 @pytest.fixture(scope="module")
 def hc():
-    so = os.path.join(HC_DIR, "_hostcheck.so")
+    # M0_HOSTCHECK_SANITIZE=1 (tests/hostcheck/run_sanitized.sh): the same harness under AddressSanitizer + UBSan -- the stand-in for
+    # compute-sanitizer (closed on the GPU pool) as far as the code shared by host and device goes
+    sanitize = os.environ.get("M0_HOSTCHECK_SANITIZE", "") == "1"
+    so = os.path.join(HC_DIR, "_hostcheck_san.so" if sanitize else "_hostcheck.so")
     src = os.path.join(HC_DIR, "hostcheck.cpp")
     core = os.path.join(ROOT, "matrix0_b200", "csrc", "chess_core.cuh")
     ssl = os.path.join(ROOT, "matrix0_b200", "csrc", "ssl_core.cuh")
     mg = os.path.join(ROOT, "matrix0_b200", "csrc", "movegen_warp.cuh")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(ssl), os.path.getmtime(mg)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+        flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"] if sanitize else ["-O2"]
+        subprocess.check_call(["g++", *flags, "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     return ctypes.CDLL(so)
 
 
