@@ -75,9 +75,10 @@ M0_HD float np_pairwise_sum_rec(const float* a, int n) {
 }
 template <>
 M0_HD float np_pairwise_sum_rec<0>(const float* a, int n) { return np_pairwise_block_f32(a, n); }
-// valid for n <= 1024 (three halvings); legal-move lists have n <= 256
+// three halvings: exact while every part is <= 128 after them -- the larger half of n is n - (n/2 - (n/2) % 8) <= n/2 + 8, so any
+// n <= 900 (and n = 1024) qualifies; legal-move lists have n <= 256 (tests/test_hostcheck.py checks every length up to 300)
 M0_HD float np_pairwise_sum_f32(const float* a, int n) { return np_pairwise_sum_rec<3>(a, n); }
-// valid for n <= 8192 (six halvings): the whole 4672-entry policy vector
+// six halvings: any n <= 7000 (and n = 8192) by the same bound -- the whole 4672-entry policy vector
 M0_HD float np_pairwise_sum_f32_big(const float* a, int n) { return np_pairwise_sum_rec<6>(a, n); }
 
 // the same reduction for float64 arrays (DOUBLE_pairwise_sum): `dist.sum()` at azchess/mcts.py:184 after the float64 noise was added

@@ -5,6 +5,7 @@
 #include "../../matrix0_b200/csrc/chess_core.cuh"
 #include "../../matrix0_b200/csrc/ssl_core.cuh"
 #include "../../matrix0_b200/csrc/movegen_warp.cuh"
+#include "../../matrix0_b200/csrc/search_math.cuh"
 #include <string.h>
 using namespace m0;
 
@@ -193,4 +194,15 @@ long hc_legal_set_sweep(const uint64_t* start9, uint64_t seed, int games, int ma
   }
   return seen;
 }
+}
+
+// csrc/search_math.cuh: the single-rounding arithmetic of the search (numpy's pairwise sums, the PUCT score, repeated backups)
+extern "C" {
+float hc_pairwise_f32(const float* a, int n, int big) { return big ? np_pairwise_sum_f32_big(a, n) : np_pairwise_sum_f32(a, n); }
+double hc_pairwise_f64(const double* a, int n, int big) { return big ? np_pairwise_sum_f64_big(a, n) : np_pairwise_sum_f64(a, n); }
+double hc_puct_score(double q, double cpuct, double prior, double sqrt_parent_visits, int child_n) {
+  return puct_score(q, cpuct, prior, sqrt_parent_visits, child_n);
+}
+void hc_backup_repeated(int* n, double* w, double* q, double v, int times) { backup_repeated(*n, *w, *q, v, times); }
+double hc_clip_unit(double x) { return py_clip_unit(x); }
 }

@@ -28,7 +28,8 @@ def hc():
     core = os.path.join(ROOT, "matrix0_b200", "csrc", "chess_core.cuh")
     ssl = os.path.join(ROOT, "matrix0_b200", "csrc", "ssl_core.cuh")
     mg = os.path.join(ROOT, "matrix0_b200", "csrc", "movegen_warp.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(ssl), os.path.getmtime(mg)):
+    sm = os.path.join(ROOT, "matrix0_b200", "csrc", "search_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in (src, core, ssl, mg, sm)):
         flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"] if sanitize else ["-O2"]
         subprocess.check_call(["g++", *flags, "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
     return ctypes.CDLL(so)
@@ -181,3 +182,54 @@ def test_warp_ordered_generator_matches_python_chess_order(hc, golden_dir):
         n1 = hc.hc_legal_moves_warp(pos[i].ctypes.data_as(U64P), a.ctypes.data_as(u16p), ctypes.byref(chk))
         n2 = hc.hc_legal_moves(pos[i].ctypes.data_as(U64P), bb.ctypes.data_as(u16p), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
         assert n1 == n2 and (a[:n1] == bb[:n1]).all(), i
+
+
+def test_search_math_is_numpy_and_python_arithmetic(hc):
+    """csrc/search_math.cuh on the host (-ffp-contract=off, like the *_rn intrinsics on the device): numpy's pairwise float32 / float64
+    `sum()` (mcts.py:206 `lp / lp.sum()`, :184 `dist.sum()`) bit for bit at every length the search meets (legal-move lists of 1 ... 300
+    entries and a few longer ones, the whole 4,672-entry policy), the PUCT score and the repeated backup against the reference's Python expressions
+    (mcts.py:878-881, :946-953), and Python's min / max clamp (:948) including its NaN behaviour."""
+    import math
+    import struct
+    rng = np.random.default_rng(5)
+    f32p, f64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    hc.hc_pairwise_f32.restype = ctypes.c_float
+    hc.hc_pairwise_f64.restype = ctypes.c_double
+    hc.hc_puct_score.restype = ctypes.c_double
+    hc.hc_clip_unit.restype = ctypes.c_double
+    bits32 = lambda x: struct.pack("<f", x)
+    bits64 = lambda x: struct.pack("<d", x)
+    lengths = list(range(1, 301)) + [511, 512, 513, 777, 900, 1024]
+    for n in lengths:
+        for scale in (1.0, 1e-3):
+            a = (rng.random(n, dtype=np.float32) * np.float32(scale)).astype(np.float32)
+            a[rng.integers(0, n)] *= np.float32(37.5)
+            assert bits32(hc.hc_pairwise_f32(a.ctypes.data_as(f32p), n, 0)) == bits32(float(np.add.reduce(a))), n
+            d = a.astype(np.float64) + rng.normal(0, 0.1, n)
+            assert bits64(hc.hc_pairwise_f64(d.ctypes.data_as(f64p), n, 0)) == bits64(float(np.add.reduce(d))), n
+    for n in (1023, 1025, 2048, 4672, 7000, 8192):
+        a = rng.random(n, dtype=np.float32)
+        assert bits32(hc.hc_pairwise_f32(a.ctypes.data_as(f32p), n, 1)) == bits32(float(a.sum())), n
+        d = rng.normal(0, 1, n)
+        assert bits64(hc.hc_pairwise_f64(d.ctypes.data_as(f64p), n, 1)) == bits64(float(d.sum())), n
+    for _ in range(2000):
+        q, cpuct, prior = float(rng.uniform(-1, 1)), float(rng.uniform(0.5, 4.0)), float(np.float32(rng.random()))
+        parent, child_n = int(rng.integers(1, 100000)), int(rng.integers(0, 5000))
+        sq = math.sqrt(parent)
+        exp = q + cpuct * prior * (sq / (1.0 + child_n))                     # mcts.py:878-881
+        got = hc.hc_puct_score(ctypes.c_double(q), ctypes.c_double(cpuct), ctypes.c_double(prior), ctypes.c_double(sq), child_n)
+        assert bits64(got) == bits64(exp)
+    for _ in range(300):
+        n0, w0, v, times = int(rng.integers(0, 1000)), float(rng.uniform(-50, 50)), float(rng.uniform(-1, 1)), int(rng.integers(1, 97))
+        n, w, q = ctypes.c_int(n0), ctypes.c_double(w0), ctypes.c_double(0.0)
+        hc.hc_backup_repeated(ctypes.byref(n), ctypes.byref(w), ctypes.byref(q), ctypes.c_double(v), times)
+        en, ew = n0, w0
+        for _k in range(times):                                              # mcts.py:946-953, one sample at a time
+            en += 1
+            ew += v
+            eq = ew / en
+        assert n.value == en and bits64(w.value) == bits64(ew) and bits64(q.value) == bits64(eq)
+    for x in (0.3, -0.3, 1.0, -1.0, 1.5, -7.0, float("inf"), float("-inf"), float("nan"), -0.0):
+        exp = max(-1.0, min(1.0, x))                                         # mcts.py:948
+        got = hc.hc_clip_unit(ctypes.c_double(x))
+        assert (math.isnan(exp) and math.isnan(got)) or bits64(got) == bits64(exp), x
